@@ -1,0 +1,688 @@
+// brov_api.cu — the C ABI of libbrov.so (include/brov.h): engine handle, host-side constant preparation in extended
+// precision (mass matrix inverse, Coriolis coefficient differences, thruster allocation from the reference's
+// geometry formula, zero-order-hold discretisation of the thruster lag and its closed form over the sub-steps of an
+// integrator step), argument validation, kernel launches, and the host-buffer streaming rollout.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/brov.h"
+#include "brov_kernels.cuh"
+
+using namespace brov;
+
+static_assert(BROV_NKP == KP_COUNT, "coefficient vector length");
+static_assert(BROV_MAX_H == MAX_H, "horizon count");
+
+// ---------------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return fail(BROV_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" const char* brov_last_error(void) { return g_err; }
+extern "C" int brov_abi_version(void) { return BROV_ABI_VERSION; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// engine
+// ---------------------------------------------------------------------------------------------------------------
+struct LagDisc {
+    double dt;
+    double Ad[9];
+    double Bd[3];
+};
+
+struct HostStage {  // resources of brov_rollout_host, grown on demand
+    void* d_x = nullptr;
+    void* d_lag = nullptr;
+    void* d_u[2] = {nullptr, nullptr};
+    void* d_traj[2] = {nullptr, nullptr};
+    size_t cap_x = 0, cap_lag = 0, cap_u = 0, cap_traj = 0;
+    cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool ready = false;
+};
+
+struct brov_engine {
+    int model, dtype, device;
+    double kp[KP_COUNT];
+    double alloc[6][8];
+    int use_lag1;
+    const void* pv;
+    long long pv_n;
+    std::vector<LagDisc> lag_overrides;
+    LagDisc lag_cache;
+    HostStage hs;
+};
+
+static const double LAG_AC[9] = {-89.0, -72.33, -26.54, 128.0, 0.0, 0.0, 0.0, 32.0, 0.0};  // fossen/BlueROV2.py:476-478
+static const double LAG_BC[3] = {8.0, 0.0, 0.0};                                             // :479
+static const double LAG_CC[3] = {0.0, 5.992, 3.317};                                         // :480
+
+static int model_nx(int m) { return m == BROV_WRENCH_QUAT13 ? 13 : 12; }
+static int model_nu(int m) { return m == BROV_THRUSTER8_LAG3 ? 8 : 6; }
+static int model_nlag(const brov_engine* e) {
+    return e->model == BROV_THRUSTER8_LAG3 ? 24 : (e->use_lag1 ? 6 : 0);
+}
+static size_t scalar_size(int dtype) { return dtype == BROV_F32 ? 4 : 8; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// constants
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int brov_default_physical(double rho, double* ph) {
+    if (!ph) return fail(BROV_EINVAL, "phys is NULL");
+    const double g = 9.82, m = 13.5, vol = 0.0134;
+    ph[BROV_PH_M] = m;
+    ph[BROV_PH_W] = m * g;
+    ph[BROV_PH_B] = rho * g * vol;
+    ph[BROV_PH_XB + 0] = 0.0; ph[BROV_PH_XB + 1] = 0.0; ph[BROV_PH_XB + 2] = -0.01;
+    ph[BROV_PH_I + 0] = 0.26; ph[BROV_PH_I + 1] = 0.23; ph[BROV_PH_I + 2] = 0.37;
+    const double added[6] = {-6.36, -7.12, -18.68, -0.189, -0.135, -0.222};
+    const double lin[6] = {-13.7, -0.0, -33.0, -0.0, -0.8, -0.0};
+    const double quad[6] = {-141.0, -217.0, -190.0, -1.19, -0.47, -1.5};
+    for (int i = 0; i < 6; ++i) {
+        ph[BROV_PH_ADDED + i] = added[i];
+        ph[BROV_PH_LIN + i] = lin[i];
+        ph[BROV_PH_QUAD + i] = quad[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        ph[BROV_PH_MINV + i] = 1.0 / (m - added[i]);
+        ph[BROV_PH_MINV + 3 + i] = 1.0 / (ph[BROV_PH_I + i] - added[3 + i]);
+        ph[BROV_PH_CURRENT + i] = 0.0;
+    }
+    ph[BROV_PH_TLAG1] = 0.0;
+    return BROV_OK;
+}
+
+extern "C" int brov_derive_params(const double* ph, double* kp) {
+    if (!ph || !kp) return fail(BROV_EINVAL, "NULL argument");
+    const double m = ph[BROV_PH_M];
+    double a[3], b[3];
+    for (int i = 0; i < 3; ++i) {
+        a[i] = m - ph[BROV_PH_ADDED + i];
+        b[i] = ph[BROV_PH_I + i] - ph[BROV_PH_ADDED + 3 + i];
+    }
+    for (int i = 0; i < 6; ++i) kp[KP_MINV + i] = ph[BROV_PH_MINV + i];
+    for (int i = 0; i < 3; ++i) kp[KP_A + i] = a[i];
+    kp[KP_DA + 0] = a[2] - a[1]; kp[KP_DA + 1] = a[0] - a[2]; kp[KP_DA + 2] = a[1] - a[0];
+    kp[KP_DB + 0] = b[2] - b[1]; kp[KP_DB + 1] = b[0] - b[2]; kp[KP_DB + 2] = b[1] - b[0];
+    for (int i = 0; i < 6; ++i) {
+        kp[KP_DL + i] = -ph[BROV_PH_LIN + i];
+        kp[KP_DQ + i] = -ph[BROV_PH_QUAD + i];
+    }
+    kp[KP_WMB] = ph[BROV_PH_W] - ph[BROV_PH_B];
+    for (int i = 0; i < 3; ++i) {
+        kp[KP_XBB + i] = ph[BROV_PH_XB + i] * ph[BROV_PH_B];
+        kp[KP_CUR + i] = ph[BROV_PH_CURRENT + i];
+    }
+    kp[KP_ILAG1] = ph[BROV_PH_TLAG1] > 0.0 ? 1.0 / ph[BROV_PH_TLAG1] : 0.0;
+    kp[KP_ILAG1 + 1] = 0.0;
+    return BROV_OK;
+}
+
+// Thruster geometry: r_i = Rz(alpha_i) r_base, e_i = Rz(beta_i) e_base with the paper's rounded placement angles
+// (fossen/BlueROV2.py:172-232; never symmetrised, SURVEY trap T6); column i of the allocation is [e_i; r_i x e_i].
+extern "C" int brov_default_allocation(double* alloc, double* r_out, double* dir_out) {
+    const double PI = 3.141592653589793;
+    const double r_h[3] = {0.156, 0.111, 0.085}, r_v[3] = {0.12, 0.218, 0.0};
+    const double s2 = 1.0 / std::sqrt(2.0);
+    const double e_h[3] = {s2, -s2, 0.0};
+    const double ang_r[8] = {0.0, 5.05, 1.91, PI, 0.0, 4.15, 1.01, PI};
+    const double ang_e[4] = {0.0, PI / 2, 3 * PI / 2, PI};
+    for (int i = 0; i < 8; ++i) {
+        const double* rb = i < 4 ? r_h : r_v;
+        double c = std::cos(ang_r[i]), s = std::sin(ang_r[i]);
+        double r[3] = {c * rb[0] - s * rb[1], s * rb[0] + c * rb[1], rb[2]};
+        double e[3];
+        if (i < 4) {
+            double ce = std::cos(ang_e[i]), se = std::sin(ang_e[i]);
+            e[0] = ce * e_h[0] - se * e_h[1];
+            e[1] = se * e_h[0] + ce * e_h[1];
+            e[2] = e_h[2];
+        } else {
+            e[0] = 0.0; e[1] = 0.0; e[2] = -1.0;
+        }
+        if (alloc) {
+            alloc[0 * 8 + i] = e[0];
+            alloc[1 * 8 + i] = e[1];
+            alloc[2 * 8 + i] = e[2];
+            alloc[3 * 8 + i] = r[1] * e[2] - r[2] * e[1];
+            alloc[4 * 8 + i] = r[2] * e[0] - r[0] * e[2];
+            alloc[5 * 8 + i] = r[0] * e[1] - r[1] * e[0];
+        }
+        for (int j = 0; j < 3; ++j) {
+            if (r_out) r_out[3 * i + j] = r[j];
+            if (dir_out) dir_out[3 * i + j] = e[j];
+        }
+    }
+    return BROV_OK;
+}
+
+// exp([[A, B], [0, 0]] dt) by scaling and squaring of a Taylor series in long double: (Ad, Bd) of the zero-order hold,
+// i.e. what scipy.signal.cont2discrete(method='zoh') returns at fossen/BlueROV2.py:494-495.
+extern "C" int brov_lag_discretize(double dt, double* Ad, double* Bd) {
+    if (!Ad || !Bd || !(dt > 0.0) || !std::isfinite(dt)) return fail(BROV_EINVAL, "brov_lag_discretize: bad dt or NULL output");
+    typedef long double ld;
+    ld M[4][4] = {{0}};
+    ld nrm = 0;
+    for (int i = 0; i < 3; ++i) {
+        ld row = 0;
+        for (int j = 0; j < 3; ++j) { M[i][j] = (ld)LAG_AC[3 * i + j] * (ld)dt; row += fabsl(M[i][j]); }
+        M[i][3] = (ld)LAG_BC[i] * (ld)dt;
+        row += fabsl(M[i][3]);
+        if (row > nrm) nrm = row;
+    }
+    int s = 0;
+    while (nrm > 0.0625L) { nrm *= 0.5L; ++s; }
+    ld scale = ldexpl(1.0L, -s);
+    for (auto& row : M) for (auto& v : row) v *= scale;
+    ld E[4][4], term[4][4], tmp[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) E[i][j] = term[i][j] = (i == j) ? 1.0L : 0.0L;
+    for (int k = 1; k <= 24; ++k) {
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+            ld v = 0;
+            for (int q = 0; q < 4; ++q) v += term[i][q] * M[q][j];
+            tmp[i][j] = v / (ld)k;
+        }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { term[i][j] = tmp[i][j]; E[i][j] += tmp[i][j]; }
+    }
+    for (int q = 0; q < s; ++q) {
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) {
+            ld v = 0;
+            for (int r = 0; r < 4; ++r) v += E[i][r] * E[r][j];
+            tmp[i][j] = v;
+        }
+        memcpy(E, tmp, sizeof(E));
+    }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Ad[3 * i + j] = (double)E[i][j];
+        Bd[i] = (double)E[i][3];
+    }
+    return BROV_OK;
+}
+
+static const LagDisc* lag_for_dt(brov_engine* e, double dt) {
+    for (const auto& o : e->lag_overrides)
+        if (o.dt == dt) return &o;
+    if (e->lag_cache.dt != dt) {
+        if (brov_lag_discretize(dt, e->lag_cache.Ad, e->lag_cache.Bd) != BROV_OK) return nullptr;
+        e->lag_cache.dt = dt;
+    }
+    return &e->lag_cache;
+}
+
+template <typename T>
+static int make_consts(brov_engine* e, double dt, int nsub, Consts<T>* c) {
+    memset(c, 0, sizeof(*c));
+    for (int i = 0; i < KP_COUNT; ++i) c->kp[i] = (T)e->kp[i];
+    for (int r = 0; r < 6; ++r) for (int i = 0; i < 8; ++i) c->alloc[r][i] = (T)e->alloc[r][i];
+    c->dt = (T)dt;
+    c->has_current = (e->kp[KP_CUR] != 0.0 || e->kp[KP_CUR + 1] != 0.0 || e->kp[KP_CUR + 2] != 0.0 || e->pv != nullptr) ? 1 : 0;
+    c->use_lag1 = e->use_lag1;
+    if (e->model == BROV_THRUSTER8_LAG3) {
+        const LagDisc* d = lag_for_dt(e, dt);
+        if (!d) return BROV_EINVAL;
+        typedef long double ld;
+        ld P[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, S[3][3] = {{0}}, tmp[3][3];
+        for (int j = 0; j < nsub; ++j) {
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) S[a][b] += P[a][b];       // S_{j+1}
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) {                          // P = Ad^{j+1}
+                ld v = 0;
+                for (int q = 0; q < 3; ++q) v += P[a][q] * (ld)d->Ad[3 * q + b];
+                tmp[a][b] = v;
+            }
+            memcpy(P, tmp, sizeof(P));
+            ld h = 0;
+            for (int b = 0; b < 3; ++b) {
+                ld g = 0, sb = 0;
+                for (int a = 0; a < 3; ++a) g += (ld)LAG_CC[a] * P[a][b];
+                c->lagG[j][b] = (T)(double)g;
+                for (int q = 0; q < 3; ++q) sb += S[b][q] * (ld)d->Bd[q];
+                h += (ld)LAG_CC[b] * sb;
+            }
+            c->lagH[j] = (T)(double)h;
+        }
+        for (int a = 0; a < 3; ++a) {
+            ld sb = 0;
+            for (int b = 0; b < 3; ++b) { c->lagA[a][b] = (T)(double)P[a][b]; sb += S[a][b] * (ld)d->Bd[b]; }
+            c->lagB[a] = (T)(double)sb;
+        }
+    }
+    return BROV_OK;
+}
+
+extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out) {
+    if (!out) return fail(BROV_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (model < 0 || model > 2) return fail(BROV_EINVAL, "unknown model %d", model);
+    if (dtype != BROV_F64 && dtype != BROV_F32) return fail(BROV_EINVAL, "unknown dtype %d", dtype);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(BROV_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(BROV_EUNSUPPORTED, "libbrov is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    brov_engine* e = new (std::nothrow) brov_engine();
+    if (!e) return fail(BROV_ENOMEM, "out of host memory");
+    e->model = model; e->dtype = dtype; e->device = device;
+    e->use_lag1 = 0; e->pv = nullptr; e->pv_n = 0;
+    e->lag_cache.dt = -1.0;
+    double ph[BROV_NPHYS];
+    brov_default_physical(1000.0, ph);
+    brov_derive_params(ph, e->kp);
+    brov_default_allocation(&e->alloc[0][0], nullptr, nullptr);
+    *out = e;
+    return BROV_OK;
+}
+
+static void hs_release(brov_engine* e) {
+    HostStage& h = e->hs;
+    cudaSetDevice(e->device);
+    cudaFree(h.d_x); cudaFree(h.d_lag);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(h.d_u[b]); cudaFree(h.d_traj[b]);
+        if (h.ev_in[b]) cudaEventDestroy(h.ev_in[b]);
+        if (h.ev_done[b]) cudaEventDestroy(h.ev_done[b]);
+        if (h.ev_out[b]) cudaEventDestroy(h.ev_out[b]);
+    }
+    if (h.s_compute) cudaStreamDestroy(h.s_compute);
+    if (h.s_in) cudaStreamDestroy(h.s_in);
+    if (h.s_out) cudaStreamDestroy(h.s_out);
+    h = HostStage();
+}
+
+extern "C" void brov_destroy(brov_engine_t* e) {
+    if (!e) return;
+    hs_release(e);
+    delete e;
+}
+
+extern "C" int brov_set_params(brov_engine_t* e, const double* kp) {
+    if (!e || !kp) return fail(BROV_EINVAL, "NULL argument");
+    for (int i = 0; i < KP_COUNT; ++i) {
+        if (!std::isfinite(kp[i])) return fail(BROV_EINVAL, "coefficient %d is not finite", i);
+        e->kp[i] = kp[i];
+    }
+    return BROV_OK;
+}
+extern "C" int brov_get_params(const brov_engine_t* e, double* kp) {
+    if (!e || !kp) return fail(BROV_EINVAL, "NULL argument");
+    memcpy(kp, e->kp, sizeof(e->kp));
+    return BROV_OK;
+}
+extern "C" int brov_set_allocation(brov_engine_t* e, const double* alloc) {
+    if (!e || !alloc) return fail(BROV_EINVAL, "NULL argument");
+    // the kernel skips the structural zeros of the BlueROV2 heavy layout (4 horizontal + 4 vertical thrusters)
+    for (int r = 0; r < 6; ++r)
+        for (int i = 0; i < 8; ++i) {
+            const bool nz = (r < 2) ? (i < 4) : (r == 2) ? (i >= 4) : (r == 5) ? (i < 4) : true;
+            if (!nz && alloc[r * 8 + i] != 0.0)
+                return fail(BROV_EUNSUPPORTED, "allocation[%d][%d] must be zero (horizontal thrusters 0-3 act in x,y,N; vertical 4-7 in z)", r, i);
+        }
+    memcpy(e->alloc, alloc, sizeof(e->alloc));
+    return BROV_OK;
+}
+extern "C" int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (kp_soa_dev && n <= 0) return fail(BROV_EINVAL, "vehicle table with n = %lld", n);
+    e->pv = kp_soa_dev;
+    e->pv_n = kp_soa_dev ? n : 0;
+    return BROV_OK;
+}
+extern "C" int brov_set_wrench_lag1(brov_engine_t* e, int enable) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (enable && e->model == BROV_THRUSTER8_LAG3)
+        return fail(BROV_EUNSUPPORTED, "the first-order wrench lag applies to the wrench-input models only");
+    e->use_lag1 = enable ? 1 : 0;
+    return BROV_OK;
+}
+extern "C" int brov_set_lag_discrete(brov_engine_t* e, double dt, const double* Ad, const double* Bd) {
+    if (!e || !Ad || !Bd) return fail(BROV_EINVAL, "NULL argument");
+    LagDisc d;
+    d.dt = dt;
+    memcpy(d.Ad, Ad, sizeof(d.Ad));
+    memcpy(d.Bd, Bd, sizeof(d.Bd));
+    for (auto& o : e->lag_overrides)
+        if (o.dt == dt) { o = d; return BROV_OK; }
+    e->lag_overrides.push_back(d);
+    return BROV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// device entry points
+// ---------------------------------------------------------------------------------------------------------------
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+template <typename T>
+static int rhs_impl(brov_engine* e, long long n, const void* x, const void* u, void* lag, double dt, void* xdot, cudaStream_t st) {
+    RhsArgs<T> a;
+    int rc = make_consts<T>(e, dt, 1, &a.c);
+    if (rc) return rc;
+    a.x = (const T*)x; a.u = (const T*)u; a.lag = (T*)lag; a.pv = (const T*)e->pv; a.xdot = (T*)xdot; a.n = (int)n;
+    CUDA_TRY(launch_rhs<T>(e->model, e->use_lag1 != 0, a, st));
+    return BROV_OK;
+}
+
+extern "C" int brov_rhs(brov_engine_t* e, long long n, const void* x, const void* u, void* lag, double dt, void* xdot, void* stream) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (n < 0 || n > 0x7fffffffLL) return fail(BROV_EINVAL, "n = %lld out of range", n);
+    if (n == 0) return BROV_OK;
+    if (!x || !u || !xdot) return fail(BROV_EINVAL, "x, u and xdot must not be NULL");
+    if (e->model == BROV_THRUSTER8_LAG3 && !(dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0 (it fixes the lag discretisation)");
+    if (e->pv && e->pv_n != n) return fail(BROV_EINVAL, "vehicle table has %lld rows, call has n = %lld", e->pv_n, n);
+    CUDA_TRY(cudaSetDevice(e->device));
+    return e->dtype == BROV_F32 ? rhs_impl<float>(e, n, x, u, lag, dt, xdot, (cudaStream_t)stream)
+                                : rhs_impl<double>(e, n, x, u, lag, dt, xdot, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int thruster_impl(brov_engine* e, long long n, const void* u, void* lag, double dt, void* tau, cudaStream_t st) {
+    ThrusterArgs<T> a;
+    int rc = make_consts<T>(e, dt, 1, &a.c);
+    if (rc) return rc;
+    a.u = (const T*)u; a.lag = (T*)lag; a.tau = (T*)tau; a.n = (int)n;
+    CUDA_TRY(launch_thruster_wrench<T>(a, st));
+    return BROV_OK;
+}
+
+extern "C" int brov_thruster_wrench(brov_engine_t* e, long long n, const void* u, void* lag, double dt, void* tau, void* stream) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (e->model != BROV_THRUSTER8_LAG3) return fail(BROV_EUNSUPPORTED, "brov_thruster_wrench needs a BROV_THRUSTER8_LAG3 engine");
+    if (n < 0 || n > 0x7fffffffLL) return fail(BROV_EINVAL, "n = %lld out of range", n);
+    if (n == 0) return BROV_OK;
+    if (!u || !tau) return fail(BROV_EINVAL, "u and tau must not be NULL");
+    if (!(dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
+    CUDA_TRY(cudaSetDevice(e->device));
+    return e->dtype == BROV_F32 ? thruster_impl<float>(e, n, u, lag, dt, tau, (cudaStream_t)stream)
+                                : thruster_impl<double>(e, n, u, lag, dt, tau, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t st) {
+    const int NX = model_nx(e->model), NU = model_nu(e->model);
+    RolloutArgs<T> a;
+    int rc = make_consts<T>(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &a.c);
+    if (rc) return rc;
+    a.x0 = (const T*)d->x0_dev; a.xT = (T*)d->xT_dev; a.U = (const T*)d->u_dev;
+    a.u_stride_t = d->u_stride_t; a.u_stride_n = d->u_stride_n;
+    a.lag_in = (const T*)d->lag_in_dev; a.lag_out = (T*)d->lag_out_dev;
+    a.pv = (const T*)e->pv;
+    a.traj = (T*)d->traj_dev;
+    a.snap_base = d->snap_base; a.step0 = d->step0;
+    a.n = (int)d->n; a.steps = (int)d->steps; a.stride = (int)(d->traj_dev ? d->stride : 1);
+    const size_t ualign = (sizeof(T) == 4 && NU == 6) ? 8 : 16;
+    a.u_vec = aligned(d->u_dev, ualign) && (d->u_stride_t * sizeof(T)) % ualign == 0 && (d->u_stride_n * sizeof(T)) % ualign == 0;
+    a.traj_vec = d->traj_dev && aligned(d->traj_dev, 16) && ((size_t)d->n * NX * sizeof(T)) % 16 == 0;
+    CUDA_TRY(launch_rollout<T>(e->model, d->integrator, e->use_lag1 != 0, a, st));
+    return BROV_OK;
+}
+
+static int check_rollout_common(brov_engine* e, int integrator, long long n, long long steps, double dt) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (integrator != BROV_RK4 && integrator != BROV_EULER) return fail(BROV_EINVAL, "unknown integrator %d", integrator);
+    if (n < 0 || n > 0x7fffffffLL) return fail(BROV_EINVAL, "n = %lld out of range", n);
+    if (steps < 0 || steps > 0x7fffffffLL) return fail(BROV_EINVAL, "steps = %lld out of range", steps);
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(BROV_EINVAL, "dt must be a positive finite number");
+    if (e->pv && e->pv_n != n) return fail(BROV_EINVAL, "vehicle table has %lld rows, call has n = %lld", e->pv_n, n);
+    return BROV_OK;
+}
+
+extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* stream) {
+    if (!d || d->struct_size != sizeof(brov_rollout_desc)) return fail(BROV_EINVAL, "brov_rollout_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
+    int rc = check_rollout_common(e, d->integrator, d->n, d->steps, d->dt);
+    if (rc) return rc;
+    if (d->n == 0) return BROV_OK;
+    if (!d->x0_dev || !d->xT_dev) return fail(BROV_EINVAL, "x0 and xT must not be NULL");
+    if (d->steps > 0 && !d->u_dev) return fail(BROV_EINVAL, "u is NULL");
+    if (d->u_stride_t < 0 || d->u_stride_n < 0) return fail(BROV_EINVAL, "negative input stride");
+    if (d->traj_dev && d->stride < 1) return fail(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
+    if (d->traj_dev && (d->step0 < 0 || d->step0 / d->stride < d->snap_base)) return fail(BROV_EINVAL, "snap_base lies after the first snapshot of this call");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (d->steps == 0) {
+        const size_t sz = scalar_size(e->dtype);
+        if (d->xT_dev != d->x0_dev)
+            CUDA_TRY(cudaMemcpyAsync(d->xT_dev, d->x0_dev, (size_t)d->n * model_nx(e->model) * sz, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        if (d->lag_out_dev && model_nlag(e)) {
+            const size_t lb = (size_t)d->n * model_nlag(e) * sz;
+            if (d->lag_in_dev) { if (d->lag_in_dev != d->lag_out_dev) CUDA_TRY(cudaMemcpyAsync(d->lag_out_dev, d->lag_in_dev, lb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); }
+            else CUDA_TRY(cudaMemsetAsync(d->lag_out_dev, 0, lb, (cudaStream_t)stream));
+        }
+        return BROV_OK;
+    }
+    return e->dtype == BROV_F32 ? rollout_impl<float>(e, d, (cudaStream_t)stream) : rollout_impl<double>(e, d, (cudaStream_t)stream);
+}
+
+extern "C" size_t brov_se_workspace_bytes(long long n_windows) {
+    if (n_windows < 1) n_windows = 1;
+    return (size_t)((n_windows + SE_BLOCK - 1) / SE_BLOCK) * MAX_H * sizeof(double);
+}
+
+template <typename T>
+static int se_impl(brov_engine* e, const brov_se_desc* d, cudaStream_t st) {
+    SeArgs<T> a;
+    int rc = make_consts<T>(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &a.c);
+    if (rc) return rc;
+    a.X = (const T*)d->X_dev; a.U = (const T*)d->U_dev; a.lag0 = (const T*)d->lag0_dev;
+    a.partial = (double*)d->workspace_dev;
+    a.rows = (int)d->rows; a.nwin = (int)d->n_windows; a.nH = d->n_horizons;
+    for (int h = 0; h < MAX_H; ++h) a.H[h] = h < d->n_horizons ? d->horizons[h] : 0x7fffffff;
+    const int nblocks = (int)((d->n_windows + SE_BLOCK - 1) / SE_BLOCK);
+    CUDA_TRY(launch_se<T>(e->model, d->integrator, a, nblocks, d->se_out_dev, st));
+    return BROV_OK;
+}
+
+extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* stream) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (!d || d->struct_size != sizeof(brov_se_desc)) return fail(BROV_EINVAL, "brov_se_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
+    if (d->integrator != BROV_RK4 && d->integrator != BROV_EULER) return fail(BROV_EINVAL, "unknown integrator %d", d->integrator);
+    if (e->use_lag1) return fail(BROV_EUNSUPPORTED, "the evaluator does not support the first-order wrench lag");
+    if (e->pv) return fail(BROV_EUNSUPPORTED, "the evaluator scores one vehicle; clear the per-vehicle table first");
+    if (d->n_horizons < 1 || d->n_horizons > MAX_H) return fail(BROV_EINVAL, "n_horizons must be 1..%d", MAX_H);
+    for (int h = 0; h < d->n_horizons; ++h)
+        if (d->horizons[h] < 1 || (h && d->horizons[h] <= d->horizons[h - 1])) return fail(BROV_EINVAL, "horizons must be >= 1 and strictly ascending");
+    if (d->rows < 0 || d->rows > 0x7fffffffLL || d->n_windows < 0 || d->n_windows > d->rows) return fail(BROV_EINVAL, "rows / n_windows out of range");
+    if (!(d->dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
+    if (!d->se_out_dev) return fail(BROV_EINVAL, "se_out is NULL");
+    CUDA_TRY(cudaSetDevice(e->device));
+    for (int h = 0; h < MAX_H; ++h) {
+        long long cnt = 0;
+        if (h < d->n_horizons) {
+            cnt = d->rows - d->horizons[h];
+            if (cnt > d->n_windows) cnt = d->n_windows;
+            if (cnt < 0) cnt = 0;
+        }
+        if (d->count_out) d->count_out[h] = cnt;
+    }
+    if (d->n_windows == 0 || d->rows < 2) {
+        CUDA_TRY(cudaMemsetAsync(d->se_out_dev, 0, MAX_H * sizeof(double), (cudaStream_t)stream));
+        return BROV_OK;
+    }
+    if (!d->X_dev || !d->U_dev) return fail(BROV_EINVAL, "X and U must not be NULL");
+    if (!d->workspace_dev || d->workspace_bytes < brov_se_workspace_bytes(d->n_windows)) return fail(BROV_EINVAL, "workspace too small: need %zu bytes", brov_se_workspace_bytes(d->n_windows));
+    return e->dtype == BROV_F32 ? se_impl<float>(e, d, (cudaStream_t)stream) : se_impl<double>(e, d, (cudaStream_t)stream);
+}
+
+// fossen/parameters.py:3-33
+template <typename T> static Red9Consts<T> red9_consts() {
+    const double m = 11.4, g = 9.82, F_bouy = 1026 * 0.0115 * g;
+    const double X_ud = -2.6, Y_vd = -18.5, Z_wd = -13.3, N_rd = -0.28, I_zz = 0.245;
+    Red9Consts<T> c;
+    c.im_u = (T)(1.0 / (m - X_ud)); c.im_v = (T)(1.0 / (m - Y_vd)); c.im_w = (T)(1.0 / (m - Z_wd)); c.im_r = (T)(1.0 / (I_zz - N_rd));
+    c.mYv = (T)(m - Y_vd); c.mXu = (T)(m - X_ud); c.dXY = (T)(X_ud - Y_vd);
+    c.Xu = (T)-0.09; c.Xuc = (T)-34.96; c.Yv = (T)-0.26; c.Yvc = (T)-103.25;
+    c.Zw = (T)-0.19; c.Zwc = (T)-74.23; c.Nr = (T)-4.64; c.Nrc = (T)-0.43;
+    c.wnet = (T)(m * g - F_bouy);
+    return c;
+}
+
+extern "C" int brov_reduced9_rhs(int dtype, const void* x, const void* u, void* out, long long B, void* stream) {
+    if (dtype != BROV_F64 && dtype != BROV_F32) return fail(BROV_EINVAL, "unknown dtype %d", dtype);
+    if (B < 0 || B > (long long)0x7fffffff * RED9_BLOCK) return fail(BROV_EINVAL, "B out of range");
+    if (B == 0) return BROV_OK;
+    if (!x || !u || !out) return fail(BROV_EINVAL, "NULL argument");
+    if (dtype == BROV_F32) CUDA_TRY(launch_reduced9<float>(red9_consts<float>(), (const float*)x, (const float*)u, (float*)out, B, (cudaStream_t)stream));
+    else CUDA_TRY(launch_reduced9<double>(red9_consts<double>(), (const double*)x, (const double*)u, (double*)out, B, (cudaStream_t)stream));
+    return BROV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-buffer rollout: time-chunked H2D of inputs on a copy stream, double buffered against the rollout kernels;
+// snapshots return on a third stream
+// ---------------------------------------------------------------------------------------------------------------
+static int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return BROV_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    cudaError_t er = cudaMalloc(p, need);
+    if (er != cudaSuccess) return fail(BROV_ENOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(er));
+    *cap = need;
+    return BROV_OK;
+}
+
+extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc* d) {
+    if (!d || d->struct_size != sizeof(brov_rollout_host_desc)) return fail(BROV_EINVAL, "brov_rollout_host_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
+    int rc = check_rollout_common(e, d->integrator, d->n, d->steps, d->dt);
+    if (rc) return rc;
+    if (d->n == 0) return BROV_OK;
+    if (!d->x0_host || !d->xT_host) return fail(BROV_EINVAL, "x0 and xT must not be NULL");
+    if (d->steps > 0 && !d->u_host) return fail(BROV_EINVAL, "u is NULL");
+    if (d->traj_host && d->stride < 1) return fail(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t sz = scalar_size(e->dtype);
+    const int NX = model_nx(e->model), NU = model_nu(e->model), NLAG = model_nlag(e);
+    const long long n = d->n;
+    const size_t row_u = (d->u_shared ? 1 : (size_t)n) * NU * sz;  // bytes of one time step of inputs
+    long long chunk = d->chunk_steps > 0 ? d->chunk_steps : (long long)((256ull << 20) / row_u);
+    if (chunk < 1) chunk = 1;
+    if (d->traj_host) chunk = ((chunk + d->stride - 1) / d->stride) * d->stride;  // whole snapshots per chunk
+    if (chunk > d->steps) chunk = d->steps > 0 ? d->steps : 1;
+    const long long snaps_per_chunk = d->traj_host ? (chunk + d->stride - 1) / d->stride + 1 : 0;
+    const size_t snap_bytes = (size_t)n * NX * sz;
+
+    HostStage& h = e->hs;
+    if (!h.ready) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h.s_compute, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h.s_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h.s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&h.ev_in[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h.ev_done[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h.ev_out[b], cudaEventDisableTiming));
+        }
+        h.ready = true;
+    }
+    if ((rc = grow(&h.d_x, &h.cap_x, snap_bytes))) return rc;
+    if (NLAG && (rc = grow(&h.d_lag, &h.cap_lag, (size_t)n * NLAG * sz))) return rc;
+    {
+        size_t need_u = (size_t)chunk * row_u, cap = h.cap_u;
+        for (int b = 0; b < 2; ++b) { cap = h.cap_u; if ((rc = grow(&h.d_u[b], &cap, need_u))) return rc; }
+        h.cap_u = cap;
+        if (d->traj_host) {
+            size_t need_t = (size_t)snaps_per_chunk * snap_bytes;
+            for (int b = 0; b < 2; ++b) { cap = h.cap_traj; if ((rc = grow(&h.d_traj[b], &cap, need_t))) return rc; }
+            h.cap_traj = cap;
+        }
+    }
+
+    CUDA_TRY(cudaMemcpyAsync(h.d_x, d->x0_host, snap_bytes, cudaMemcpyHostToDevice, h.s_compute));
+    if (NLAG) {
+        if (d->lag_in_host) CUDA_TRY(cudaMemcpyAsync(h.d_lag, d->lag_in_host, (size_t)n * NLAG * sz, cudaMemcpyHostToDevice, h.s_compute));
+        else CUDA_TRY(cudaMemsetAsync(h.d_lag, 0, (size_t)n * NLAG * sz, h.s_compute));
+    }
+    long long done = 0;
+    int b = 0;
+    for (long long c = 0; done < d->steps; ++c, b ^= 1) {
+        const long long len = (d->steps - done < chunk) ? (d->steps - done) : chunk;
+        // inputs of chunk c -> d_u[b] once the kernel that last read d_u[b] (chunk c-2) has finished
+        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h.s_in, h.ev_done[b], 0));
+        CUDA_TRY(cudaMemcpyAsync(h.d_u[b], (const char*)d->u_host + (size_t)done * row_u, (size_t)len * row_u, cudaMemcpyHostToDevice, h.s_in));
+        CUDA_TRY(cudaEventRecord(h.ev_in[b], h.s_in));
+        CUDA_TRY(cudaStreamWaitEvent(h.s_compute, h.ev_in[b], 0));
+        const long long first_snap = d->traj_host ? done / d->stride : 0;
+        const long long last_snap = d->traj_host ? (done + len) / d->stride : 0;  // snapshots [first, last)
+        if (d->traj_host && c >= 2) CUDA_TRY(cudaStreamWaitEvent(h.s_compute, h.ev_out[b], 0));
+        brov_rollout_desc r;
+        memset(&r, 0, sizeof(r));
+        r.struct_size = sizeof(r);
+        r.integrator = d->integrator; r.n = n; r.steps = len; r.dt = d->dt;
+        r.x0_dev = h.d_x; r.xT_dev = h.d_x; r.u_dev = h.d_u[b];
+        r.u_stride_t = d->u_shared ? NU : n * NU;
+        r.u_stride_n = d->u_shared ? 0 : NU;
+        r.lag_in_dev = NLAG ? h.d_lag : nullptr; r.lag_out_dev = NLAG ? h.d_lag : nullptr;
+        r.traj_dev = d->traj_host ? h.d_traj[b] : nullptr;
+        r.stride = d->traj_host ? d->stride : 1; r.step0 = done; r.snap_base = first_snap;
+        if ((rc = brov_rollout(e, &r, h.s_compute))) return rc;
+        CUDA_TRY(cudaEventRecord(h.ev_done[b], h.s_compute));
+        if (d->traj_host && last_snap > first_snap) {
+            CUDA_TRY(cudaStreamWaitEvent(h.s_out, h.ev_done[b], 0));
+            CUDA_TRY(cudaMemcpyAsync((char*)d->traj_host + (size_t)first_snap * snap_bytes, h.d_traj[b], (size_t)(last_snap - first_snap) * snap_bytes, cudaMemcpyDeviceToHost, h.s_out));
+        }
+        if (d->traj_host) CUDA_TRY(cudaEventRecord(h.ev_out[b], h.s_out));
+        done += len;
+    }
+    CUDA_TRY(cudaMemcpyAsync(d->xT_host, h.d_x, snap_bytes, cudaMemcpyDeviceToHost, h.s_compute));
+    if (NLAG && d->lag_out_host) CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag, (size_t)n * NLAG * sz, cudaMemcpyDeviceToHost, h.s_compute));
+    CUDA_TRY(cudaStreamSynchronize(h.s_in));
+    CUDA_TRY(cudaStreamSynchronize(h.s_compute));
+    CUDA_TRY(cudaStreamSynchronize(h.s_out));
+    return BROV_OK;
+}
+
+extern "C" int brov_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(BROV_EINVAL, "out is NULL");
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return BROV_OK;
+}
+extern "C" int brov_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return BROV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP pipe peak
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int brov_fma_peak(int dtype, int device, int iters, double* tflops_out, double* ms_out) {
+    if (dtype != BROV_F64 && dtype != BROV_F32) return fail(BROV_EINVAL, "unknown dtype %d", dtype);
+    if (iters < 1) return fail(BROV_EINVAL, "iters must be >= 1");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8;
+    void* scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)blocks * 256 * 8));
+    cudaEvent_t t0, t1;
+    CUDA_TRY(cudaEventCreate(&t0));
+    CUDA_TRY(cudaEventCreate(&t1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(t0, 0));
+        if (dtype == BROV_F32) CUDA_TRY(launch_fma_peak<float>(iters, blocks, (float*)scratch, 0));
+        else CUDA_TRY(launch_fma_peak<double>(iters, blocks, (double*)scratch, 0));
+        CUDA_TRY(cudaEventRecord(t1, 0));
+        CUDA_TRY(cudaEventSynchronize(t1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, t0, t1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(scratch);
+    const double flops = (double)blocks * 256.0 * (double)iters * 64.0 * 2.0;
+    if (tflops_out) *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return BROV_OK;
+}

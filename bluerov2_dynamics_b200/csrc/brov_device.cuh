@@ -1,0 +1,392 @@
+// brov_device.cuh — device-side BlueROV2 Fossen dynamics, written for one-thread-per-vehicle execution on sm_100a.
+//
+// Everything a vehicle needs between two HBM touches lives in registers: the 12/13-state vector, the RK4
+// accumulator and stage state, the 8x3 thruster-lag state (or the 6 filtered wrench components).  Constants
+// reach the FP pipes as constant-bank operands (they are members of the __grid_constant__ kernel argument), or,
+// for Monte-Carlo ensembles, from a per-block shared-memory table laid out [param][thread] (conflict-free).
+//
+// Reference behaviour restated here (file:line in ViktorNfa/bluerov2_dynamics):
+//   rotation / Euler-rate kinematics        fossen/BlueROV2.py:23-62
+//   T200 polynomial                         fossen/BlueROV2.py:251-257
+//   ThrusterLag.step (x <- Ad x + Bd u)     fossen/BlueROV2.py:503-510   (advanced once per dynamics() call)
+//   allocation  tau = sum F_i [e_i; r_i x e_i]   fossen/BlueROV2.py:265-278
+//   C(nu) nu, D(nu_r) nu_r, g(eta)          fossen/BlueROV2.py:280-355
+//   nu_dot = Minv (tau - C nu - D nu_r - g) fossen/BlueROV2.py:390-391
+//   quaternion kinematics                   fossen/BlueROV2_wrench.py:27-80,322-367
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace brov {
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel-parameter vector (derived coefficients; see brov_derive_params in brov_api.cu and include/brov.h)
+// ---------------------------------------------------------------------------------------------------------------
+enum : int {
+    KP_MINV = 0,   // 6: 1/(m - X_udot) ... 1/(Iz - N_rdot)
+    KP_A = 6,      // 3: a1 = m - X_udot, a2 = m - Y_vdot, a3 = m - Z_wdot
+    KP_DA = 9,     // 3: a3-a2, a1-a3, a2-a1
+    KP_DB = 12,    // 3: b3-b2, b1-b3, b2-b1   (b = I - K_pdot ...)
+    KP_DL = 15,    // 6: -X_u ...   (linear damping, positive)
+    KP_DQ = 21,    // 6: -X_|u|u ... (quadratic damping, positive)
+    KP_WMB = 27,   // W - B
+    KP_XBB = 28,   // xb*B, yb*B, zb*B
+    KP_CUR = 31,   // 3: current velocity, NED
+    KP_ILAG1 = 34, // 1 / T_lag of the optional first-order wrench lag (extension)
+    KP_COUNT = 36
+};
+
+constexpr int MODEL_THRUSTER8 = 0;
+constexpr int MODEL_WRENCH12 = 1;
+constexpr int MODEL_QUAT13 = 2;
+constexpr int INTEG_RK4 = 0;
+constexpr int INTEG_EULER = 1;
+
+template <int MODEL> struct ModelDim {
+    static constexpr int NX = (MODEL == MODEL_QUAT13) ? 13 : 12;
+    static constexpr int NU = (MODEL == MODEL_THRUSTER8) ? 8 : 6;
+    static constexpr int NLAG = (MODEL == MODEL_THRUSTER8) ? 24 : 6;  // hidden state per vehicle
+    static constexpr int VOFF = (MODEL == MODEL_QUAT13) ? 7 : 6;      // offset of nu in the state
+};
+
+// Constants shared by every vehicle of a launch.  Lives in the kernel argument => constant bank 0.
+template <typename T> struct Consts {
+    T kp[KP_COUNT];
+    T alloc[6][8];   // tau = alloc * F
+    // closed-form 3rd-order lag over the NSUB dynamics() calls of one integrator step with the input held:
+    //   y_j = lagG[j] . x + lagH[j] * F   (output seen by sub-step j, j = 0..NSUB-1)
+    //   x  <- lagA x + lagB F             (state after all NSUB sub-steps)
+    T lagG[4][3];
+    T lagH[4];
+    T lagA[3][3];
+    T lagB[3];
+    T dt;
+    int has_current;
+    int use_lag1;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float abs_(float a) { return fabsf(a); }
+__device__ __forceinline__ double abs_(double a) { return fabs(a); }
+__device__ __forceinline__ float sqrt_(float a) { return sqrtf(a); }
+__device__ __forceinline__ double sqrt_(double a) { return sqrt(a); }
+
+// 1/a.  fp32: MUFU.RCP seed + one Newton step (<= 1 ulp for normal a); inf/0 behave like IEEE division.
+__device__ __forceinline__ float rcp_(float a) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    float e = fmaf(-a, r, 1.0f);
+    float r2 = fmaf(r, e, r);
+    // keep the seed when the Newton step degenerates (a = 0 or inf: e is NaN)
+    return (e == e) ? r2 : r;
+}
+__device__ __forceinline__ double rcp_(double a) { return 1.0 / a; }
+
+// sin & cos.  fp32: 3-term Cody-Waite reduction by pi/2 (FMA keeps the products exact) + minimax polynomials on
+// [-pi/4, pi/4] (Cephes sinf/cosf coefficients); |error| <= ~1.5 ulp.  No slow path, no local memory; domain
+// |a| < 2^30 rad (a float that large has an ulp of 64 rad anyway).
+__device__ __forceinline__ void sincos_(float a, float* s, float* c) {
+    float j = rintf(a * 0.6366197466850281f);
+    float r = fmaf(-j, 1.5707963705062866f, a);
+    r = fmaf(-j, -4.371138828673793e-08f, r);
+    r = fmaf(-j, -1.7151245100058819e-15f, r);
+    int q = (int)j;
+    float z = r * r;
+    float ps = fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f);
+    float sn = fmaf(ps * z, r, r);
+    float pc = fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f);
+    float cs = fmaf(pc * z, z, fmaf(-0.5f, z, 1.0f));
+    float ss = (q & 1) ? cs : sn;
+    float cc = (q & 1) ? sn : cs;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
+// fp64: same scheme with the fdlibm __kernel_sin/__kernel_cos coefficients.  The FMA makes each reduction step a
+// single rounding, so full-precision parts of pi/2 suffice.  Domain |a| < 2^30 rad (quadrant held in an int).
+__device__ __forceinline__ void sincos_(double a, double* s, double* c) {
+    double j = rint(a * 0.6366197723675814);
+    double r = fma(-j, 1.5707963267948966, a);
+    r = fma(-j, 6.123233995736766e-17, r);
+    r = fma(-j, -1.4973849048591698e-33, r);
+    int q = (int)j;
+    double z = r * r;
+    double ps = fma(fma(fma(fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08), z,
+                            2.75573137070700676789e-06), z, -1.98412698298579493134e-04), z,
+                    8.33333333332248946124e-03);
+    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double sn = fma(ps * z, r, r);
+    double pc = fma(fma(fma(fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09), z,
+                            -2.75573143513906633035e-07), z, 2.48015872894767294178e-05), z,
+                    -1.38888888888741095749e-03);
+    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double cs = fma(pc * z, z, fma(-0.5, z, 1.0));
+    double ss = (q & 1) ? cs : sn;
+    double cc = (q & 1) ? sn : cs;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// parameter access: constant bank (shared by all vehicles) or shared-memory table (per-vehicle Monte-Carlo)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct ParamsConst {
+    const T* kp;  // points into the __grid_constant__ argument
+    __device__ __forceinline__ T operator[](int i) const { return kp[i]; }
+};
+template <typename T> struct ParamsShared {
+    const T* base;  // &table[0][threadIdx.x]
+    int pitch;      // blockDim.x
+    __device__ __forceinline__ T operator[](int i) const { return base[i * pitch]; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// model pieces
+// ---------------------------------------------------------------------------------------------------------------
+
+// T200 static thrust curve, Horner in V^2 (fossen/BlueROV2.py:251-257; the reference uses pow(), <= 3 ulp apart).
+template <typename T> __device__ __forceinline__ T thrust_poly(T V) {
+    T z = V * V;
+    T p = T(-140.3) * z + T(389.9);
+    p = p * z + T(-404.1);
+    p = p * z + T(176.0);
+    p = p * z + T(8.9);
+    return p * V;
+}
+
+// nu_dot = Minv (tau - C(nu) nu - D(nu_r) nu_r - g); g from (sin th, cos th sin phi, cos th cos phi).
+template <typename T, class P>
+__device__ __forceinline__ void nu_dot(const T* __restrict__ nu, const T* __restrict__ nur, const T* __restrict__ tau,
+                                       T sth, T cs, T cc, const P& p, T* __restrict__ out) {
+    const T u = nu[0], v = nu[1], w = nu[2], pp = nu[3], q = nu[4], r = nu[5];
+    const T a1u = p[KP_A + 0] * u, a2v = p[KP_A + 1] * v, a3w = p[KP_A + 2] * w;
+    T c[6];
+    c[0] = a3w * q - a2v * r;
+    c[1] = a1u * r - a3w * pp;
+    c[2] = a2v * pp - a1u * q;
+    c[3] = p[KP_DA + 0] * (v * w) + p[KP_DB + 0] * (q * r);
+    c[4] = p[KP_DA + 1] * (u * w) + p[KP_DB + 1] * (pp * r);
+    c[5] = p[KP_DA + 2] * (u * v) + p[KP_DB + 2] * (pp * q);
+    const T wmb = p[KP_WMB], xbB = p[KP_XBB + 0], ybB = p[KP_XBB + 1], zbB = p[KP_XBB + 2];
+    T g[6];
+    g[0] = wmb * sth;
+    g[1] = -wmb * cs;
+    g[2] = -wmb * cc;
+    g[3] = ybB * cc - zbB * cs;
+    g[4] = -zbB * sth - xbB * cc;
+    g[5] = xbB * cs + ybB * sth;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        T d = p[KP_DQ + i] * abs_(nur[i]) + p[KP_DL + i];
+        out[i] = p[KP_MINV + i] * (tau[i] - c[i] - d * nur[i] - g[i]);
+    }
+}
+
+// Euler-angle models: xdot[12] from x[12] and the body wrench tau[6].
+template <typename T, class P>
+__device__ __forceinline__ void rhs_euler12(const T* __restrict__ x, const T* __restrict__ tau, const P& p,
+                                            bool has_current, T* __restrict__ xd) {
+    T sphi, cphi, sth, cth, spsi, cpsi;
+    sincos_(x[3], &sphi, &cphi);
+    sincos_(x[4], &sth, &cth);
+    sincos_(x[5], &spsi, &cpsi);
+    const T* nu = x + 6;
+    // p_dot = Rz(psi) Ry(theta) Rx(phi) nu_1 as three planar rotations
+    {
+        T v1 = cphi * nu[1] - sphi * nu[2];
+        T w1 = sphi * nu[1] + cphi * nu[2];
+        T u2 = cth * nu[0] + sth * w1;
+        xd[2] = cth * w1 - sth * nu[0];
+        xd[0] = cpsi * u2 - spsi * v1;
+        xd[1] = spsi * u2 + cpsi * v1;
+    }
+    // Euler rates with the reference's cos(theta) clamp: |c| < 1e-7 -> 1e-7 * sign(c), sign(0) = 0
+    {
+        T ct = cth;
+        if (abs_(ct) < T(1e-7)) ct = (ct > T(0)) ? T(1e-7) : ((ct < T(0)) ? T(-1e-7) : T(0));
+        T ic = rcp_(ct);
+        T sq = sphi * nu[4] + cphi * nu[5];
+        T psd = sq * ic;
+        xd[5] = psd;
+        xd[4] = cphi * nu[4] - sphi * nu[5];
+        xd[3] = nu[3] + sth * psd;
+    }
+    T nur[6] = {nu[0], nu[1], nu[2], nu[3], nu[4], nu[5]};
+    if (has_current) {  // nu_r = nu - R^T v_c  (inverse rotations in the opposite order)
+        T cx = p[KP_CUR + 0], cy = p[KP_CUR + 1], cz = p[KP_CUR + 2];
+        T x1 = cpsi * cx + spsi * cy;
+        T y1 = cpsi * cy - spsi * cx;
+        T x2 = cth * x1 - sth * cz;
+        T z2 = sth * x1 + cth * cz;
+        T y3 = cphi * y1 + sphi * z2;
+        T z3 = cphi * z2 - sphi * y1;
+        nur[0] -= x2;
+        nur[1] -= y3;
+        nur[2] -= z3;
+    }
+    nu_dot<T>(nu, nur, tau, sth, cth * sphi, cth * cphi, p, xd + 6);
+}
+
+// Quaternion model: xdot[13] from x[13] = [pos, qw qx qy qz, nu] (fossen/BlueROV2_wrench.py:322-367).
+template <typename T, class P>
+__device__ __forceinline__ void rhs_quat13(const T* __restrict__ x, const T* __restrict__ tau, const P& p,
+                                           bool has_current, T* __restrict__ xd) {
+    T qw = x[3], qx = x[4], qy = x[5], qz = x[6];
+    {
+        T n2 = qw * qw + qx * qx + qy * qy + qz * qz;
+        T n = sqrt_(n2);
+        if (n < T(1e-12)) { qw = T(1); qx = qy = qz = T(0); }
+        else { T in = rcp_(n); qw *= in; qx *= in; qy *= in; qz *= in; }
+    }
+    const T* nu = x + 7;
+    T R00 = T(1) - T(2) * (qy * qy + qz * qz), R01 = T(2) * (qx * qy - qz * qw), R02 = T(2) * (qx * qz + qy * qw);
+    T R10 = T(2) * (qx * qy + qz * qw), R11 = T(1) - T(2) * (qx * qx + qz * qz), R12 = T(2) * (qy * qz - qx * qw);
+    T R20 = T(2) * (qx * qz - qy * qw), R21 = T(2) * (qy * qz + qx * qw), R22 = T(1) - T(2) * (qx * qx + qy * qy);
+    xd[0] = R00 * nu[0] + R01 * nu[1] + R02 * nu[2];
+    xd[1] = R10 * nu[0] + R11 * nu[1] + R12 * nu[2];
+    xd[2] = R20 * nu[0] + R21 * nu[1] + R22 * nu[2];
+    const T wp = nu[3], wq = nu[4], wr = nu[5];
+    xd[3] = T(0.5) * (-qx * wp - qy * wq - qz * wr);
+    xd[4] = T(0.5) * (qw * wp + qy * wr - qz * wq);
+    xd[5] = T(0.5) * (qw * wq - qx * wr + qz * wp);
+    xd[6] = T(0.5) * (qw * wr + qx * wq - qy * wp);
+    T nur[6] = {nu[0], nu[1], nu[2], nu[3], nu[4], nu[5]};
+    if (has_current) {
+        T cx = p[KP_CUR + 0], cy = p[KP_CUR + 1], cz = p[KP_CUR + 2];
+        nur[0] -= R00 * cx + R10 * cy + R20 * cz;
+        nur[1] -= R01 * cx + R11 * cy + R21 * cz;
+        nur[2] -= R02 * cx + R12 * cy + R22 * cz;
+    }
+    nu_dot<T>(nu, nur, tau, -R20, R21, R22, p, xd + 7);
+}
+
+template <typename T> __device__ __forceinline__ void quat_renorm(T* q) {
+    T n = sqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    if (n < T(1e-12)) { q[0] = T(1); q[1] = q[2] = q[3] = T(0); }
+    else { T in = rcp_(n); q[0] *= in; q[1] *= in; q[2] *= in; q[3] *= in; }
+}
+
+// Thruster wrench seen by sub-step j of a step: y_i = G_j . lag_i + H_j F_i ; tau = alloc y.
+template <typename T>
+__device__ __forceinline__ void thruster_tau(const Consts<T>& c, int j, const T* __restrict__ lag,
+                                             const T* __restrict__ F, T* __restrict__ tau) {
+    T y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        y[i] = c.lagG[j][0] * lag[3 * i] + c.lagG[j][1] * lag[3 * i + 1] + c.lagG[j][2] * lag[3 * i + 2] + c.lagH[j] * F[i];
+    // rows 0..2 and 5 of the allocation matrix are structurally sparse (horizontal thrusters have no z
+    // component, vertical ones only z); their zero entries are skipped at compile time below.
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        T s = T(0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool nz = (r < 2) ? (i < 4) : (r == 2) ? (i >= 4) : (r == 5) ? (i < 4) : true;
+            if (nz) s += c.alloc[r][i] * y[i];
+        }
+        tau[r] = s;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void lag_advance(const Consts<T>& c, T* __restrict__ lag, const T* __restrict__ F) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        T a = lag[3 * i], b = lag[3 * i + 1], d = lag[3 * i + 2];
+        lag[3 * i + 0] = c.lagA[0][0] * a + c.lagA[0][1] * b + c.lagA[0][2] * d + c.lagB[0] * F[i];
+        lag[3 * i + 1] = c.lagA[1][0] * a + c.lagA[1][1] * b + c.lagA[1][2] * d + c.lagB[1] * F[i];
+        lag[3 * i + 2] = c.lagA[2][0] * a + c.lagA[2][1] * b + c.lagA[2][2] * d + c.lagB[2] * F[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one integrator step of one vehicle, everything in registers
+//   x[NX]   state (in/out)
+//   lag[]   THRUSTER8: 8x3 lag state; wrench models with LAG1: the 6 filtered wrench components
+//   u[NU]   input held over the step
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODEL, bool LAG1, class P>
+__device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int substep, const T* __restrict__ x,
+                                          const T* __restrict__ lag, const T* __restrict__ Fu,
+                                          T* __restrict__ xd, T* __restrict__ lagd) {
+    // Fu: THRUSTER8 -> static thrust F[8] of this step;  wrench models -> commanded wrench u[6]
+    if constexpr (MODEL == MODEL_THRUSTER8) {
+        T tau[6];
+        thruster_tau<T>(c, substep, lag, Fu, tau);
+        rhs_euler12<T>(x, tau, p, c.has_current != 0, xd);
+    } else {
+        const T* tau = Fu;
+        if constexpr (LAG1) {
+            tau = lag;
+            const T il = p[KP_ILAG1];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) lagd[i] = (Fu[i] - lag[i]) * il;
+        }
+        if constexpr (MODEL == MODEL_WRENCH12) rhs_euler12<T>(x, tau, p, c.has_current != 0, xd);
+        else rhs_quat13<T>(x, tau, p, c.has_current != 0, xd);
+    }
+}
+
+template <typename T, int MODEL, int INTEG, bool LAG1, class P>
+__device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x,
+                                               T* __restrict__ lag, const T* __restrict__ u) {
+    constexpr int NX = ModelDim<MODEL>::NX;
+    constexpr int NL = LAG1 ? 6 : 1;  // continuous auxiliary states integrated with x
+    const T dt = c.dt;
+    T Fu[ModelDim<MODEL>::NU];
+    if constexpr (MODEL == MODEL_THRUSTER8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Fu[i] = thrust_poly<T>(u[i]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) Fu[i] = u[i];
+    }
+    T k[NX], kl[NL];
+    if constexpr (INTEG == INTEG_EULER) {
+        model_rhs<T, MODEL, LAG1>(c, p, 0, x, lag, Fu, k, kl);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] += dt * k[i];
+        if constexpr (LAG1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) lag[i] += dt * kl[i];
+        }
+    } else {
+        // classic RK4 in low-storage form: acc accumulates k1 + 2 k2 + 2 k3 + k4, xs is the stage state
+        T acc[NX], xs[NX], accl[NL], ls[NL];
+        const T hdt = T(0.5) * dt;
+        model_rhs<T, MODEL, LAG1>(c, p, 0, x, lag, Fu, k, kl);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { acc[i] = k[i]; xs[i] = x[i] + hdt * k[i]; }
+        if constexpr (LAG1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { accl[i] = kl[i]; ls[i] = lag[i] + hdt * kl[i]; }
+        }
+        model_rhs<T, MODEL, LAG1>(c, p, 1, xs, LAG1 ? ls : lag, Fu, k, kl);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { acc[i] += T(2) * k[i]; xs[i] = x[i] + hdt * k[i]; }
+        if constexpr (LAG1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { accl[i] += T(2) * kl[i]; ls[i] = lag[i] + hdt * kl[i]; }
+        }
+        model_rhs<T, MODEL, LAG1>(c, p, 2, xs, LAG1 ? ls : lag, Fu, k, kl);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { acc[i] += T(2) * k[i]; xs[i] = x[i] + dt * k[i]; }
+        if constexpr (LAG1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { accl[i] += T(2) * kl[i]; ls[i] = lag[i] + dt * kl[i]; }
+        }
+        model_rhs<T, MODEL, LAG1>(c, p, 3, xs, LAG1 ? ls : lag, Fu, k, kl);
+        const T dt6 = dt * T(1.0 / 6.0);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i] + k[i]);
+        if constexpr (LAG1) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) lag[i] += dt6 * (accl[i] + kl[i]);
+        }
+    }
+    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T>(c, lag, Fu);
+    if constexpr (MODEL == MODEL_QUAT13) quat_renorm<T>(x + 3);
+}
+
+}  // namespace brov

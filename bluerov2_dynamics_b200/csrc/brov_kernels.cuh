@@ -1,0 +1,471 @@
+// brov_kernels.cuh — the sm_100a kernels of the engine and their launchers (templated on the scalar type; the two
+// translation units brov_kernels_f32.cu / brov_kernels_f64.cu instantiate them so nvcc can build them in parallel).
+//
+//   rollout_kernel   open-loop rollout of N vehicles, one thread per vehicle, optional strided trajectory
+//                    writeback through per-warp shared-memory staging        (simulate_physics,
+//                    training/train_tank_brov2_rk4.py:375-396 and its Euler twins)
+//   rhs_kernel       one dynamics() call for N vehicles                       (fossen/BlueROV2.py:357-400 etc.)
+//   se_kernel        sliding-window multi-horizon endpoint squared error, one thread per window, warp-shuffle +
+//                    block reduction into per-block partial sums              (multistep_rmse_endpoint_physics,
+//                    training/train_tank_brov2_rk4.py:399-417 and twins)
+//   se_finish_kernel fixed-order sum of the per-block partials (bit-reproducible result)
+//   reduced9_kernel  bluerov_compute RHS, shared-memory transposed, HBM-bound  (fossen/bluerov_torch.py:20-67)
+//   fma_peak_kernel  FMA-chain microbenchmark: the FP32 / FP64 pipe roofline denominator measured in-run
+#pragma once
+#include <type_traits>
+#include "brov_device.cuh"
+
+namespace brov {
+
+constexpr int MAX_H = 4;          // horizons per se launch
+constexpr int ROLLOUT_BLOCK = 128;
+constexpr int SE_BLOCK = 128;
+constexpr int RED9_BLOCK = 256;
+
+template <typename T> struct RolloutArgs {
+    Consts<T> c;
+    const T* x0;        // [n][NX]
+    T* xT;              // [n][NX] (may alias x0)
+    const T* U;         // element (k, i, j) at U[k*u_stride_t + i*u_stride_n + j]
+    long long u_stride_t, u_stride_n;
+    const T* lag_in;    // [n][NLAG] or nullptr (zeros)
+    T* lag_out;         // [n][NLAG] or nullptr
+    const T* pv;        // [KP_COUNT][n] or nullptr
+    T* traj;            // snapshot s (global step (s+1)*stride) at traj[(s - snap_base)*n*NX ...] or nullptr
+    long long snap_base;
+    long long step0;    // global index of the first step of this launch
+    int n, steps, stride;
+    int u_vec, traj_vec;
+};
+
+template <typename T> struct RhsArgs {
+    Consts<T> c;
+    const T* x;
+    const T* u;
+    T* lag;    // in/out, nullptr = zero lag, not written
+    const T* pv;
+    T* xdot;
+    int n;
+};
+
+template <typename T> struct SeArgs {
+    Consts<T> c;
+    const T* X;     // [rows][NX]
+    const T* U;     // [rows][NU]
+    const T* lag0;  // [nwin][NLAG] or nullptr
+    double* partial;  // [gridDim.x][MAX_H]
+    int rows, nwin, nH;
+    int H[MAX_H];   // ascending
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// vectorised, cache-hinted input loads
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int NU, bool STREAM>
+__device__ __forceinline__ void load_u(const T* __restrict__ p, bool vec, T* __restrict__ u) {
+    if (vec) {
+        if constexpr (sizeof(T) == 4 && NU == 8) {
+            const float4* q = reinterpret_cast<const float4*>(p);
+            float4 a = STREAM ? __ldcs(q) : __ldg(q);
+            float4 b = STREAM ? __ldcs(q + 1) : __ldg(q + 1);
+            u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w; u[4] = b.x; u[5] = b.y; u[6] = b.z; u[7] = b.w;
+        } else if constexpr (sizeof(T) == 4) {
+            const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+            for (int i = 0; i < NU / 2; ++i) {
+                float2 a = STREAM ? __ldcs(q + i) : __ldg(q + i);
+                u[2 * i] = a.x; u[2 * i + 1] = a.y;
+            }
+        } else {
+            const double2* q = reinterpret_cast<const double2*>(p);
+#pragma unroll
+            for (int i = 0; i < NU / 2; ++i) {
+                double2 a = STREAM ? __ldcs(q + i) : __ldg(q + i);
+                u[2 * i] = a.x; u[2 * i + 1] = a.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = STREAM ? __ldcs(p + i) : __ldg(p + i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// trajectory snapshot: registers -> per-warp shared-memory tile [32][NX] -> 128-bit coalesced streaming stores
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int NX>
+__device__ __forceinline__ void snapshot_warp(T* __restrict__ tile, const T* __restrict__ x, T* __restrict__ dst,
+                                              int n_valid, bool vec, int lane) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) tile[lane * NX + j] = x[j];
+    __syncwarp();
+    constexpr int VEC = 16 / sizeof(T);
+    if (vec) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+#pragma unroll
+        for (int e = 0; e < 32 * NX; e += 32 * VEC) {
+            int idx = e + lane * VEC;
+            if (idx + VEC <= n_valid) {
+                __stcs(reinterpret_cast<V*>(dst + idx), *reinterpret_cast<const V*>(tile + idx));
+            } else {
+#pragma unroll
+                for (int t = 0; t < VEC; ++t)
+                    if (idx + t < n_valid) __stcs(dst + idx + t, tile[idx + t]);
+            }
+        }
+    } else {
+        for (int idx = lane; idx < n_valid; idx += 32) __stcs(dst + idx, tile[idx]);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rollout
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODEL, bool LAG1> struct LagRegs {
+    static constexpr int N = (MODEL == MODEL_THRUSTER8) ? 24 : (LAG1 ? 6 : 1);
+    static constexpr bool HAS = (MODEL == MODEL_THRUSTER8) || LAG1;
+};
+
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV>
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
+    constexpr int NX = ModelDim<MODEL>::NX;
+    constexpr int NU = ModelDim<MODEL>::NU;
+    constexpr int NL = LagRegs<T, MODEL, LAG1>::N;
+    constexpr bool HASLAG = LagRegs<T, MODEL, LAG1>::HAS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const long long gi = (long long)blockIdx.x * ROLLOUT_BLOCK + tid;
+    const bool live = gi < a.n;
+    const long long i = live ? gi : (long long)a.n - 1;  // dead lanes shadow the last vehicle, never store
+
+    T* tiles = smem;
+    typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type p;
+    if constexpr (PV) {
+#pragma unroll 4
+        for (int j = 0; j < KP_COUNT; ++j) smem[j * ROLLOUT_BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
+        __syncthreads();
+        p.base = smem + tid;
+        p.pitch = ROLLOUT_BLOCK;
+        tiles = smem + KP_COUNT * ROLLOUT_BLOCK;
+    } else {
+        p.kp = a.c.kp;
+    }
+
+    T x[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.x0 + i * NX + j);
+    T lag[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) lag[j] = (HASLAG && a.lag_in) ? __ldg(a.lag_in + i * NL + j) : T(0);
+
+    const T* up = a.U + i * a.u_stride_n;
+    const bool uvec = a.u_vec != 0;
+    const bool stream = a.u_stride_n != 0;  // per-vehicle inputs are read exactly once: evict-first
+    T u[NU];
+    if (stream) load_u<T, NU, true>(up, uvec, u); else load_u<T, NU, false>(up, uvec, u);
+
+    int countdown = a.traj ? (int)(a.stride - (a.step0 % a.stride)) : 0x7fffffff;
+    long long snap = a.traj ? (a.step0 / a.stride - a.snap_base) : 0;
+    const long long warp_v0 = (long long)blockIdx.x * ROLLOUT_BLOCK + warp * 32;
+    const long long rem = (long long)a.n - warp_v0;
+    const int n_valid = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem)) * NX;
+
+    for (int k = 0; k < a.steps; ++k) {
+        // prefetch the next step's inputs before the ~1e3 dependent FP ops of this step
+        T un[NU];
+        const T* nxt = up + (long long)((k + 1 < a.steps) ? (k + 1) : k) * a.u_stride_t;
+        if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
+
+        integrate_step<T, MODEL, INTEG, LAG1>(a.c, p, x, lag, u);
+
+        if (--countdown == 0) {
+            countdown = a.stride;
+            T* dst = a.traj + (snap * a.n + warp_v0) * NX;
+            snapshot_warp<T, NX>(tiles + warp * 32 * NX, x, dst, n_valid, a.traj_vec != 0, lane);
+            ++snap;
+        }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) u[j] = un[j];
+    }
+
+    if (live) {
+#pragma unroll
+        for (int j = 0; j < NX; ++j) a.xT[i * NX + j] = x[j];
+        if (HASLAG && a.lag_out) {
+#pragma unroll
+            for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// single state-derivative evaluation (the reference's dynamics(): the 3rd-order lag advances by ONE sub-step)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODEL, bool LAG1, bool PV>
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) rhs_kernel(const __grid_constant__ RhsArgs<T> a) {
+    constexpr int NX = ModelDim<MODEL>::NX;
+    constexpr int NU = ModelDim<MODEL>::NU;
+    constexpr int NL = LagRegs<T, MODEL, LAG1>::N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* smem = reinterpret_cast<T*>(smem_raw);
+    const int tid = threadIdx.x;
+    const long long gi = (long long)blockIdx.x * ROLLOUT_BLOCK + tid;
+    const bool live = gi < a.n;
+    const long long i = live ? gi : (long long)a.n - 1;
+    typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type p;
+    if constexpr (PV) {
+        for (int j = 0; j < KP_COUNT; ++j) smem[j * ROLLOUT_BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
+        __syncthreads();
+        p.base = smem + tid;
+        p.pitch = ROLLOUT_BLOCK;
+    } else {
+        p.kp = a.c.kp;
+    }
+    T x[NX], u[NU], lag[NL], Fu[NU], xd[NX], lagd[6];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.x + i * NX + j);
+#pragma unroll
+    for (int j = 0; j < NU; ++j) u[j] = __ldg(a.u + i * NU + j);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) lag[j] = (LagRegs<T, MODEL, LAG1>::HAS && a.lag) ? a.lag[i * NL + j] : T(0);
+#pragma unroll
+    for (int j = 0; j < NU; ++j) Fu[j] = (MODEL == MODEL_THRUSTER8) ? thrust_poly<T>(u[j]) : u[j];
+    model_rhs<T, MODEL, LAG1>(a.c, p, 0, x, lag, Fu, xd, lagd);
+    if (!live) return;
+#pragma unroll
+    for (int j = 0; j < NX; ++j) a.xdot[i * (NX + (LAG1 ? 6 : 0)) + j] = xd[j];
+    if constexpr (LAG1) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) a.xdot[i * (NX + 6) + NX + j] = lagd[j];
+    }
+    if constexpr (MODEL == MODEL_THRUSTER8) {
+        if (a.lag) {
+            lag_advance<T>(a.c, lag, Fu);
+#pragma unroll
+            for (int j = 0; j < NL; ++j) a.lag[i * NL + j] = lag[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// thruster map alone: voltages -> polynomial -> one lag step -> body wrench   (compute_thruster_forces,
+// fossen/BlueROV2.py:265-278; stateful like the reference)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct ThrusterArgs {
+    Consts<T> c;
+    const T* u;   // [n][8]
+    T* lag;       // [n][24] in/out or nullptr
+    T* tau;       // [n][6]
+    int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) thruster_wrench_kernel(const __grid_constant__ ThrusterArgs<T> a) {
+    const long long i = (long long)blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    T u[8], F[8], lag[24], tau[6];
+    load_u<T, 8, false>(a.u + i * 8, (reinterpret_cast<uintptr_t>(a.u) & 15) == 0, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
+#pragma unroll
+    for (int j = 0; j < 24; ++j) lag[j] = a.lag ? a.lag[i * 24 + j] : T(0);
+    thruster_tau<T>(a.c, 0, lag, F, tau);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a.tau[i * 6 + j] = tau[j];
+    if (a.lag) {
+        lag_advance<T>(a.c, lag, F);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) a.lag[i * 24 + j] = lag[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// multi-horizon endpoint squared error over sliding windows
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODEL, int INTEG>
+__global__ void __launch_bounds__(SE_BLOCK) se_kernel(const __grid_constant__ SeArgs<T> a) {
+    constexpr int NX = ModelDim<MODEL>::NX;
+    constexpr int NU = ModelDim<MODEL>::NU;
+    constexpr int NL = LagRegs<T, MODEL, false>::N;
+    __shared__ double red[SE_BLOCK / 32][MAX_H];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long gk = (long long)blockIdx.x * SE_BLOCK + tid;
+    const bool live = gk < a.nwin;
+    const long long k = live ? gk : 0;
+    ParamsConst<T> p;
+    p.kp = a.c.kp;
+
+    T x[NX], lag[NL];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + k * NX + j);
+#pragma unroll
+    for (int j = 0; j < NL; ++j) lag[j] = (MODEL == MODEL_THRUSTER8 && a.lag0) ? __ldg(a.lag0 + k * NL + j) : T(0);
+
+    double se[MAX_H];
+#pragma unroll
+    for (int h = 0; h < MAX_H; ++h) se[h] = 0.0;
+    const int hmax = a.H[a.nH - 1];
+    // window k may run j steps while row k + j exists
+    long long room = (long long)a.rows - 1 - k;
+    const int nsteps = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
+    const bool uvec = ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && (sizeof(T) * NU % 16 == 0);
+    for (int j = 0; j < nsteps; ++j) {
+        T u[NU];
+        load_u<T, NU, false>(a.U + (k + j) * NU, uvec, u);
+        integrate_step<T, MODEL, INTEG, false>(a.c, p, x, lag, u);
+#pragma unroll
+        for (int h = 0; h < MAX_H; ++h) {
+            if (h < a.nH && j + 1 == a.H[h]) {
+                const T* tgt = a.X + (k + j + 1) * NX;
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < NX; ++q) {
+                    double e = (double)x[q] - (double)__ldg(tgt + q);
+                    s += e * e;
+                }
+                se[h] = s;
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < MAX_H; ++h) {
+        double v = se[h];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][h] = v;
+    }
+    __syncthreads();
+    if (tid < MAX_H) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < SE_BLOCK / 32; ++w) v += red[w][tid];
+        a.partial[(long long)blockIdx.x * MAX_H + tid] = v;
+    }
+}
+
+// one block; thread t sums partials t, t+256, ... in order, then a fixed tree: same bits every run
+static __global__ void __launch_bounds__(256) se_finish_kernel(const double* __restrict__ partial, int nblocks,
+                                                        double* __restrict__ se_out) {
+    __shared__ double sh[256];
+    for (int h = 0; h < MAX_H; ++h) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += 256) v += partial[(long long)b * MAX_H + h];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) se_out[h] = sh[0];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reduced 9-state model RHS (bluerov_compute): 13 scalars in, 9 out per row; rows staged through shared memory so
+// that every global access is a full-line coalesced (vector) transaction
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct Red9Consts {
+    T im_u, im_v, im_w, im_r;   // 1/(m - X_ud), 1/(m - Y_vd), 1/(m - Z_wd), 1/(I_zz - N_rd)
+    T mYv, mXu, dXY;            // m - Y_vd, m - X_ud, X_ud - Y_vd
+    T Xu, Xuc, Yv, Yvc, Zw, Zwc, Nr, Nrc;
+    T wnet;                     // m g - F_bouy
+};
+
+template <typename T>
+__global__ void __launch_bounds__(RED9_BLOCK) reduced9_kernel(const __grid_constant__ Red9Consts<T> c,
+                                                              const T* __restrict__ X, const T* __restrict__ U,
+                                                              T* __restrict__ O, long long B, int vec) {
+    __shared__ __align__(16) T tile[RED9_BLOCK * 9];
+    constexpr int VEC = 16 / sizeof(T);
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int tid = threadIdx.x;
+    const long long r0 = (long long)blockIdx.x * RED9_BLOCK;
+    const long long rows = (B - r0 < RED9_BLOCK) ? (B - r0) : RED9_BLOCK;
+    const int nel = (int)rows * 9;
+    const T* src = X + r0 * 9;
+    if (vec) {
+        for (int e = tid * VEC; e < nel; e += RED9_BLOCK * VEC) {
+            if (e + VEC <= nel) *reinterpret_cast<V*>(tile + e) = __ldcs(reinterpret_cast<const V*>(src + e));
+            else for (int t = 0; e + t < nel; ++t) tile[e + t] = __ldcs(src + e + t);
+        }
+    } else {
+        for (int e = tid; e < nel; e += RED9_BLOCK) tile[e] = __ldcs(src + e);
+    }
+    __syncthreads();
+    T o[9];
+    if (tid < rows) {
+        const T* x = tile + tid * 9;  // stride 9 words: conflict-free
+        T cps = x[3], sps = x[4], u = x[5], v = x[6], w = x[7], r = x[8];
+        T in[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) in[j] = __ldcs(U + (r0 + tid) * 4 + j);
+        o[0] = cps * u - sps * v;
+        o[1] = sps * u + cps * v;
+        o[2] = w;
+        o[3] = -sps * r;
+        o[4] = cps * r;
+        o[5] = c.im_u * (in[0] + c.mYv * v * r + (c.Xu + c.Xuc * abs_(u)) * u);
+        o[6] = c.im_v * (in[1] - c.mXu * u * r + (c.Yv + c.Yvc * abs_(v)) * v);
+        o[7] = c.im_w * (in[2] + (c.Zw + c.Zwc * abs_(w)) * w + c.wnet);
+        o[8] = c.im_r * (in[3] - c.dXY * u * v + (c.Nr + c.Nrc * abs_(r)) * r);
+    }
+    __syncthreads();
+    if (tid < rows) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) tile[tid * 9 + j] = o[j];
+    }
+    __syncthreads();
+    T* dst = O + r0 * 9;
+    if (vec) {
+        for (int e = tid * VEC; e < nel; e += RED9_BLOCK * VEC) {
+            if (e + VEC <= nel) __stcs(reinterpret_cast<V*>(dst + e), *reinterpret_cast<const V*>(tile + e));
+            else for (int t = 0; e + t < nel; ++t) __stcs(dst + e + t, tile[e + t]);
+        }
+    } else {
+        for (int e = tid; e < nel; e += RED9_BLOCK) __stcs(dst + e, tile[e]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FMA-chain microbenchmark: 8 independent chains per thread, 2 flops per FMA
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b) {
+    T v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = T(threadIdx.x + j) * T(1e-3);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = v[j] * a + b;
+        }
+    }
+    T s = T(0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[j];
+    if (s == T(123456789)) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers (defined in brov_kernels_impl.cuh, instantiated per scalar type)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st);
+template <typename T>
+cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t st);
+template <typename T>
+cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, int nblocks, double* se_out, cudaStream_t st);
+template <typename T>
+cudaError_t launch_reduced9(const Red9Consts<T>& c, const T* X, const T* U, T* O, long long B, cudaStream_t st);
+template <typename T>
+cudaError_t launch_fma_peak(int iters, int blocks, T* scratch, cudaStream_t st);
+template <typename T>
+cudaError_t launch_thruster_wrench(const ThrusterArgs<T>& a, cudaStream_t st);
+
+}  // namespace brov

@@ -1,0 +1,372 @@
+"""Host side of the B200 engine: torch provides device memory and streams, libbrov.so (C ABI) does the work.
+
+`Engine` is the batched counterpart of the reference's model objects: where the reference evaluates one vehicle per
+Python call (`rov.dynamics`, `simulate_physics`, `multistep_rmse_endpoint_physics`), an Engine call covers N
+vehicles / windows with one kernel launch.  Array conventions follow the reference: a state is a row
+`[x y z phi theta psi u v w p q r]` (or the 13-state quaternion row), an input row is 8 thruster voltages or a
+6-component body wrench.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MODELS = {"thruster8": L.THRUSTER8_LAG3, "wrench12": L.WRENCH_EULER12, "quat13": L.WRENCH_QUAT13}
+DTYPES = {"f64": (L.F64, torch.float64, np.float64), "f32": (L.F32, torch.float32, np.float32)}
+INTEGRATORS = {"rk4": L.RK4, "euler": L.EULER}
+
+
+def default_physical(rho: float = 1000.0) -> np.ndarray:
+    """Scalar attributes of the reference classes as one vector (layout: include/brov.h BROV_PH_*)."""
+    ph = np.zeros(L.NPHYS)
+    L.check(L.lib.brov_default_physical(float(rho), L.dptr(ph)))
+    return ph
+
+
+def derive_params(phys: np.ndarray) -> np.ndarray:
+    """Physical vector(s) [..., NPHYS] -> kernel coefficient vector(s) [..., NKP] (float64, host)."""
+    phys = np.ascontiguousarray(phys, dtype=np.float64)
+    flat = phys.reshape(-1, L.NPHYS)
+    out = np.zeros((flat.shape[0], L.NKP))
+    for i in range(flat.shape[0]):
+        L.check(L.lib.brov_derive_params(L.dptr(flat[i]), L.dptr(out[i])))
+    return out.reshape(phys.shape[:-1] + (L.NKP,))
+
+
+def default_allocation():
+    """(alloc [6,8], r [8,3], dir [8,3]) from the reference's thruster geometry formula."""
+    a, r, d = np.zeros((6, 8)), np.zeros((8, 3)), np.zeros((8, 3))
+    L.check(L.lib.brov_default_allocation(L.dptr(a), L.dptr(r), L.dptr(d)))
+    return a, r, d
+
+
+def lag_discretize(dt: float):
+    """(Ad [3,3], Bd [3]): zero-order hold of the 3rd-order thruster lag at sampling time dt."""
+    Ad, Bd = np.zeros((3, 3)), np.zeros(3)
+    L.check(L.lib.brov_lag_discretize(float(dt), L.dptr(Ad), L.dptr(Bd)))
+    return Ad, Bd
+
+
+@dataclass
+class RolloutResult:
+    xT: torch.Tensor                 # [N, NX]
+    lag: Optional[torch.Tensor]      # [N, NLAG] or None
+    traj: Optional[torch.Tensor]     # [S, N, NX] or None
+
+
+class Engine:
+    def __init__(self, model: str = "thruster8", dtype: str = "f64", device: Optional[int] = None,
+                 rho: float = 1000.0, current: Optional[Sequence[float]] = None):
+        if model not in MODELS:
+            raise ValueError(f"model must be one of {list(MODELS)}")
+        if dtype not in DTYPES:
+            raise ValueError(f"dtype must be one of {list(DTYPES)}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("bluerov2_dynamics_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.model, self.dtype = model, dtype
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._code, self.tdtype, self.ndtype = DTYPES[dtype]
+        self.nx = 13 if model == "quat13" else 12
+        self.nu = 8 if model == "thruster8" else 6
+        self._lag1 = False
+        h = C.c_void_p()
+        L.check(L.lib.brov_create(MODELS[model], self._code, self.device_index, C.byref(h)))
+        self._h = h
+        self._pv = None
+        self._ws = None
+        self.phys = default_physical(rho)
+        if current is not None:
+            self.phys[L.PH_CURRENT:L.PH_CURRENT + 3] = np.asarray(current, float).reshape(3)
+        self.set_physical(self.phys)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib.brov_destroy(h)
+            self._h = None
+
+    # ------------------------------------------------------------------ constants
+    @property
+    def nlag(self) -> int:
+        return 24 if self.model == "thruster8" else (6 if self._lag1 else 0)
+
+    def set_physical(self, phys: np.ndarray) -> None:
+        """Constants shared by all vehicles, from a physical vector (BROV_PH_* layout)."""
+        self.phys = np.array(phys, dtype=np.float64).reshape(L.NPHYS)
+        kp = derive_params(self.phys)
+        L.check(L.lib.brov_set_params(self._h, L.dptr(kp)))
+
+    def set_vehicle_physical(self, phys_table: Optional[np.ndarray]) -> None:
+        """Per-vehicle (Monte-Carlo) constants: phys_table [N, NPHYS] or None to clear."""
+        if phys_table is None:
+            self._pv = None
+            L.check(L.lib.brov_set_vehicle_params(self._h, None, 0))
+            return
+        kp = derive_params(np.asarray(phys_table, float))          # [N, NKP]
+        soa = torch.from_numpy(np.ascontiguousarray(kp.T)).to(self.device, self.tdtype).contiguous()  # [NKP, N]
+        self._pv = soa
+        L.check(L.lib.brov_set_vehicle_params(self._h, soa.data_ptr(), soa.shape[1]))
+
+    def set_wrench_lag1(self, enable: bool, T_lag: Optional[float] = None) -> None:
+        """First-order wrench lag tau_dot = (tau_cmd - tau)/T_lag (extension; wrench models only)."""
+        L.check(L.lib.brov_set_wrench_lag1(self._h, int(bool(enable))))
+        self._lag1 = bool(enable)
+        if T_lag is not None:
+            self.phys[L.PH_TLAG1] = float(T_lag)
+            self.set_physical(self.phys)
+
+    def set_allocation(self, alloc: np.ndarray) -> None:
+        a = np.ascontiguousarray(alloc, dtype=np.float64).reshape(6, 8)
+        L.check(L.lib.brov_set_allocation(self._h, L.dptr(a)))
+
+    def set_lag_discrete(self, dt: float, Ad: np.ndarray, Bd: np.ndarray) -> None:
+        """Override the native ZOH for one dt (e.g. with scipy.signal.cont2discrete's result)."""
+        Ad = np.ascontiguousarray(Ad, dtype=np.float64).reshape(3, 3)
+        Bd = np.ascontiguousarray(Bd, dtype=np.float64).reshape(3)
+        L.check(L.lib.brov_set_lag_discrete(self._h, float(dt), L.dptr(Ad), L.dptr(Bd)))
+
+    # ------------------------------------------------------------------ helpers
+    def tensor(self, a, shape=None) -> torch.Tensor:
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+        t = t.to(device=self.device, dtype=self.tdtype).contiguous()
+        return t if shape is None else t.reshape(shape)
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _check_rows(self, t: torch.Tensor, cols: int, what: str) -> None:
+        if t.dim() != 2 or t.shape[1] != cols:
+            raise ValueError(f"{what} must have shape [N, {cols}], got {tuple(t.shape)}")
+
+    # ------------------------------------------------------------------ device API
+    def rhs(self, x, u, lag: Optional[torch.Tensor] = None, dt: float = 0.02) -> torch.Tensor:
+        """xdot for N vehicles (`rov.dynamics(x, u, dt)`).  For the thruster model `lag` [N,24] is advanced in place
+        by one ThrusterLag.step, as a reference call does; None = zero lag state, nothing carried."""
+        x = self.tensor(x)
+        u = self.tensor(u)
+        self._check_rows(x, self.nx, "x")
+        self._check_rows(u, self.nu, "u")
+        n = x.shape[0]
+        if u.shape[0] != n:
+            raise ValueError("x and u disagree on N")
+        if lag is not None:
+            if lag.dtype != self.tdtype or not lag.is_contiguous() or lag.numel() != n * self.nlag:
+                raise ValueError(f"lag must be a contiguous {self.tdtype} tensor with N*{self.nlag} elements")
+        out = torch.empty((n, self.nx + (6 if self._lag1 else 0)), device=self.device, dtype=self.tdtype)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_rhs(self._h, n, x.data_ptr(), u.data_ptr(), lag.data_ptr() if lag is not None else None,
+                                   float(dt), out.data_ptr(), self._stream()))
+        return out
+
+    def thruster_wrench(self, u, lag: Optional[torch.Tensor] = None, dt: float = 0.02) -> torch.Tensor:
+        """Body wrench of the thruster map (`rov.compute_thruster_forces(u, dt)`), lag advanced in place."""
+        u = self.tensor(u)
+        self._check_rows(u, 8, "u")
+        n = u.shape[0]
+        out = torch.empty((n, 6), device=self.device, dtype=self.tdtype)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_thruster_wrench(self._h, n, u.data_ptr(), lag.data_ptr() if lag is not None else None,
+                                               float(dt), out.data_ptr(), self._stream()))
+        return out
+
+    def rollout(self, x0, U, dt: float = 0.02, integrator: str = "rk4", lag0=None, stride: int = 0,
+                u_layout: str = "auto", step0: int = 0, xT_out: Optional[torch.Tensor] = None,
+                lag_out: Optional[torch.Tensor] = None, traj_out: Optional[torch.Tensor] = None,
+                want_lag: bool = True) -> RolloutResult:
+        """Open-loop rollout of N vehicles (`simulate_physics` batched).
+
+        x0 [N,NX]; U is one of
+          [T,N,NU]  per-vehicle series, time-major     (u_layout "tnc")
+          [T,NU]    one series shared by every vehicle (u_layout "shared")
+          [N,NU]    one constant input per vehicle     (u_layout "const", needs `steps` via U.shape... see below)
+        With u_layout="auto" a 3-D U is "tnc" and a 2-D U is "shared".  For "const" pass U=(tensor [N,NU], steps).
+        stride > 0 stores the state after every stride-th step into traj [T//stride, N, NX].
+        """
+        x0 = self.tensor(x0)
+        self._check_rows(x0, self.nx, "x0")
+        n = x0.shape[0]
+        if u_layout == "const":
+            Ut, steps = U
+            Ut = self.tensor(Ut)
+            self._check_rows(Ut, self.nu, "U")
+            st, sn = 0, self.nu
+        else:
+            Ut = self.tensor(U)
+            if u_layout == "auto":
+                u_layout = "tnc" if Ut.dim() == 3 else "shared"
+            if u_layout == "tnc":
+                if Ut.dim() != 3 or Ut.shape[1] != n or Ut.shape[2] != self.nu:
+                    raise ValueError(f"U must have shape [T, {n}, {self.nu}], got {tuple(Ut.shape)}")
+                st, sn = n * self.nu, self.nu
+            elif u_layout == "shared":
+                self._check_rows(Ut, self.nu, "U")
+                st, sn = self.nu, 0
+            else:
+                raise ValueError("u_layout must be auto|tnc|shared|const")
+            steps = Ut.shape[0]
+        integ = INTEGRATORS[integrator]
+        xT = xT_out if xT_out is not None else torch.empty_like(x0)
+        nlag = self.nlag
+        lag_in = None
+        if nlag and lag0 is not None:
+            lag_in = self.tensor(lag0).reshape(n, nlag)
+        if nlag and want_lag and lag_out is None:
+            lag_out = torch.empty((n, nlag), device=self.device, dtype=self.tdtype)
+        traj = traj_out
+        if stride and traj is None:
+            nsnap = (step0 + steps) // stride - step0 // stride
+            traj = torch.empty((nsnap, n, self.nx), device=self.device, dtype=self.tdtype)
+        d = L.RolloutDesc()
+        d.struct_size = C.sizeof(L.RolloutDesc)
+        d.integrator = integ
+        d.n, d.steps, d.dt = n, steps, float(dt)
+        d.x0_dev, d.xT_dev, d.u_dev = x0.data_ptr(), xT.data_ptr(), Ut.data_ptr()
+        d.u_stride_t, d.u_stride_n = st, sn
+        d.lag_in_dev = lag_in.data_ptr() if lag_in is not None else None
+        d.lag_out_dev = lag_out.data_ptr() if (nlag and lag_out is not None) else None
+        d.traj_dev = traj.data_ptr() if (stride and traj is not None and traj.numel()) else None
+        d.stride = max(int(stride), 1)
+        d.step0 = int(step0)
+        d.snap_base = int(step0) // max(int(stride), 1)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_rollout(self._h, C.byref(d), self._stream()))
+        return RolloutResult(xT=xT, lag=lag_out if nlag else None, traj=traj if stride else None)
+
+    def step(self, x, u, lag=None, dt: float = 0.02, integrator: str = "rk4") -> RolloutResult:
+        """One integrator step for N vehicles (u [N,NU])."""
+        return self.rollout(x, (u, 1), dt=dt, integrator=integrator, lag0=lag, u_layout="const")
+
+    def multistep_se(self, X, U, horizons: Sequence[int], dt: float = 0.02, integrator: str = "rk4",
+                     lag0=None, n_windows: Optional[int] = None):
+        """Sum of squared endpoint errors per horizon over sliding windows of one recorded series.
+        Returns (se [MAX_H] float64 device tensor, counts list).  See brov_multistep_se in include/brov.h."""
+        X = self.tensor(X)
+        U = self.tensor(U)
+        self._check_rows(X, self.nx, "X")
+        self._check_rows(U, self.nu, "U")
+        rows = X.shape[0]
+        if U.shape[0] != rows:
+            raise ValueError("X and U must have the same number of rows")
+        hs = [int(h) for h in horizons]
+        if not 1 <= len(hs) <= L.MAX_H or any(h < 1 for h in hs) or sorted(set(hs)) != hs:
+            raise ValueError(f"horizons must be 1..{L.MAX_H} strictly ascending positive integers")
+        nwin = max(rows - hs[0], 0) if n_windows is None else int(n_windows)
+        nbytes = L.lib.brov_se_workspace_bytes(nwin)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        se = torch.zeros(L.MAX_H, dtype=torch.float64, device=self.device)
+        counts = (C.c_longlong * L.MAX_H)()
+        d = L.SeDesc()
+        d.struct_size = C.sizeof(L.SeDesc)
+        d.integrator = INTEGRATORS[integrator]
+        d.rows, d.n_windows, d.dt = rows, nwin, float(dt)
+        d.X_dev, d.U_dev = X.data_ptr(), U.data_ptr()
+        lag_t = None
+        if lag0 is not None:
+            lag_t = self.tensor(lag0).reshape(nwin, 24)
+        d.lag0_dev = lag_t.data_ptr() if lag_t is not None else None
+        d.n_horizons = len(hs)
+        for i, h in enumerate(hs):
+            d.horizons[i] = h
+        d.se_out_dev = se.data_ptr()
+        d.count_out = counts
+        d.workspace_dev = self._ws.data_ptr()
+        d.workspace_bytes = nbytes
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_multistep_se(self._h, C.byref(d), self._stream()))
+        return se, [int(counts[i]) for i in range(len(hs))]
+
+    def multistep_rmse(self, X, U, horizons, dt: float = 0.02, integrator: str = "rk4", lag0=None):
+        """RMSE per horizon, `sqrt(se / (n_windows * n_states))`, NaN where no window fits (reference semantics)."""
+        single = np.isscalar(horizons)
+        hs = [int(horizons)] if single else [int(h) for h in horizons]
+        order = sorted(set(hs))
+        out = {}
+        for i in range(0, len(order), L.MAX_H):
+            part = order[i:i + L.MAX_H]
+            se, cnt = self.multistep_se(X, U, part, dt, integrator, lag0)
+            se = se.cpu().numpy()
+            for j, h in enumerate(part):
+                out[h] = float(np.sqrt(se[j] / (cnt[j] * self.nx))) if cnt[j] > 0 else float("nan")
+        return out[hs[0]] if single else [out[h] for h in hs]
+
+    # ------------------------------------------------------------------ host-buffer API (end-to-end path)
+    def rollout_host(self, x0: np.ndarray, U: np.ndarray, dt: float = 0.02, integrator: str = "rk4",
+                     lag0: Optional[np.ndarray] = None, stride: int = 0, chunk_steps: int = 0,
+                     out_xT: Optional[np.ndarray] = None, out_traj: Optional[np.ndarray] = None,
+                     out_lag: Optional[np.ndarray] = None):
+        """Rollout with every array in HOST memory (numpy, engine dtype, C-contiguous; pinned memory overlaps the
+        copies).  Inputs stream to the device in time chunks, double buffered against the kernels.
+        U [T,N,NU] or [T,NU] (shared).  Returns (xT, lag or None, traj or None) as numpy arrays."""
+        def host(a, what):
+            if not isinstance(a, np.ndarray) or a.dtype != self.ndtype or not a.flags.c_contiguous:
+                raise ValueError(f"{what} must be a C-contiguous numpy array of dtype {np.dtype(self.ndtype)}")
+            return a
+        x0 = host(x0, "x0")
+        U = host(U, "U")
+        n = x0.shape[0]
+        if x0.shape != (n, self.nx):
+            raise ValueError(f"x0 must be [N, {self.nx}]")
+        shared = U.ndim == 2
+        if (shared and U.shape[1] != self.nu) or (not shared and U.shape[1:] != (n, self.nu)):
+            raise ValueError("U must be [T, N, NU] or [T, NU]")
+        steps = U.shape[0]
+        xT = out_xT if out_xT is not None else np.empty_like(x0)
+        nlag = self.nlag
+        lag_out = None
+        if nlag:
+            lag_out = out_lag if out_lag is not None else np.empty((n, nlag), dtype=self.ndtype)
+        traj = None
+        if stride:
+            traj = out_traj if out_traj is not None else np.empty((steps // stride, n, self.nx), dtype=self.ndtype)
+        d = L.RolloutHostDesc()
+        d.struct_size = C.sizeof(L.RolloutHostDesc)
+        d.integrator = INTEGRATORS[integrator]
+        d.n, d.steps, d.dt = n, steps, float(dt)
+        d.x0_host, d.xT_host, d.u_host = x0.ctypes.data, host(xT, "out_xT").ctypes.data, U.ctypes.data
+        d.u_shared = int(shared)
+        d.lag_in_host = host(lag0, "lag0").ctypes.data if (nlag and lag0 is not None) else None
+        d.lag_out_host = lag_out.ctypes.data if lag_out is not None else None
+        d.traj_host = host(traj, "out_traj").ctypes.data if traj is not None else None
+        d.stride = max(int(stride), 1)
+        d.chunk_steps = int(chunk_steps)
+        L.check(L.lib.brov_rollout_host(self._h, C.byref(d)))
+        return xT, lag_out, traj
+
+
+def reduced9_rhs(x: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """bluerov_compute RHS on CUDA tensors x [B,9], u [B,4] (float32 or float64)."""
+    if x.dtype not in (torch.float32, torch.float64) or u.dtype != x.dtype:
+        raise TypeError("x and u must both be float32 or both float64")
+    if not x.is_cuda or not u.is_cuda:
+        raise RuntimeError("reduced9_rhs expects CUDA tensors")
+    x = x.contiguous()
+    u = u.contiguous()
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        L.check(L.lib.brov_reduced9_rhs(L.F32 if x.dtype == torch.float32 else L.F64, x.data_ptr(), u.data_ptr(),
+                                        out.data_ptr(), x.shape[0], torch.cuda.current_stream(x.device).cuda_stream))
+    return out
+
+
+def fma_peak(dtype: str = "f32", device: int = 0, iters: int = 4096):
+    """(TFLOP/s, ms) of an FMA-chain microbenchmark: the measured FP pipe peak of this GPU."""
+    tf, ms = C.c_double(), C.c_double()
+    L.check(L.lib.brov_fma_peak(DTYPES[dtype][0], int(device), int(iters), C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """Pinned (page-locked) host numpy array, via torch's allocator."""
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+    t = torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
+    a = t.numpy()
+    a.setflags(write=True)
+    return a

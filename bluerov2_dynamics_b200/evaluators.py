@@ -1,0 +1,69 @@
+"""Drop-in versions of the free functions the reference's training scripts define around the models:
+`simulate_physics`, `one_step_rmse_physics`, `multistep_rmse_endpoint_physics` (training/train_tank_brov2_rk4.py:375-417
+and the Euler twins in train_tank_brov2_full_comparison.py:453-487, train_tank_brov2_koopmanEDMDc.py:222-283,
+train_tank_brov2_wrench_comp.py:208-250, train_tank_brov2_wrench_quat.py:249-297).
+
+The reference picks the integrator by which script the function sits in (RK4 in train_tank_brov2_rk4.py, explicit
+Euler everywhere else); here it is the `integrator` argument.  One kernel launch replaces the Python loop over
+steps (rollout) or the double loop over windows and steps (evaluators)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .fossen.BlueROV2 import BlueROV2 as _Thruster
+
+
+def _model_of(rov):
+    return rov._MODEL
+
+
+def simulate_physics(x0: np.ndarray, U_seq: np.ndarray, dt: float, rov, integrator: str = "rk4") -> np.ndarray:
+    """Open-loop rollout of one vehicle under the recorded inputs; returns the trajectory [len(U_seq)+1, n_states]
+    with row 0 = x0.  For the 8-thruster model the rollout starts from, and leaves behind, `rov`'s lag state — as the
+    reference's loop over `rov.dynamics` does."""
+    x0 = np.asarray(x0, dtype=float)
+    U_seq = np.asarray(U_seq, dtype=float)
+    eng = rov.engine("f64")
+    H = len(U_seq)
+    traj = np.zeros((H + 1, x0.shape[0]))
+    traj[0] = x0
+    if H == 0:
+        return traj
+    lag0 = rov._lag_tensor(eng) if isinstance(rov, _Thruster) else None
+    res = eng.rollout(x0.reshape(1, -1), U_seq.reshape(H, eng.nu), dt=dt, integrator=integrator, lag0=lag0, stride=1,
+                      u_layout="shared")
+    traj[1:] = res.traj[:, 0, :].cpu().numpy()
+    if lag0 is not None:
+        rov._store_lag(res.lag, dt)
+    return traj
+
+
+def _engine_for(X_test, model, dtype, engine):
+    if engine is not None:
+        return engine
+    if model is None:
+        model = "quat13" if np.shape(X_test)[1] == 13 else "thruster8"
+    return Engine(model, dtype)
+
+
+def multistep_rmse_endpoint_physics(X_test: np.ndarray, U_test: np.ndarray, H, dt: float, model: str = None,
+                                    integrator: str = "rk4", dtype: str = "f64", engine: Engine = None):
+    """Strict H-step-ahead endpoint RMSE over all sliding windows of a recorded series:
+    sqrt(sum_k |sim(X[k], U[k:k+H])[-1] - X[k+H]|^2 / ((T-H) * n_states)), NaN if T <= H.
+    `H` may be a list: all horizons share one pass.  Every window starts from zero thruster-lag state (the reference
+    lets the lag state leak from window to window because it reuses one model object — SURVEY trap T3)."""
+    eng = _engine_for(X_test, model, dtype, engine)
+    return eng.multistep_rmse(X_test, U_test, H, dt=dt, integrator=integrator)
+
+
+def one_step_rmse_physics(X_test: np.ndarray, U_test: np.ndarray, dt: float, model: str = None, dtype: str = "f64",
+                          engine: Engine = None) -> float:
+    """Teacher-forced one-step Euler prediction RMSE, rmse(X[1:], X[:-1] + dt f(X[:-1], U[:-1]))."""
+    eng = _engine_for(X_test, model, dtype, engine)
+    return eng.multistep_rmse(X_test, U_test, 1, dt=dt, integrator="euler")
+
+
+def rmse(y_true: np.ndarray, y_pred: np.ndarray) -> float:
+    return float(np.sqrt(np.mean((np.asarray(y_true) - np.asarray(y_pred)) ** 2)))

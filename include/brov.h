@@ -1,0 +1,208 @@
+/* brov.h — C ABI of libbrov.so, the B200 (sm_100a) batched BlueROV2 Fossen-dynamics engine.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference (ViktorNfa/bluerov2_dynamics) is pure
+ * Python and has no FFI layer; what it offers instead is a Python call surface, and each entry point below is what
+ * a binding of that surface calls (the ctypes stub a maintainer would add is shown in INTEGRATION.md and lives in
+ * bluerov2_dynamics_b200/_lib.py).  Citations are file:line in the reference checkout.
+ *
+ * Conventions
+ *   - plain C types only; every array is row-major and contiguous; "dev" pointers are device pointers valid in the
+ *     calling process's primary CUDA context on the engine's device, "host" pointers are host pointers;
+ *   - arrays have the engine's scalar type (float for BROV_F32, double for BROV_F64) unless typed otherwise;
+ *   - every call returns 0 on success, a negative BROV_E* code otherwise; brov_last_error() describes the last
+ *     failure on the calling thread;
+ *   - device calls are asynchronous on `stream` (a cudaStream_t cast to void*; NULL = legacy default stream);
+ *   - an engine handle is not thread-safe; use one per stream.
+ *
+ * State layouts (same as the reference)
+ *   BROV_THRUSTER8_LAG3  x[12] = [x y z phi theta psi u v w p q r], input u[8] = normalised thruster voltages,
+ *                        hidden lag state lag[8][3] (ThrusterLag._x of each thruster)     fossen/BlueROV2.py:357-400
+ *   BROV_WRENCH_EULER12  x[12] as above, input tau[6] = body wrench                    fossen/BlueROV2_thrust.py:235
+ *   BROV_WRENCH_QUAT13   x[13] = [x y z qw qx qy qz u v w p q r], input tau[6]         fossen/BlueROV2_wrench.py:322
+ *   With the optional first-order wrench lag enabled (extension, no reference counterpart) the two wrench models
+ *   carry a hidden state lag[6] = filtered wrench.
+ */
+#ifndef BROV_H
+#define BROV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BROV_ABI_VERSION 1
+
+enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2 };
+enum { BROV_F64 = 0, BROV_F32 = 1 };
+enum { BROV_RK4 = 0, BROV_EULER = 1 };
+
+enum {
+    BROV_OK = 0,
+    BROV_EINVAL = -1,   /* bad argument */
+    BROV_ECUDA = -2,    /* CUDA runtime error (text in brov_last_error) */
+    BROV_ENOMEM = -3,
+    BROV_EUNSUPPORTED = -4
+};
+
+/* Physical parameter vector (double[BROV_NPHYS]): the scalar attributes of the reference classes
+ * (fossen/BlueROV2.py:81-150 = BlueROV2_thrust.py:82-147 = BlueROV2_wrench.py:160-225). */
+enum {
+    BROV_PH_M = 0, BROV_PH_W = 1, BROV_PH_B = 2,
+    BROV_PH_XB = 3, /* xb yb zb */
+    BROV_PH_I = 6,  /* Ix Iy Iz */
+    BROV_PH_ADDED = 9,   /* Xu_dot Yv_dot Zw_dot Kp_dot Mq_dot Nr_dot */
+    BROV_PH_LIN = 15,    /* Xu Yv Zw Kp Mq Nr */
+    BROV_PH_QUAD = 21,   /* Xu_abs ... Nr_abs */
+    BROV_PH_MINV = 27,   /* diag(Minv): kept separate because the reference freezes Minv in __init__ (trap T5) */
+    BROV_PH_CURRENT = 33,/* current_speed, NED */
+    BROV_PH_TLAG1 = 36,  /* first-order wrench lag time constant [s] (extension) */
+    BROV_NPHYS = 37
+};
+/* Kernel coefficient vector (double[BROV_NKP]) derived from the physical one; layout in csrc/brov_device.cuh. */
+#define BROV_NKP 36
+#define BROV_MAX_H 4
+
+typedef struct brov_engine brov_engine_t;
+
+int brov_abi_version(void);
+const char* brov_last_error(void);
+
+/* Engine lifetime.  Replaces `BlueROV2(rho=..., current_speed=...)` (fossen/BlueROV2.py:79): the new engine holds
+ * the reference constants, the reference thruster geometry and the reference lag model. */
+int brov_create(int model, int dtype, int device, brov_engine_t** out);
+void brov_destroy(brov_engine_t* e);
+
+/* Constants. */
+int brov_default_physical(double rho, double* phys /*[BROV_NPHYS]*/);          /* fossen/BlueROV2.py:81-150 */
+int brov_derive_params(const double* phys /*[BROV_NPHYS]*/, double* kp /*[BROV_NKP]*/);
+int brov_default_allocation(double* alloc /*[6][8]*/, double* r /*[8][3] or NULL*/, double* dir /*[8][3] or NULL*/);
+                                                                                /* fossen/BlueROV2.py:159-232 */
+int brov_set_params(brov_engine_t* e, const double* kp /*[BROV_NKP]*/);
+int brov_get_params(const brov_engine_t* e, double* kp /*[BROV_NKP]*/);
+int brov_set_allocation(brov_engine_t* e, const double* alloc /*[6][8]*/);
+/* Per-vehicle (Monte-Carlo) coefficient table, dev, engine scalar type, layout [BROV_NKP][n]; NULL clears it.
+ * The table is borrowed, not copied: it must outlive the calls that use it. */
+int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n);
+/* Optional first-order wrench lag tau_dot = (tau_cmd - tau)/T_lag for the two wrench models (extension). */
+int brov_set_wrench_lag1(brov_engine_t* e, int enable);
+
+/* ThrusterLag discretisation (fossen/BlueROV2.py:490-501: scipy cont2discrete(zoh)).  `discretize` computes the
+ * zero-order hold natively (matrix exponential, extended precision); `set_lag_discrete` overrides (Ad, Bd) for one
+ * dt, e.g. with scipy's own result. */
+int brov_lag_discretize(double dt, double* Ad /*[3][3]*/, double* Bd /*[3]*/);
+int brov_set_lag_discrete(brov_engine_t* e, double dt, const double* Ad, const double* Bd);
+
+/* One state-derivative evaluation for n vehicles — `rov.dynamics(x, u, dt)` (fossen/BlueROV2.py:357,
+ * BlueROV2_thrust.py:235, BlueROV2_wrench.py:322).  x [n][NX], u [n][NU], xdot [n][NX] (NX+6 with the wrench lag:
+ * the last 6 are tau_dot).  lag_inout [n][NLAG] or NULL: for the thruster model the lag state is read, advanced by
+ * ONE ThrusterLag.step and written back, exactly as a reference dynamics() call mutates it (NULL = zero state,
+ * nothing written). */
+int brov_rhs(brov_engine_t* e, long long n, const void* x_dev, const void* u_dev, void* lag_inout_dev, double dt,
+             void* xdot_dev, void* stream);
+
+/* Thruster map alone — `rov.compute_thruster_forces(u_thrust, dt)` (fossen/BlueROV2.py:265-278): voltages -> T200
+ * polynomial -> ONE ThrusterLag.step per thruster -> body wrench.  u [n][8], lag_inout [n][8][3] or NULL (zero state,
+ * nothing written), tau [n][6].  BROV_THRUSTER8_LAG3 engines only. */
+int brov_thruster_wrench(brov_engine_t* e, long long n, const void* u_dev, void* lag_inout_dev, double dt,
+                         void* tau_dev, void* stream);
+
+/* Open-loop rollout — `simulate_physics(x0, U_seq, dt, rov)` for n vehicles at once
+ * (RK4: training/train_tank_brov2_rk4.py:375-396; Euler: training/train_tank_brov2_full_comparison.py:453-466,
+ * quaternion re-normalisation per step: training/train_tank_brov2_wrench_quat.py:262-263).
+ * Input element (step k, vehicle i, channel j) is read at u[k*u_stride_t + i*u_stride_n + j] (strides in scalars):
+ *   per-vehicle series, time-major  [steps][n][NU] : u_stride_t = n*NU, u_stride_n = NU
+ *   one series shared by all        [steps][NU]    : u_stride_t = NU,   u_stride_n = 0
+ *   one constant input per vehicle  [n][NU]        : u_stride_t = 0,    u_stride_n = NU
+ * With an RK4 step the thruster lag advances four times per step (once per stage) as in the reference.
+ * traj (optional): state after global step g = step0+k+1 is stored when g % stride == 0, as snapshot
+ * s = g/stride - 1 at traj[(s - snap_base)][n][NX].  Chunked rollouts pass xT/lag_out of one call as x0/lag_in of
+ * the next and advance step0. */
+typedef struct brov_rollout_desc {
+    uint32_t struct_size;       /* = sizeof(brov_rollout_desc) */
+    int32_t integrator;
+    long long n;
+    long long steps;
+    double dt;
+    const void* x0_dev;         /* [n][NX] */
+    void* xT_dev;               /* [n][NX], may alias x0_dev */
+    const void* u_dev;
+    long long u_stride_t, u_stride_n;
+    const void* lag_in_dev;     /* [n][NLAG] or NULL = zeros */
+    void* lag_out_dev;          /* [n][NLAG] or NULL */
+    void* traj_dev;             /* or NULL */
+    long long stride;           /* >= 1 when traj_dev != NULL */
+    long long step0;
+    long long snap_base;
+} brov_rollout_desc;
+int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* stream);
+
+/* Multi-step endpoint squared error over sliding windows — `multistep_rmse_endpoint_physics(X, U, H, dt)`
+ * (training/train_tank_brov2_rk4.py:399-417 and the Euler twins in train_tank_brov2_full_comparison.py:469-487,
+ * train_tank_brov2_wrench_comp.py:232-250, train_tank_brov2_wrench_quat.py:279-297) for up to BROV_MAX_H horizons in
+ * one pass; with H = {1} and BROV_EULER it is also `one_step_rmse_physics`.
+ * X [rows][NX], U [rows][NU]: one recorded series.  Window k in [0, n_windows) starts at X[k] and is driven by
+ * U[k..]; it contributes to horizon H_h iff k + H_h <= rows-1.  se_out_dev[h] (double[BROV_MAX_H], dev) receives the
+ * sum over windows of |x_end - X[k+H_h]|^2; count_out[h] (host, may be NULL) the number of contributing windows;
+ * rmse_h = sqrt(se_h / (count_h * NX)).  lag0_dev [n_windows][24] or NULL: initial lag state per window (the
+ * reference shares ONE model object over all windows so its lag state leaks from window to window, SURVEY trap T3;
+ * this evaluator is window-parallel and starts each window from lag0, default zero).
+ * workspace_dev: at least brov_se_workspace_bytes(n_windows) bytes. */
+typedef struct brov_se_desc {
+    uint32_t struct_size;
+    int32_t integrator;
+    long long rows;
+    long long n_windows;
+    double dt;
+    const void* X_dev;
+    const void* U_dev;
+    const void* lag0_dev;
+    int32_t n_horizons;
+    int32_t horizons[BROV_MAX_H];   /* strictly ascending, >= 1 */
+    double* se_out_dev;             /* [BROV_MAX_H] */
+    long long* count_out;           /* host [BROV_MAX_H] or NULL */
+    void* workspace_dev;
+    size_t workspace_bytes;
+} brov_se_desc;
+size_t brov_se_workspace_bytes(long long n_windows);
+int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* stream);
+
+/* Reduced 9-state RHS — `bluerov_compute(t, x_, u_)` (fossen/bluerov_torch.py:20-67, constants fossen/parameters.py).
+ * x [B][9], u [B][4], out [B][9]. */
+int brov_reduced9_rhs(int dtype, const void* x_dev, const void* u_dev, void* out_dev, long long B, void* stream);
+
+/* Host-buffer rollout: the same operation as brov_rollout with every array in HOST memory (pinned memory gives
+ * asynchronous copies).  The engine streams the inputs to the device in time chunks on a copy stream, double
+ * buffered against the rollout kernels, and copies snapshots and final state back; it returns after everything has
+ * landed in the host arrays.  u_host is time-major [steps][n][NU] (u_shared = 0) or [steps][NU] (u_shared = 1). */
+typedef struct brov_rollout_host_desc {
+    uint32_t struct_size;
+    int32_t integrator;
+    long long n;
+    long long steps;
+    double dt;
+    const void* x0_host;        /* [n][NX] */
+    void* xT_host;              /* [n][NX] */
+    const void* u_host;
+    int32_t u_shared;
+    int32_t reserved;
+    const void* lag_in_host;    /* or NULL */
+    void* lag_out_host;         /* or NULL */
+    void* traj_host;            /* [steps/stride][n][NX] or NULL */
+    long long stride;
+    long long chunk_steps;      /* 0 = choose (about 256 MiB of inputs per chunk) */
+} brov_rollout_host_desc;
+int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc* d);
+
+/* Pinned host memory helpers for brov_rollout_host callers without their own allocator. */
+int brov_host_alloc(size_t bytes, void** out);
+int brov_host_free(void* p);
+
+/* FMA-chain microbenchmark on `device`: the FP32 / FP64 pipe peak used as roofline denominator. */
+int brov_fma_peak(int dtype, int device, int iters, double* tflops_out, double* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BROV_H */

@@ -1,0 +1,458 @@
+"""GPU parity tests: the CUDA engine (through the C ABI, via bluerov2_dynamics_b200.Engine) against
+ (a) the frozen outputs of the unmodified reference (tests/golden/reference_vectors.npz), and
+ (b) the numpy oracle (oracle/fossen_np.py) on seeded inputs at sizes the oracle finishes in seconds.
+
+Tolerances (BASELINE.json north_star): fp64 <= 1e-10 normwise relative, ||a-b||_inf / max(||b||_inf, 1);
+fp32 <= 1e-4 after 1000 steps."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import normwise
+from oracle import fossen_np as O
+
+pytestmark = pytest.mark.gpu
+
+DT = 0.02
+TOL64 = 1e-10
+TOL32 = 1e-4
+
+
+@pytest.fixture(scope="module")
+def B():
+    import bluerov2_dynamics_b200 as b
+    return b
+
+
+def cpu(t):
+    return t.detach().cpu().numpy().astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------------------ RHS
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 2e-5)])
+@pytest.mark.parametrize("tag", ["", "_cur"])
+def test_rhs_against_reference(B, golden, dtype, tol, tag):
+    cur = golden["rhs_current"] if tag else None
+    e = B.Engine("thruster8", dtype, current=cur)
+    lag = e.tensor(golden["rhs_thr_lag0"].reshape(-1, 24)).clone()
+    xd = e.rhs(golden["rhs_thr_x"], golden["rhs_thr_u"], lag=lag, dt=DT)
+    assert normwise(cpu(xd), golden[f"rhs_thr{tag}_xdot"]) < tol
+    assert normwise(cpu(lag).reshape(-1, 8, 3), golden[f"rhs_thr{tag}_lag1"]) < tol
+    e = B.Engine("wrench12", dtype, current=cur)
+    assert normwise(cpu(e.rhs(golden["rhs_thr_x"], golden["rhs_w_tau"])), golden[f"rhs_w12{tag}_xdot"]) < tol
+    e = B.Engine("quat13", dtype, current=cur)
+    assert normwise(cpu(e.rhs(golden["rhs_q13_x"], golden["rhs_w_tau"])), golden[f"rhs_q13{tag}_xdot"]) < tol
+
+
+def test_rhs_without_lag_buffer_is_fresh_lag(B, golden):
+    e = B.Engine("thruster8", "f64")
+    n = 32  # first half of the golden set starts from zero lag
+    xd = e.rhs(golden["rhs_thr_x"][:n], golden["rhs_thr_u"][:n], lag=None, dt=DT)
+    assert normwise(cpu(xd), golden["rhs_thr_xdot"][:n]) < 1e-12
+
+
+def test_thruster_wrench_matches_oracle(B, golden):
+    e = B.Engine("thruster8", "f64")
+    u = golden["rhs_thr_u"]
+    lag0 = golden["rhs_thr_lag0"]
+    lag = e.tensor(lag0.reshape(-1, 24)).clone()
+    tau = cpu(e.thruster_wrench(u, lag=lag, dt=DT))
+    Ad, Bd = O.lag_zoh(DT)
+    tau_o, lag_o = O.thruster_wrench(u, lag0, Ad, Bd, O.thruster_geometry()[2])
+    assert normwise(tau, tau_o) < 1e-12
+    assert normwise(cpu(lag).reshape(-1, 8, 3), lag_o) < 1e-12
+
+
+def test_trig_range_reduction_large_angles(B):
+    """yaw winds up without bound in long rollouts; the kernels' own sincos must stay accurate far from 0."""
+    rng = np.random.default_rng(7)
+    n = 4096
+    x = np.zeros((n, 12))
+    x[:, 3:6] = rng.uniform(-1, 1, (n, 3)) * np.array([1.0, 1.0, 1.0]) * 10.0 ** rng.uniform(-3, 4, (n, 1))
+    x[:, 6:] = rng.uniform(-1, 1, (n, 6))
+    tau = rng.uniform(-10, 10, (n, 6))
+    ref = O.rhs_wrench12(x, tau, O.default_params())
+    ok = np.abs(np.cos(x[:, 4])) > 1e-2  # away from the Euler-angle singularity, where the RHS is ill-conditioned
+    got = cpu(B.Engine("wrench12", "f64").rhs(x, tau))
+    assert normwise(got[ok], ref[ok]) < 1e-12
+    x32 = x.astype(np.float32).astype(np.float64)  # same rounded angles for both sides
+    ref32 = O.rhs_wrench12(x32, tau.astype(np.float32).astype(np.float64), O.default_params())
+    got32 = cpu(B.Engine("wrench12", "f32").rhs(x32, tau))
+    assert normwise(got32[ok], ref32[ok]) < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ cfg 1
+@pytest.mark.parametrize("dtype,tol", [("f64", TOL64), ("f32", TOL32)])
+def test_cfg1_thruster_rk4_1000_steps(B, golden, dtype, tol):
+    e = B.Engine("thruster8", dtype)
+    x0 = golden["cfg1_x0"][None]
+    U = np.tile(golden["cfg1_u_const"], (1000, 1))
+    r = e.rollout(x0, U, dt=DT, integrator="rk4", stride=10)
+    assert normwise(cpu(r.traj)[:, 0], golden["cfg1_const_traj_s10"][1:]) < tol
+    assert normwise(cpu(r.lag).reshape(8, 3), golden["cfg1_const_lagT"]) < tol
+    # same thing with one constant input row per vehicle
+    r2 = e.rollout(x0, (golden["cfg1_u_const"][None], 1000), dt=DT, u_layout="const")
+    assert torch.equal(r2.xT, r.xT)
+    r = e.rollout(x0, golden["cfg1_U_var"], dt=DT, integrator="rk4", stride=10)
+    assert normwise(cpu(r.traj)[:, 0], golden["cfg1_var_traj_s10"][1:]) < tol
+    assert normwise(cpu(r.lag).reshape(8, 3), golden["cfg1_var_lagT"]) < tol
+
+
+def test_cfg1_euler_dt001(B, golden):
+    e = B.Engine("thruster8", "f64")
+    U = np.tile(golden["cfg1_u_const"], (500, 1))
+    r = e.rollout(golden["cfg1_x0"][None], U, dt=0.01, integrator="euler", stride=10)
+    assert normwise(cpu(r.traj)[:, 0], golden["cfg1_euler_dt001_traj_s10"][1:]) < TOL64
+    assert normwise(cpu(r.lag).reshape(8, 3), golden["cfg1_euler_dt001_lagT"]) < TOL64
+
+
+def test_scipy_zoh_override_is_equivalent(B, golden):
+    e = B.Engine("thruster8", "f64")
+    e.set_lag_discrete(DT, golden["const_lag_Ad_0.02"], golden["const_lag_Bd_0.02"])
+    r = e.rollout(golden["cfg1_x0"][None], golden["cfg1_U_var"], dt=DT, stride=10)
+    assert normwise(cpu(r.traj)[:, 0], golden["cfg1_var_traj_s10"][1:]) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ ensembles
+ENS = [("thruster8", "rk4", "ens_x0", "ens_U8", "ens_thr_rk4_s20"),
+       ("thruster8", "euler", "ens_x0", "ens_U8", "ens_thr_euler_s20"),
+       ("wrench12", "rk4", "ens_x0", "ens_W6", "ens_w12_rk4_s20"),
+       ("wrench12", "euler", "ens_x0", "ens_W6", "ens_w12_euler_s20"),
+       ("quat13", "rk4", "ens_x0_q13", "ens_W6", "ens_q13_rk4_s20"),
+       ("quat13", "euler", "ens_x0_q13", "ens_W6", "ens_q13_euler_s20")]
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", TOL64), ("f32", TOL32)])
+@pytest.mark.parametrize("kind,integ,x0k,uk,outk", ENS)
+def test_ensembles_against_reference(B, golden, dtype, tol, kind, integ, x0k, uk, outk):
+    e = B.Engine(kind, dtype)
+    U = np.ascontiguousarray(np.transpose(golden[uk], (1, 0, 2)))
+    r = e.rollout(golden[x0k], U, dt=DT, integrator=integ, stride=20)
+    ref = np.transpose(golden[outk], (1, 0, 2))[1:]
+    assert normwise(cpu(r.traj), ref) < tol
+    assert normwise(cpu(r.xT), ref[-1]) < tol
+    if kind == "thruster8":
+        assert normwise(cpu(r.lag).reshape(-1, 8, 3), golden[f"ens_thr_{integ}_lagT"]) < tol
+
+
+def _mc_phys(B, scales):
+    ph = np.tile(B.default_physical(), (scales.shape[0], 1))
+    from bluerov2_dynamics_b200 import _lib as L
+    ph[:, L.PH_ADDED:L.PH_ADDED + 6] *= scales[:, :6]
+    ph[:, L.PH_LIN:L.PH_LIN + 6] *= scales[:, 6:12]
+    ph[:, L.PH_QUAD:L.PH_QUAD + 6] *= scales[:, 12:18]
+    m = ph[:, L.PH_M:L.PH_M + 1]
+    ph[:, L.PH_MINV:L.PH_MINV + 3] = 1.0 / (m - ph[:, L.PH_ADDED:L.PH_ADDED + 3])
+    ph[:, L.PH_MINV + 3:L.PH_MINV + 6] = 1.0 / (ph[:, L.PH_I:L.PH_I + 3] - ph[:, L.PH_ADDED + 3:L.PH_ADDED + 6])
+    return ph
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", TOL64), ("f32", TOL32)])
+def test_monte_carlo_vehicle_params(B, golden, dtype, tol):
+    ph = _mc_phys(B, golden["mc_scales"])
+    U = np.ascontiguousarray(np.transpose(golden["mc_W6"], (1, 0, 2)))
+    for kind, x0k, outk in (("wrench12", "mc_x0", "mc_w12_rk4_xT"), ("quat13", "mc_x0_q13", "mc_q13_rk4_xT")):
+        e = B.Engine(kind, dtype)
+        e.set_vehicle_physical(ph)
+        r = e.rollout(golden[x0k], U, dt=DT, integrator="rk4")
+        assert normwise(cpu(r.xT), golden[outk]) < tol
+        e.set_vehicle_physical(None)
+
+
+# ------------------------------------------------------------------------------------------------ evaluators
+def test_multistep_rmse_against_reference(B, golden):
+    HS = [int(h) for h in golden["rmse_H"]]
+    X, U8, W6, Xq = golden["rmse_X12"], golden["rmse_U8"], golden["rmse_W6"], golden["rmse_X13"]
+    e = B.Engine("thruster8", "f64")
+    assert np.allclose(e.multistep_rmse(X, U8, HS, dt=DT, integrator="rk4"), golden["rmse_thr_rk4_reset"], rtol=1e-10)
+    assert np.allclose(e.multistep_rmse(X, U8, HS, dt=DT, integrator="euler"), golden["rmse_thr_euler_reset"], rtol=1e-10)
+    assert np.isclose(e.multistep_rmse(X, U8, 1, dt=DT, integrator="euler"), golden["rmse_thr_onestep_reset"], rtol=1e-10)
+    e = B.Engine("wrench12", "f64")
+    assert np.allclose(e.multistep_rmse(X, W6, HS, dt=DT, integrator="euler"), golden["rmse_w12_euler"], rtol=1e-10)
+    assert np.isclose(e.multistep_rmse(X, W6, 1, dt=DT, integrator="euler"), golden["rmse_w12_onestep"], rtol=1e-10)
+    e = B.Engine("quat13", "f64")
+    assert np.allclose(e.multistep_rmse(Xq, W6, HS, dt=DT, integrator="euler"), golden["rmse_q13_euler"], rtol=1e-10)
+    assert np.isclose(e.multistep_rmse(Xq, W6, 1, dt=DT, integrator="euler"), golden["rmse_q13_onestep"], rtol=1e-10)
+    # horizon by horizon == all horizons in one pass; too-short series -> NaN as the reference
+    e = B.Engine("wrench12", "f64")
+    one_pass = e.multistep_rmse(X, W6, HS, dt=DT, integrator="euler")
+    assert one_pass == [e.multistep_rmse(X, W6, h, dt=DT, integrator="euler") for h in HS]
+    assert np.isnan(e.multistep_rmse(X[:5], W6[:5], 10, dt=DT, integrator="euler"))
+    # fp32 evaluator
+    e = B.Engine("thruster8", "f32")
+    assert np.allclose(e.multistep_rmse(X, U8, HS, dt=DT, integrator="rk4"), golden["rmse_thr_rk4_reset"], rtol=1e-4)
+
+
+def test_multistep_rmse_lag_carry_via_lag0(B, golden):
+    """The reference's literal semantics (one model object, lag state leaking across windows, trap T3) are
+    reproduced by handing the evaluator the carried lag state of every window, computed by the oracle's
+    sequential recurrence (it depends on the inputs only)."""
+    X, U = golden["rmse_X12"], golden["rmse_U8"]
+    H = 10
+    ns = len(X) - H
+    Ad, Bd = O.lag_zoh(DT)
+    lag = np.zeros((1, 8, 3))
+    lag0 = np.zeros((ns, 8, 3))
+    for k in range(ns):
+        lag0[k] = lag[0]
+        for j in range(H):
+            F = O.thrust_poly(U[k + j:k + j + 1])
+            for _ in range(4):
+                lag, _ = O.lag_step(lag, F, Ad, Bd)
+    e = B.Engine("thruster8", "f64")
+    se, cnt = e.multistep_se(X, U, [H], dt=DT, integrator="rk4", lag0=lag0.reshape(ns, 24), n_windows=ns)
+    got = float(np.sqrt(se[0].item() / (cnt[0] * 12)))
+    assert np.isclose(got, golden["rmse_thr_rk4_carry"][1], rtol=1e-10)
+
+
+def test_sim_data_generator(B, golden):
+    """training/train_sim_brov2_koopmanEDMDc.py:179-182: Euler rollout, dt = 0.05, 1500 stored inputs."""
+    e = B.Engine("thruster8", "f64")
+    r = e.rollout(np.zeros((1, 12)), golden["simgen_inputs"], dt=0.05, integrator="euler", stride=1)
+    assert normwise(cpu(r.traj)[::10, 0], golden["simgen_states_true_s10"]) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ reduced model
+def test_reduced9_against_reference(B, golden):
+    x, u = golden["red9_x"], golden["red9_u"]
+    out = B.reduced9_rhs(torch.tensor(x, device="cuda"), torch.tensor(u, device="cuda"))
+    assert normwise(cpu(out), golden["red9_xdot_f64"]) < 1e-14
+    out = B.reduced9_rhs(torch.tensor(x, device="cuda", dtype=torch.float32), torch.tensor(u, device="cuda", dtype=torch.float32))
+    assert out.dtype == torch.float32
+    assert normwise(cpu(out), golden["red9_xdot_f32"]) < 2e-6
+    # ragged size (not a multiple of the block) and an unaligned view
+    rng = np.random.default_rng(5)
+    xb = rng.standard_normal((1000 + 1, 9))
+    ub = rng.standard_normal((1000 + 1, 4))
+    got = B.reduced9_rhs(torch.tensor(xb, device="cuda")[1:], torch.tensor(ub, device="cuda")[1:])
+    assert normwise(cpu(got), O.rhs_reduced9(xb[1:], ub[1:])) < 1e-14
+
+
+# ------------------------------------------------------------------------------------------------ oracle, larger
+@pytest.mark.parametrize("kind,nu,scale", [("thruster8", 8, 1.0), ("wrench12", 6, O.np.array([40, 40, 40, 5, 5, 5.0])),
+                                           ("quat13", 6, O.np.array([40, 40, 40, 5, 5, 5.0]))])
+def test_fp64_against_oracle_4096_vehicles(B, kind, nu, scale):
+    rng = np.random.default_rng(11)
+    n, T = 4096, 150
+    x0 = np.zeros((n, 12))
+    x0[:, :3] = rng.uniform(-2, 2, (n, 3))
+    x0[:, 3:5] = rng.uniform(-0.2, 0.2, (n, 2))
+    x0[:, 5] = rng.uniform(-np.pi, np.pi, n)
+    U = O.smooth_inputs(rng, T, nu, n=n, scale=scale, sigma=0.05)
+    if kind == "quat13":
+        q = O.euler_to_quat(x0[:, 3], x0[:, 4], x0[:, 5])
+        x0 = np.concatenate([x0[:, :3], q, x0[:, 6:]], axis=1)
+    m = O.Model(kind, DT)
+    snaps, xT, lagT = O.rollout(m, "rk4", x0, U, stride=50)
+    r = B.Engine(kind, "f64").rollout(x0, U, dt=DT, integrator="rk4", stride=50)
+    assert normwise(cpu(r.traj), snaps) < TOL64
+    assert normwise(cpu(r.xT), xT) < TOL64
+    if kind == "thruster8":
+        assert normwise(cpu(r.lag).reshape(n, 8, 3), lagT) < TOL64
+
+
+def test_fp32_tolerance_after_1000_steps(B):
+    """north_star: fp32 kernel within 1e-4 relative of the float64 reference algorithm after 1000 steps."""
+    rng = np.random.default_rng(12)
+    n, T = 256, 1000
+    x0 = np.zeros((n, 12))
+    x0[:, :3] = rng.uniform(-2, 2, (n, 3))
+    x0[:, 3:5] = rng.uniform(-0.2, 0.2, (n, 2))
+    x0[:, 5] = rng.uniform(-np.pi, np.pi, n)
+    U = O.smooth_inputs(rng, T, 8, n=n, sigma=0.05).astype(np.float32)
+    _, xT, _ = O.rollout(O.Model("thruster8", DT), "rk4", x0.astype(np.float32).astype(np.float64), U.astype(np.float64))
+    r = B.Engine("thruster8", "f32").rollout(x0, U, dt=DT, integrator="rk4")
+    assert normwise(cpu(r.xT), xT) < TOL32
+
+
+def test_wrench_lag1_extension_against_oracle(B):
+    """First-order wrench lag (north-star extension; no reference counterpart -> parity unpinned, oracle only)."""
+    rng = np.random.default_rng(13)
+    n, T = 64, 200
+    x0 = np.zeros((n, 12))
+    x0[:, 2] = 1.0
+    x0[:, 5] = rng.uniform(-3, 3, n)
+    scale = np.array([40, 40, 40, 5, 5, 5.0])
+    U = O.smooth_inputs(rng, T, 6, n=n, scale=scale, sigma=0.05)
+    for integ in ("rk4", "euler"):
+        m = O.Model("wrench12", DT, lag1_T=0.15)
+        xa = np.concatenate([x0, np.zeros((n, 6))], axis=1)
+        _, xT, _ = O.rollout(m, integ, xa, U)
+        e = B.Engine("wrench12", "f64")
+        e.set_wrench_lag1(True, T_lag=0.15)
+        r = e.rollout(x0, U, dt=DT, integrator=integ)
+        assert normwise(cpu(r.xT), xT[:, :12]) < TOL64
+        assert normwise(cpu(r.lag), xT[:, 12:]) < TOL64
+
+
+# ------------------------------------------------------------------------------------------------ invariances
+def test_chunking_strides_and_host_path_are_bit_identical(B):
+    rng = np.random.default_rng(14)
+    n, T = 333, 64  # ragged: partial warp, partial block
+    x0 = rng.uniform(-1, 1, (n, 12)) * 0.3
+    U = O.smooth_inputs(rng, T, 8, n=n, sigma=0.05)
+    for dtype in ("f64", "f32"):
+        e = B.Engine("thruster8", dtype)
+        full = e.rollout(x0, U, dt=DT, stride=4)
+        # chunked: 3 launches, carrying state and lag, same snapshots
+        x, lag = e.tensor(x0), None
+        parts = []
+        for a, b in ((0, 10), (10, 37), (37, 64)):
+            r = e.rollout(x, U[a:b], dt=DT, stride=4, lag0=lag, step0=a)
+            x, lag = r.xT, r.lag
+            parts.append(r.traj)
+        assert torch.equal(x, full.xT) and torch.equal(lag, full.lag)
+        assert torch.equal(torch.cat(parts), full.traj)
+        # host-buffer path (pageable and pinned), tiny chunks so the double buffering cycles
+        x0h = x0.astype(e.ndtype)
+        Uh = np.ascontiguousarray(U.astype(e.ndtype))
+        xT, lagT, traj = e.rollout_host(x0h, Uh, dt=DT, stride=4, chunk_steps=8)
+        assert np.array_equal(xT, full.xT.cpu().numpy()) and np.array_equal(lagT, full.lag.cpu().numpy())
+        assert np.array_equal(traj, full.traj.cpu().numpy())
+        Up = B.pinned_empty(Uh.shape, e.ndtype)
+        Up[...] = Uh
+        xT2, _, traj2 = e.rollout_host(x0h, Up, dt=DT, stride=4, chunk_steps=0)
+        assert np.array_equal(xT2, xT) and np.array_equal(traj2, traj)
+        # a shard of the ensemble gives the same rows as the whole (no cross-vehicle coupling)
+        half = e.rollout(x0[100:200], np.ascontiguousarray(U[:, 100:200]), dt=DT)
+        assert torch.equal(half.xT, full.xT[100:200])
+
+
+def test_quat13_odd_n_unaligned_snapshots(B):
+    rng = np.random.default_rng(15)
+    n, T = 37, 12
+    x0 = np.zeros((n, 13))
+    x0[:, 3] = 1.0
+    x0[:, :3] = rng.uniform(-1, 1, (n, 3))
+    U = O.smooth_inputs(rng, T, 6, n=n, scale=10.0, sigma=0.1)
+    snaps, xT, _ = O.rollout(O.Model("quat13", DT), "euler", x0, U, stride=1)
+    for dtype, tol in (("f64", TOL64), ("f32", TOL32)):
+        r = B.Engine("quat13", dtype).rollout(x0, U, dt=DT, integrator="euler", stride=1)
+        assert normwise(cpu(r.traj), snaps) < tol
+
+
+def test_edge_cases(B):
+    e = B.Engine("wrench12", "f64")
+    x0 = np.zeros((1, 12))
+    r = e.rollout(x0, np.zeros((0, 6)), dt=DT)  # zero steps: identity
+    assert torch.equal(r.xT, e.tensor(x0))
+    r = e.rollout(np.zeros((0, 12)), np.zeros((5, 0, 6)), dt=DT)  # empty ensemble
+    assert r.xT.shape == (0, 12)
+    with pytest.raises(ValueError):
+        e.rollout(np.zeros((2, 11)), np.zeros((5, 6)), dt=DT)
+    with pytest.raises(ValueError):
+        e.rollout(np.zeros((2, 12)), np.zeros((5, 3, 6)), dt=DT)
+    with pytest.raises(B.BrovError):
+        e.rollout(np.zeros((2, 12)), np.zeros((5, 6)), dt=-1.0)
+    with pytest.raises(B.BrovError):
+        B.Engine("thruster8", "f64").set_wrench_lag1(True)
+    with pytest.raises(ValueError):
+        e.multistep_rmse(np.zeros((10, 12)), np.zeros((10, 6)), [10, 1])
+
+
+def test_full_size_cfg2_properties(B):
+    """BASELINE config 2 at full width (65,536 vehicles, fp64, thruster model), short horizon: determinism, chunking
+    invariance and agreement with the oracle on a random subset of vehicles."""
+    n, T = 65536, 40
+    g = torch.Generator(device="cuda").manual_seed(2)
+    e = B.Engine("thruster8", "f64")
+    x0 = torch.zeros((n, 12), device="cuda", dtype=torch.float64)
+    x0[:, :3] = torch.rand((n, 3), device="cuda", dtype=torch.float64, generator=g) * 4 - 2
+    x0[:, 5] = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 6 - 3
+    U = (torch.rand((T, n, 8), device="cuda", dtype=torch.float64, generator=g) * 0.8 - 0.4).contiguous()
+    a = e.rollout(x0, U, dt=DT)
+    b = e.rollout(x0, U, dt=DT)
+    assert torch.equal(a.xT, b.xT) and torch.equal(a.lag, b.lag)
+    m1 = e.rollout(x0, U[:17], dt=DT)
+    m2 = e.rollout(m1.xT, U[17:], dt=DT, lag0=m1.lag, step0=17)
+    assert torch.equal(m2.xT, a.xT)
+    idx = torch.randint(0, n, (64,), generator=torch.Generator().manual_seed(3))
+    _, xT, _ = O.rollout(O.Model("thruster8", DT), "rk4", cpu(x0[idx]), cpu(U[:, idx]))
+    assert normwise(cpu(a.xT[idx]), xT) < TOL64
+
+
+def test_full_size_cfg3_properties(B):
+    """BASELINE config 3 at full width (1,048,576 vehicles, fp32, stride-10 writeback), short horizon."""
+    n, T = 1 << 20, 20
+    g = torch.Generator(device="cuda").manual_seed(4)
+    e = B.Engine("thruster8", "f32")
+    x0 = torch.zeros((n, 12), device="cuda", dtype=torch.float32)
+    x0[:, 5] = torch.rand(n, device="cuda", generator=g) * 6 - 3
+    U = (torch.rand((T, n, 8), device="cuda", generator=g) * 0.8 - 0.4).contiguous()
+    r = e.rollout(x0, U, dt=DT, stride=10)
+    assert r.traj.shape == (2, n, 12)
+    assert torch.equal(r.traj[1], r.xT)
+    mid = e.rollout(x0, U[:10], dt=DT)
+    assert torch.equal(r.traj[0], mid.xT)
+    assert bool(torch.isfinite(r.xT).all())
+    idx = torch.randint(0, n, (64,), generator=torch.Generator().manual_seed(5))
+    _, xT, _ = O.rollout(O.Model("thruster8", DT), "rk4", cpu(x0[idx]), cpu(U[:, idx]))
+    assert normwise(cpu(r.xT[idx]), xT) < TOL32
+
+
+# ------------------------------------------------------------------------------------------------ reference API mirror
+def test_fossen_mirror_classes(B, golden):
+    from bluerov2_dynamics_b200.fossen.BlueROV2 import BlueROV2, ThrusterLag
+    from bluerov2_dynamics_b200.fossen.BlueROV2_thrust import BlueROV2 as W12
+    from bluerov2_dynamics_b200.fossen import BlueROV2_wrench as QW
+    from bluerov2_dynamics_b200.evaluators import simulate_physics, multistep_rmse_endpoint_physics, one_step_rmse_physics
+
+    rov = BlueROV2(dt=0.02)
+    assert np.allclose(np.diag(rov.Minv), golden["const_Minv_diag"], rtol=1e-15)
+    assert np.allclose(np.stack([t["r"] for t in rov.thrusters_r]), golden["const_thr_r"], atol=1e-16)
+    # dynamics() is stateful: the second call sees the lag state left by the first
+    x, u = golden["rhs_thr_x"][0], golden["rhs_thr_u"][0]
+    xd1 = rov.dynamics(x, u, DT)
+    assert normwise(xd1, golden["rhs_thr_xdot"][0]) < 1e-12
+    assert normwise(np.stack([l._x for l in rov.thruster_lags]), golden["rhs_thr_lag1"][0]) < 1e-12
+    xd2 = rov.dynamics(x, u, DT)
+    assert not np.allclose(xd1, xd2)
+    # simulate_physics: RK4 loop of train_tank_brov2_rk4.py, trajectory incl. row 0, lag state left in rov
+    rov = BlueROV2()
+    traj = simulate_physics(golden["cfg1_x0"], golden["cfg1_U_var"], DT, rov, integrator="rk4")
+    assert traj.shape == (1001, 12) and np.array_equal(traj[0], golden["cfg1_x0"])
+    assert normwise(traj[::10], golden["cfg1_var_traj_s10"]) < TOL64
+    assert normwise(np.stack([l._x for l in rov.thruster_lags]), golden["cfg1_var_lagT"]) < TOL64
+    # wrench models: shape validation by reshape (ValueError) as the reference
+    w = W12()
+    assert normwise(w.dynamics(golden["rhs_thr_x"][3], golden["rhs_w_tau"][3]), golden["rhs_w12_xdot"][3]) < 1e-12
+    with pytest.raises(ValueError):
+        w.dynamics(np.zeros(11), np.zeros(6))
+    q = QW.BlueROV2(current_speed=golden["rhs_current"])
+    assert normwise(q.dynamics(golden["rhs_q13_x"][40], golden["rhs_w_tau"][40]), golden["rhs_q13_cur_xdot"][40]) < 1e-12
+    # attribute edits after construction follow the reference's semantics (trap T5): C/D change, Minv does not
+    w2 = W12()
+    w2.Xu_abs *= 2.0
+    ref = O.default_params()
+    ref["Xu_abs"] = ref["Xu_abs"] * 2.0
+    assert normwise(w2.dynamics(golden["rhs_thr_x"][5], golden["rhs_w_tau"][5]),
+                    O.rhs_wrench12(golden["rhs_thr_x"][5:6], golden["rhs_w_tau"][5:6], ref)[0]) < 1e-12
+    # evaluators
+    HS = [int(h) for h in golden["rmse_H"]]
+    got = multistep_rmse_endpoint_physics(golden["rmse_X12"], golden["rmse_U8"], HS, DT, integrator="rk4")
+    assert np.allclose(got, golden["rmse_thr_rk4_reset"], rtol=1e-10)
+    assert np.isclose(one_step_rmse_physics(golden["rmse_X12"], golden["rmse_W6"], DT, model="wrench12"),
+                      golden["rmse_w12_onestep"], rtol=1e-10)
+    # helpers
+    assert np.allclose(QW.quat_to_rotation_matrix(golden["quat_q"][0]), golden["quat_to_R"][0], atol=1e-15)
+    assert np.allclose(QW.quat_multiply(golden["quat_q"][1], golden["quat_q2"][1]), golden["quat_multiply"][1], atol=1e-15)
+    assert np.allclose(QW.euler_to_quat(*golden["quat_euler_in"][2]), golden["quat_euler_to_quat"][2], atol=1e-15)
+    lag = ThrusterLag()
+    y = [lag.step(1.0, DT) for _ in range(3)]
+    Ad, Bd = O.lag_zoh(DT)
+    xs = np.zeros(3)
+    for k in range(3):
+        xs = Ad @ xs + Bd
+    assert np.isclose(y[-1], O.LAG_CC @ xs, rtol=1e-13)
+
+
+def test_bluerov_torch_mirror(B, golden):
+    from bluerov2_dynamics_b200.fossen.bluerov_torch import bluerov_compute, ssa
+    x = torch.tensor(golden["red9_x"])
+    u = torch.tensor(golden["red9_u"])
+    out = bluerov_compute(0.0, x, u)  # CPU tensors in -> CPU tensor out, computed on the GPU
+    assert out.device.type == "cpu" and out.dtype == torch.float64
+    assert normwise(out.numpy(), golden["red9_xdot_f64"]) < 1e-14
+    one = bluerov_compute(0.0, x[0].cuda().float(), u[0].cuda().float())  # 1-D promoted to a batch of one
+    assert one.shape == (1, 9) and one.is_cuda and one.dtype == torch.float32
+    assert np.allclose(ssa(torch.tensor(golden["ssa_in"])).numpy(), golden["ssa_out"], atol=1e-14)

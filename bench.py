@@ -1,0 +1,447 @@
+#!/usr/bin/env python3
+"""bench.py — RK4 vehicle-steps/s of the batched BlueROV2 Fossen rollout (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
+    python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference algorithm on the host CPU cores
+
+One "step" = one pass of the hot path over one batch of synthetic input: ONE rollout-kernel launch that advances
+every vehicle of the ensemble by CHUNK (=100) RK4 steps under per-vehicle random thrust inputs.  K = 100 steps is
+the full 10,000-step rollout of BASELINE configs[1] / configs[2].
+
+Primary line (`value`, `roofline`, `e2e`): configs[1] — 65,536 vehicles per GPU, fp64, 8-thruster model with the
+3rd-order lag, dt = 0.02.  The `fp32` object of the same line carries configs[2] — 1,048,576 vehicles per GPU, fp32,
+trajectory writeback every 10 steps.  N > 1: the ensemble is sharded by vehicle, each rank runs its own shard
+(weak scaling, no data-path collective); `rmse` times the multi-horizon evaluator, whose per-rank squared-error
+sums are combined with one NCCL all-reduce.
+
+Inputs are resident in HBM for `value` (a ring of two chunk buffers, each far larger than the 126 MB L2, used
+alternately) and in pinned host memory for `e2e` (every step copies its chunk host->device and reads the step's
+final state back, through Engine.rollout_host = brov_rollout_host of the C ABI).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "rk4_vehicle_steps_per_s"
+UNIT = "vehicle-steps/s"
+DT = 0.02
+CHUNK = 100                      # RK4 steps per launch ("step" of the bench)
+FLOP_PER_STEP = {"thruster8": 1756.0, "wrench12": 676.0, "quat13": 805.0}   # SURVEY 8(d), algorithmic
+CFG2 = dict(name="cfg2", model="thruster8", dtype="f64", n_per_gpu=65536, stride=0)
+CFG3 = dict(name="cfg3", model="thruster8", dtype="f32", n_per_gpu=1 << 20, stride=10)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle; the only place bench.py may execute oracle/)
+# ------------------------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    """One host core: `nveh` vehicles, one at a time, `steps` RK4 steps each — numpy float64, one vehicle per Python
+    call, the way the reference executes simulate_physics (training/train_tank_brov2_rk4.py:375-396)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    seed, nveh, steps = job
+    from oracle import fossen_np as O
+    rng = np.random.default_rng(seed)
+    m = O.Model("thruster8", DT)
+    t0 = time.perf_counter()
+    for _ in range(nveh):
+        x = np.zeros((1, 12))
+        x[0, 2] = 1.0
+        U = rng.uniform(-0.4, 0.4, (steps, 8))
+        O.rollout(m, "rk4", x, U)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_rate(cores: int, steps_per_core: int, seed: int = 0):
+    """Aggregate RK4 vehicle-steps/s of `cores` processes each rolling one vehicle for steps_per_core steps."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    jobs = [(seed + i, 1, steps_per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    return cores * steps_per_core / wall, wall
+
+
+def cpu_batched_rate(n: int = 4096, steps: int = 20):
+    """The same oracle vectorised over n vehicles in one process (numpy's own threading): a stronger CPU baseline
+    than the reference's one-vehicle-per-call structure."""
+    from oracle import fossen_np as O
+    rng = np.random.default_rng(1)
+    x = np.zeros((n, 12))
+    U = rng.uniform(-0.4, 0.4, (steps, n, 8))
+    m = O.Model("thruster8", DT)
+    O.rollout(m, "rk4", x, U[:2])
+    t0 = time.perf_counter()
+    O.rollout(m, "rk4", x, U)
+    return n * steps / (time.perf_counter() - t0)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, windows):
+        """windows: list of (t0, t1) perf_counter intervals that were timed."""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if windows and not any(a - 0.05 <= t <= b + 0.15 for a, b in windows):
+                continue
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU legs
+# ------------------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs(torch, eng, n, chunk, ring, seed):
+    """Per-vehicle random thrust inputs [ring][chunk][n][8], uniform in [-0.4, 0.4] (SURVEY 8(d) cfg2 range),
+    generated on the device by torch's Philox generator; x0 = scattered positions, random yaw, at rest."""
+    g = torch.Generator(device=eng.device).manual_seed(seed)
+    U = [(torch.rand((chunk, n, 8), device=eng.device, dtype=eng.tdtype, generator=g) * 0.8 - 0.4).contiguous()
+         for _ in range(ring)]
+    x0 = torch.zeros((n, 12), device=eng.device, dtype=eng.tdtype)
+    x0[:, 0:2] = torch.rand((n, 2), device=eng.device, dtype=eng.tdtype, generator=g) * 4 - 2
+    x0[:, 2] = torch.rand(n, device=eng.device, dtype=eng.tdtype, generator=g) * 3
+    x0[:, 5] = torch.rand(n, device=eng.device, dtype=eng.tdtype, generator=g) * 6.2 - 3.1
+    return U, x0
+
+
+def run_rollout_leg(torch, dist, B, cfg, steps, warmup, local, world, windows):
+    eng = B.Engine(cfg["model"], cfg["dtype"], device=local)
+    n, stride = cfg["n_per_gpu"], cfg["stride"]
+    ring = 2
+    U, x0 = make_inputs(torch, eng, n, CHUNK, ring, seed=1000 + int(os.environ.get("RANK", "0")))
+    x = x0.clone()
+    lag = torch.zeros((n, 24), device=eng.device, dtype=eng.tdtype)
+    traj = [torch.empty((CHUNK // stride, n, 12), device=eng.device, dtype=eng.tdtype) for _ in range(ring)] if stride else None
+
+    def one(k):
+        eng.rollout(x, U[k % ring], dt=DT, integrator="rk4", lag0=lag, stride=stride, step0=k * CHUNK, xT_out=x,
+                    lag_out=lag, traj_out=traj[k % ring] if stride else None)
+
+    for k in range(warmup):
+        one(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(steps):
+        one(warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    windows.append((t0, t1))
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=eng.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    finite = bool(torch.isfinite(x).all().item())
+    sz = 8 if cfg["dtype"] == "f64" else 4
+    bytes_per_launch = n * CHUNK * 8 * sz + (n * 12 * sz * (CHUNK // stride) if stride else 0) + 2 * n * 36 * sz
+    return dict(ms_total=ms, ms_per_step=ms / steps, vehicle_steps=float(n) * world * CHUNK * steps, finite=finite,
+                bytes_per_launch=bytes_per_launch, n=n, eng=eng, U=U, x0=x0)
+
+
+def run_e2e_leg(torch, dist, B, cfg, leg, steps, warmup, world, windows):
+    """Same workload through the host-buffer API: per step, the chunk's inputs + x0 + lag go host->device from
+    pinned memory and the step's final state + lag come back."""
+    eng, n = leg["eng"], leg["n"]
+    ring = 2
+    Uh = [B.pinned_empty((CHUNK, n, 8), eng.ndtype) for _ in range(ring)]
+    for r in range(ring):
+        Uh[r][...] = leg["U"][r].cpu().numpy()
+    xh = B.pinned_empty((n, 12), eng.ndtype)
+    xh[...] = leg["x0"].cpu().numpy()
+    lagh = B.pinned_empty((n, 24), eng.ndtype)
+    lagh[...] = 0
+
+    def one(k):
+        eng.rollout_host(xh, Uh[k % ring], dt=DT, integrator="rk4", lag0=lagh, out_xT=xh, out_lag=lagh,
+                         chunk_steps=CHUNK // 4)
+
+    for k in range(max(1, min(warmup, 3))):
+        one(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        one(k)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    windows.append((t0, t1))
+    sec = t1 - t0
+    if world > 1:
+        t = torch.tensor([sec], device=eng.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    h2d = Uh[0].nbytes + xh.nbytes + lagh.nbytes
+    d2h = xh.nbytes + lagh.nbytes
+    return dict(value=float(n) * world * CHUNK * steps / sec, unit=UNIT, h2d_bytes_per_step=int(h2d),
+                d2h_bytes_per_step=int(d2h), steps=steps, ms_per_step=1e3 * sec / steps,
+                api="Engine.rollout_host -> brov_rollout_host (C ABI), pinned host buffers, 4 sub-chunks per call "
+                    "double-buffered on a copy stream")
+
+
+def run_rmse_leg(torch, dist, B, local, rank, world, windows, T=1_000_100, horizons=(1, 10, 100)):
+    """cfg5: multi-horizon endpoint RMSE over ~1M sliding windows of a synthetic 50 Hz series; windows sharded over
+    ranks (H-row halo), per-rank squared-error sums all-reduced with NCCL."""
+    from bluerov2_dynamics_b200 import dist as D
+    eng = B.Engine("thruster8", "f64", device=local)
+    g = torch.Generator(device=eng.device).manual_seed(4)
+    U = (torch.rand((T, 8), device=eng.device, dtype=torch.float64, generator=g) * 0.8 - 0.4)
+    # "recorded" states: a smooth bounded synthetic series in a tank-sized box plus sensor-like noise
+    t = torch.arange(T, device=eng.device, dtype=torch.float64) * DT
+    X = torch.zeros((T, 12), device=eng.device, dtype=torch.float64)
+    X[:, 0] = 2.0 * torch.sin(0.05 * t); X[:, 1] = 2.0 * torch.cos(0.04 * t); X[:, 2] = 1.5 + torch.sin(0.03 * t)
+    X[:, 5] = 0.5 * torch.sin(0.02 * t)
+    X[:, 6] = 0.1 * torch.cos(0.05 * t); X[:, 7] = -0.08 * torch.sin(0.04 * t); X[:, 8] = 0.03 * torch.cos(0.03 * t)
+    X += 1e-3 * torch.randn((T, 12), device=eng.device, dtype=torch.float64, generator=g)
+    hs = list(horizons)
+    lo, hi, nloc = D.window_shard(T, hs, rank, world)
+    Xl, Ul = X[lo:hi].contiguous(), U[lo:hi].contiguous()
+
+    def one():
+        se, _ = eng.multistep_se(Xl, Ul, hs, dt=DT, integrator="rk4", n_windows=nloc)
+        vec = se[:len(hs)].clone()
+        D.allreduce_sum_(vec)
+        return vec
+
+    one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    vec = one()
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t0, time.perf_counter()))
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], device=eng.device, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    cnt = D.global_counts(T, hs)
+    # window k runs min(Hmax, T-1-k) steps; all horizons are read off the same rollout
+    hm = hs[-1]
+    vsteps = float(max(T - hm, 0) * hm + hm * (hm - 1) // 2) if T > hm else float(T * (T - 1) // 2)
+    rm = [float(np.sqrt(v / (c * 12))) for v, c in zip(vec.cpu().numpy(), cnt)]
+    return dict(workload=f"cfg5: T={T} rows, H={hs}, RK4, 8-thruster fp64, windows sharded over {world} GPU(s), "
+                         "NCCL all-reduce of the SE vector" if world > 1 else
+                         f"cfg5: T={T} rows, H={hs}, RK4, 8-thruster fp64", windows=cnt, ms=ms,
+                vehicle_steps_per_s=vsteps / (ms * 1e-3), rmse=rm)
+
+
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+    import bluerov2_dynamics_b200 as B
+    from bluerov2_dynamics_b200 import dist as D
+
+    rank, world, local = D.init_from_env()
+    if world != args.gpus and rank == 0:
+        print(f"[bench] note: WORLD_SIZE={world} but --gpus {args.gpus}; using {world}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    cores = host_cores()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # before the timed GPU region; forked workers never touch CUDA
+        spc = args.cpu_steps
+        rate, wall = cpu_reference_rate(cores, spc)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} processes x 1 vehicle x {spc} RK4 steps (thruster model, dt=0.02), numpy float64 "
+                         f"oracle executed one vehicle per call as the reference does; wall {wall:.1f} s",
+               "batched_numpy_value": cpu_batched_rate(),
+               "batched_numpy_sample": "same oracle vectorised over 4096 vehicles x 20 RK4 steps in one process"}
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    windows = []
+    peaks, peak_src = measured_peaks()
+
+    # in-run FP pipe peaks (MEASURED_PEAKS.json carries only HBM and bf16-GEMM numbers)
+    fp64_peak, _ = B.fma_peak("f64", local, 2048)
+    fp32_peak, _ = B.fma_peak("f32", local, 8192)
+
+    leg2 = run_rollout_leg(torch, dist, B, CFG2, args.steps, args.warmup, local, world, windows)
+    e2e = run_e2e_leg(torch, dist, B, CFG2, leg2, min(args.steps, args.e2e_steps), args.warmup, world, windows)
+    del leg2["U"], leg2["x0"]
+    torch.cuda.empty_cache()
+    leg3 = run_rollout_leg(torch, dist, B, CFG3, args.steps, args.warmup, local, world, windows)
+    del leg3["U"], leg3["x0"], leg3["eng"]
+    torch.cuda.empty_cache()
+    rmse = run_rmse_leg(torch, dist, B, local, rank, world, windows) if not args.no_rmse else None
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    clocks = sampler.stop(windows)
+
+    def roof(leg, cfg, peak):
+        per_gpu_steps = leg["vehicle_steps"] / world
+        tf = FLOP_PER_STEP[cfg["model"]] * per_gpu_steps / (leg["ms_total"] * 1e-3) / 1e12
+        gbs = leg["bytes_per_launch"] / (leg["ms_per_step"] * 1e-3) / 1e9
+        return {"bound": "fp64_pipe" if cfg["dtype"] == "f64" else "fp32_pipe", "achieved": tf, "peak": peak,
+                "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                "kernel": f"brov::rollout_kernel<{'double' if cfg['dtype'] == 'f64' else 'float'}, THRUSTER8, RK4>",
+                "flop_per_vehicle_step": FLOP_PER_STEP[cfg["model"]],
+                "peak_source": "in-run FMA-chain microbenchmark (brov_fma_peak), 2 flop per FMA",
+                "kernel_ms": leg["ms_per_step"],
+                "hbm": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                        "bytes_per_launch": leg["bytes_per_launch"], "peak_source": peak_src}}
+
+    v2 = leg2["vehicle_steps"] / (leg2["ms_total"] * 1e-3)
+    v3 = leg3["vehicle_steps"] / (leg3["ms_total"] * 1e-3)
+    line = {
+        "metric": METRIC, "value": v2, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": leg2["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 65,536-vehicle ensemble per GPU, 8-thruster Fossen model with "
+                               "3rd-order thruster lag, per-vehicle random thrust inputs U(-0.4,0.4), RK4, dt=0.02, "
+                               f"{args.steps * CHUNK} steps ({CHUNK} per launch), fp64",
+                   "vehicles_per_gpu": CFG2["n_per_gpu"], "rk4_steps_per_launch": CHUNK,
+                   "l2_policy": "inputs larger than L2: two 419 MB input chunks used alternately, read once per launch",
+                   "parallelism": f"vehicle-sharded x{world}, no data-path collective"},
+        "roofline": roof(leg2, CFG2, fp64_peak),
+        "e2e": e2e,
+        "gpu_launches": args.steps,
+        "clocks": clocks,
+        "finite": leg2["finite"] and leg3["finite"],
+        "fp32": {"value": v3, "unit": UNIT, "ms_per_step": leg3["ms_per_step"], "dtype": "f32",
+                 "config": {"workload": "BASELINE configs[2]: 1,048,576-vehicle ensemble per GPU, same model, fp32, "
+                                        f"{args.steps * CHUNK} RK4 steps, trajectory writeback every 10 steps",
+                            "vehicles_per_gpu": CFG3["n_per_gpu"],
+                            "l2_policy": "two 3.36 GB input chunks used alternately"},
+                 "roofline": roof(leg3, CFG3, fp32_peak), "gpu_launches": args.steps},
+        "rmse": rmse,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main_reference(args):
+    """Reference arm: the reference's algorithm (oracle port; the reference itself is Python under /root/reference and
+    does not exist on the GPU box) on all host cores.  Each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    spc = args.cpu_steps
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_rate(cores, max(spc // 4, 10))
+    rates, t0 = [], time.perf_counter()
+    steps_done = 0
+    for k in range(args.steps):
+        r, _ = cpu_reference_rate(cores, spc, seed=100 * k)
+        rates.append(r)
+        steps_done += 1
+        if time.perf_counter() - t0 > args.reference_budget_s:
+            break
+    wall = time.perf_counter() - t0
+    value = cores * spc * steps_done / wall
+    sample = (f"each step: {cores} processes x 1 vehicle x {spc} RK4 steps of configs[1]'s model (8-thruster + lag, "
+              f"dt=0.02, random thrust), numpy float64, one vehicle per Python call as the reference executes; "
+              f"{steps_done} of {args.steps} steps run within the {args.reference_budget_s:.0f} s budget")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps_done, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / max(steps_done, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] model and inputs, bounded sample on the host CPU cores"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--cpu-steps", type=int, default=400, help="RK4 steps per core of the CPU baseline sample")
+    ap.add_argument("--reference-budget-s", type=float, default=120.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rmse", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

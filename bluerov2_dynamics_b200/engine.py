@@ -367,6 +367,4 @@ def pinned_empty(shape, dtype) -> np.ndarray:
     """Pinned (page-locked) host numpy array, via torch's allocator."""
     tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
     t = torch.empty(tuple(shape), dtype=tdt, pin_memory=True)
-    a = t.numpy()
-    a.setflags(write=True)
-    return a
+    return t.numpy()

@@ -1,0 +1,164 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol include/brov.h declares, the host-only
+entry points (constants, geometry, zero-order hold) agree with the reference's golden values, argument checking
+reports errors, and the multi-rank evaluator plumbing works over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, normwise
+
+
+@pytest.fixture(scope="module")
+def L():
+    """ctypes binding; builds libbrov.so first if the checkout is fresh (nvcc cross-compiles without a GPU)."""
+    from bluerov2_dynamics_b200.build import build_lib
+    build_lib()
+    from bluerov2_dynamics_b200 import _lib
+    return _lib
+
+
+def test_every_declared_symbol_is_exported(L):
+    hdr = open(os.path.join(ROOT, "include", "brov.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(brov_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    raw = C.CDLL(L.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(raw, s)]
+    assert not missing, missing
+    assert declared == set(L._PROTOS), declared ^ set(L._PROTOS)
+    assert L.lib.brov_abi_version() == L.ABI_VERSION
+    # struct layouts match the header's field order and sizes (LP64)
+    assert C.sizeof(L.RolloutDesc) == 4 + 4 + 8 * 14
+    assert C.sizeof(L.SeDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 * 4 + 4 + 8 * 4
+    assert C.sizeof(L.RolloutHostDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 + 8 * 5
+
+
+def test_constants_match_reference(L, golden):
+    from bluerov2_dynamics_b200.engine import default_allocation, default_physical, derive_params, lag_discretize
+    ph = default_physical()
+    assert ph[L.PH_W] == golden["const_W"] and ph[L.PH_B] == golden["const_B"]
+    assert np.allclose(ph[L.PH_MINV:L.PH_MINV + 6], golden["const_Minv_diag"], rtol=1e-15)
+    alloc, r, d = default_allocation()
+    assert np.allclose(alloc, golden["const_alloc"], atol=1e-16)
+    assert np.allclose(r, golden["const_thr_r"], atol=1e-16) and np.allclose(d, golden["const_thr_dir"], atol=1e-16)
+    for dt in (0.01, 0.02, 0.05):
+        Ad, Bd = lag_discretize(dt)
+        assert np.max(np.abs(Ad - golden[f"const_lag_Ad_{dt}"])) < 2e-15
+        assert np.max(np.abs(Bd - golden[f"const_lag_Bd_{dt}"])) < 2e-15
+    kp = derive_params(ph)
+    assert kp.shape == (L.NKP,)
+    assert np.isclose(kp[27], 132.57 - 131.588) and np.allclose(kp[6:9], [19.86, 20.62, 32.18])
+    assert np.allclose(kp[15:21], [13.7, 0, 33, 0, 0.8, 0]) and np.allclose(kp[21:27], [141, 217, 190, 1.19, 0.47, 1.5])
+    batch = derive_params(np.tile(ph, (5, 1)))
+    assert batch.shape == (5, L.NKP) and np.array_equal(batch[3], kp)
+
+
+def test_errors_are_reported_without_a_gpu(L):
+    rc = L.lib.brov_default_physical(1000.0, None)
+    assert rc == -1 and b"NULL" in L.lib.brov_last_error()
+    Ad, Bd = np.zeros(9), np.zeros(3)
+    assert L.lib.brov_lag_discretize(-1.0, L.dptr(Ad), L.dptr(Bd)) == -1
+    with pytest.raises(L.BrovError):
+        L.check(L.lib.brov_lag_discretize(float("nan"), L.dptr(Ad), L.dptr(Bd)))
+    h = C.c_void_p()
+    rc = L.lib.brov_create(7, L.F64, 0, C.byref(h))  # unknown model: rejected before any CUDA call
+    assert rc == -1 and not h.value
+
+
+def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():
+    """No GPU here: constructing an engine must fail loudly, and nothing under bluerov2_dynamics_b200/ may mention
+    the oracle."""
+    import torch
+    pkg = os.path.join(ROOT, "bluerov2_dynamics_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+    if not torch.cuda.is_available():
+        import bluerov2_dynamics_b200 as B
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            B.Engine("thruster8", "f64")
+
+
+def test_parameters_module_matches_reference_values():
+    from bluerov2_dynamics_b200.fossen import parameters as P
+    from oracle.fossen_np import RED
+    for k, v in RED.items():
+        assert getattr(P, k) == v, k
+    assert P.F_bouy == 1026 * 0.0115 * 9.82 and P.z_b == -0.1 and P.I_xx == 0.21
+
+
+def test_shard_helpers():
+    from bluerov2_dynamics_b200 import dist as D
+    for n in (0, 1, 7, 64, 1000):
+        for w in (1, 2, 3, 8):
+            parts = [D.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in parts) - min(b - a for a, b in parts) <= 1
+    lo, hi, nl = D.window_shard(140, [1, 10, 100], 1, 2)
+    assert (lo, hi, nl) == (70, 140, 69)
+    assert D.global_counts(140, [1, 10, 100]) == [139, 130, 40]
+    assert D.global_counts(5, [10]) == [0]
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch
+import torch.distributed as dist
+from bluerov2_dynamics_b200 import dist as D
+from oracle import fossen_np as O
+rank, world, _ = D.init_from_env("gloo")
+g = dict(np.load(os.path.join({root!r}, "tests", "golden", "reference_vectors.npz")))
+X, U, HS = g["rmse_X12"], g["rmse_W6"], [1, 10, 100]
+m = O.Model("wrench12", 0.02)
+def local_se(Xr, Ur, hs, nwin):
+    # per-rank squared-error sums from the oracle: windows [0, nwin) of the rank's rows
+    out = []
+    for h in hs:
+        ns = min(nwin, len(Xr) - h)
+        if ns <= 0:
+            out.append(0.0); continue
+        x = Xr[:ns].copy(); lag = m.zero_lag(ns)
+        for j in range(h):
+            x, lag = O.step(m, "euler", x, Ur[j:j + ns], lag)
+        e = x - Xr[h:h + ns]
+        out.append(float(np.sum(e * e)))
+    return torch.tensor(out, dtype=torch.float64)
+got = D.sharded_multistep_rmse(local_se, X, U, HS, rank, world)
+if rank == 0:
+    assert np.allclose(got, g["rmse_w12_euler"], rtol=1e-11), (got, g["rmse_w12_euler"])
+    print("SHARDED_OK", got)
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_evaluator_world_size_2_gloo(tmp_path, golden):
+    """N > 1 path on CPU: two gloo ranks shard the sliding windows (with the H-row halo), the oracle supplies each
+    rank's squared-error sums, one all-reduce combines them; the result equals the reference's RMSE."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "SHARDED_OK" in r.stdout
+
+
+def test_bench_reference_arm_prints_contract_line():
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-steps", "20"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "vehicle-steps/s"

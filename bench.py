@@ -177,12 +177,12 @@ def run_rollout_leg(torch, dist, B, cfg, steps, warmup, local, world, windows):
     ring = 2
     U, x0 = make_inputs(torch, eng, n, CHUNK, ring, seed=1000 + int(os.environ.get("RANK", "0")))
     x = x0.clone()
-    lag = torch.zeros((n, 24), device=eng.device, dtype=eng.tdtype)
+    lag = torch.zeros((n, 18), device=eng.device, dtype=eng.tdtype)  # allocation-projected lag carried between chunks
     traj = [torch.empty((CHUNK // stride, n, 12), device=eng.device, dtype=eng.tdtype) for _ in range(ring)] if stride else None
 
     def one(k):
         eng.rollout(x, U[k % ring], dt=DT, integrator="rk4", lag0=lag, stride=stride, step0=k * CHUNK, xT_out=x,
-                    lag_out=lag, traj_out=traj[k % ring] if stride else None)
+                    lag_out=lag, traj_out=traj[k % ring] if stride else None, lag_repr="projected")
 
     for k in range(warmup):
         one(k)
@@ -206,7 +206,7 @@ def run_rollout_leg(torch, dist, B, cfg, steps, warmup, local, world, windows):
         dist.barrier()
     finite = bool(torch.isfinite(x).all().item())
     sz = 8 if cfg["dtype"] == "f64" else 4
-    bytes_per_launch = n * CHUNK * 8 * sz + (n * 12 * sz * (CHUNK // stride) if stride else 0) + 2 * n * 36 * sz
+    bytes_per_launch = n * CHUNK * 8 * sz + (n * 12 * sz * (CHUNK // stride) if stride else 0) + 2 * n * 30 * sz
     return dict(ms_total=ms, ms_per_step=ms / steps, vehicle_steps=float(n) * world * CHUNK * steps, finite=finite,
                 bytes_per_launch=bytes_per_launch, n=n, eng=eng, U=U, x0=x0)
 
@@ -221,12 +221,12 @@ def run_e2e_leg(torch, dist, B, cfg, leg, steps, warmup, world, windows):
         Uh[r][...] = leg["U"][r].cpu().numpy()
     xh = B.pinned_empty((n, 12), eng.ndtype)
     xh[...] = leg["x0"].cpu().numpy()
-    lagh = B.pinned_empty((n, 24), eng.ndtype)
+    lagh = B.pinned_empty((n, 18), eng.ndtype)
     lagh[...] = 0
 
     def one(k):
         eng.rollout_host(xh, Uh[k % ring], dt=DT, integrator="rk4", lag0=lagh, out_xT=xh, out_lag=lagh,
-                         chunk_steps=CHUNK // 4)
+                         chunk_steps=CHUNK // 4, lag_repr="projected")
 
     for k in range(max(1, min(warmup, 3))):
         one(k)

@@ -13,12 +13,22 @@ or `bluerov2_dynamics_b200.install_as_fossen()` to serve `import fossen...` from
 live on `Engine`.  All compute runs in libbrov.so (hand-written CUDA behind the C ABI of include/brov.h); there is no
 CPU fallback — importing this package without the built library raises.
 """
-from ._lib import BrovError, LIB_PATH  # noqa: F401  (raises ImportError if libbrov.so is missing)
-from .engine import (Engine, RolloutResult, default_allocation, default_physical, derive_params,  # noqa: F401
-                     fma_peak, lag_discretize, pinned_empty, reduced9_rhs)
+import importlib as _importlib
 
 __all__ = ["Engine", "RolloutResult", "BrovError", "default_physical", "derive_params", "default_allocation",
-           "lag_discretize", "reduced9_rhs", "fma_peak", "pinned_empty", "install_as_fossen"]
+           "lag_discretize", "reduced9_rhs", "fma_peak", "pinned_empty", "install_as_fossen", "LIB_PATH"]
+
+_FROM_LIB = ("BrovError", "LIB_PATH")
+
+
+def __getattr__(name):
+    """Public names resolve on first use, so that `python -m bluerov2_dynamics_b200.build` can run before the library
+    exists.  Any use of the package without a loadable libbrov.so raises ImportError (there is no CPU fallback)."""
+    if name in _FROM_LIB:
+        return getattr(_importlib.import_module(__name__ + "._lib"), name)
+    if name in __all__:
+        return getattr(_importlib.import_module(__name__ + ".engine"), name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
 
 
 def install_as_fossen() -> None:

@@ -11,10 +11,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbrov.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 THRUSTER8_LAG3, WRENCH_EULER12, WRENCH_QUAT13 = 0, 1, 2
 F64, F32 = 0, 1
 RK4, EULER = 0, 1
+LAG_THRUSTER, LAG_PROJECTED = 0, 1
 NPHYS, NKP, MAX_H = 37, 36, 4
 PH_M, PH_W, PH_B, PH_XB, PH_I, PH_ADDED, PH_LIN, PH_QUAD, PH_MINV, PH_CURRENT, PH_TLAG1 = 0, 1, 2, 3, 6, 9, 15, 21, 27, 33, 36
 
@@ -28,7 +29,8 @@ class RolloutDesc(C.Structure):
                 ("dt", C.c_double), ("x0_dev", C.c_void_p), ("xT_dev", C.c_void_p), ("u_dev", C.c_void_p),
                 ("u_stride_t", C.c_longlong), ("u_stride_n", C.c_longlong), ("lag_in_dev", C.c_void_p),
                 ("lag_out_dev", C.c_void_p), ("traj_dev", C.c_void_p), ("stride", C.c_longlong),
-                ("step0", C.c_longlong), ("snap_base", C.c_longlong)]
+                ("step0", C.c_longlong), ("snap_base", C.c_longlong), ("lag_in_repr", C.c_int32),
+                ("lag_out_repr", C.c_int32)]
 
 
 class SeDesc(C.Structure):
@@ -44,7 +46,7 @@ class RolloutHostDesc(C.Structure):
                 ("dt", C.c_double), ("x0_host", C.c_void_p), ("xT_host", C.c_void_p), ("u_host", C.c_void_p),
                 ("u_shared", C.c_int32), ("reserved", C.c_int32), ("lag_in_host", C.c_void_p),
                 ("lag_out_host", C.c_void_p), ("traj_host", C.c_void_p), ("stride", C.c_longlong),
-                ("chunk_steps", C.c_longlong)]
+                ("chunk_steps", C.c_longlong), ("lag_in_repr", C.c_int32), ("lag_out_repr", C.c_int32)]
 
 
 _DP = C.POINTER(C.c_double)

@@ -425,10 +425,12 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
     a.traj = (T*)d->traj_dev;
     a.snap_base = d->snap_base; a.step0 = d->step0;
     a.n = (int)d->n; a.steps = (int)d->steps; a.stride = (int)(d->traj_dev ? d->stride : 1);
+    const bool lagw = e->model == BROV_THRUSTER8_LAG3 && (d->lag_out_repr == BROV_LAG_PROJECTED || d->lag_out_dev == nullptr);
+    a.lag_in_w = (e->model == BROV_THRUSTER8_LAG3 && d->lag_in_repr == BROV_LAG_PROJECTED) ? 1 : 0;
     const size_t ualign = (sizeof(T) == 4 && NU == 6) ? 8 : 16;
     a.u_vec = aligned(d->u_dev, ualign) && (d->u_stride_t * sizeof(T)) % ualign == 0 && (d->u_stride_n * sizeof(T)) % ualign == 0;
     a.traj_vec = d->traj_dev && aligned(d->traj_dev, 16) && ((size_t)d->n * NX * sizeof(T)) % 16 == 0;
-    CUDA_TRY(launch_rollout<T>(e->model, d->integrator, e->use_lag1 != 0, a, st));
+    CUDA_TRY(launch_rollout<T>(e->model, d->integrator, e->use_lag1 != 0, lagw, a, st));
     return BROV_OK;
 }
 
@@ -451,6 +453,9 @@ extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* 
     if (d->steps > 0 && !d->u_dev) return fail(BROV_EINVAL, "u is NULL");
     if (d->u_stride_t < 0 || d->u_stride_n < 0) return fail(BROV_EINVAL, "negative input stride");
     if (d->traj_dev && d->stride < 1) return fail(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
+    if (d->lag_in_repr < 0 || d->lag_in_repr > 1 || d->lag_out_repr < 0 || d->lag_out_repr > 1) return fail(BROV_EINVAL, "unknown lag representation");
+    if (e->model == BROV_THRUSTER8_LAG3 && d->lag_in_dev && d->lag_in_repr == BROV_LAG_PROJECTED && d->lag_out_dev && d->lag_out_repr == BROV_LAG_THRUSTER)
+        return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in");
     if (d->traj_dev && (d->step0 < 0 || d->step0 / d->stride < d->snap_base)) return fail(BROV_EINVAL, "snap_base lies after the first snapshot of this call");
     CUDA_TRY(cudaSetDevice(e->device));
     if (d->steps == 0) {
@@ -458,7 +463,10 @@ extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* 
         if (d->xT_dev != d->x0_dev)
             CUDA_TRY(cudaMemcpyAsync(d->xT_dev, d->x0_dev, (size_t)d->n * model_nx(e->model) * sz, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         if (d->lag_out_dev && model_nlag(e)) {
-            const size_t lb = (size_t)d->n * model_nlag(e) * sz;
+            if (d->lag_in_dev && d->lag_in_repr != d->lag_out_repr && e->model == BROV_THRUSTER8_LAG3)
+                return fail(BROV_EUNSUPPORTED, "a zero-step rollout cannot change the lag representation");
+            const int nl = (e->model == BROV_THRUSTER8_LAG3 && d->lag_out_repr == BROV_LAG_PROJECTED) ? 18 : model_nlag(e);
+            const size_t lb = (size_t)d->n * nl * sz;
             if (d->lag_in_dev) { if (d->lag_in_dev != d->lag_out_dev) CUDA_TRY(cudaMemcpyAsync(d->lag_out_dev, d->lag_in_dev, lb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); }
             else CUDA_TRY(cudaMemsetAsync(d->lag_out_dev, 0, lb, (cudaStream_t)stream));
         }
@@ -469,7 +477,7 @@ extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* 
 
 extern "C" size_t brov_se_workspace_bytes(long long n_windows) {
     if (n_windows < 1) n_windows = 1;
-    return (size_t)((n_windows + SE_BLOCK - 1) / SE_BLOCK) * MAX_H * sizeof(double);
+    return (size_t)((n_windows + 63) / 64) * MAX_H * sizeof(double);  // the smaller (fp64) block size
 }
 
 template <typename T>
@@ -481,8 +489,7 @@ static int se_impl(brov_engine* e, const brov_se_desc* d, cudaStream_t st) {
     a.partial = (double*)d->workspace_dev;
     a.rows = (int)d->rows; a.nwin = (int)d->n_windows; a.nH = d->n_horizons;
     for (int h = 0; h < MAX_H; ++h) a.H[h] = h < d->n_horizons ? d->horizons[h] : 0x7fffffff;
-    const int nblocks = (int)((d->n_windows + SE_BLOCK - 1) / SE_BLOCK);
-    CUDA_TRY(launch_se<T>(e->model, d->integrator, a, nblocks, d->se_out_dev, st));
+    CUDA_TRY(launch_se<T>(e->model, d->integrator, a, d->se_out_dev, st));
     return BROV_OK;
 }
 
@@ -599,8 +606,16 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
     }
 
     CUDA_TRY(cudaMemcpyAsync(h.d_x, d->x0_host, snap_bytes, cudaMemcpyHostToDevice, h.s_compute));
+    // thruster model: chunks carry the allocation-projected lag unless per-thruster states are wanted back
+    const bool thr = e->model == BROV_THRUSTER8_LAG3;
+    if (d->lag_in_repr < 0 || d->lag_in_repr > 1 || d->lag_out_repr < 0 || d->lag_out_repr > 1) return fail(BROV_EINVAL, "unknown lag representation");
+    const int carry_repr = (thr && (d->lag_out_host == nullptr || d->lag_out_repr == BROV_LAG_PROJECTED)) ? BROV_LAG_PROJECTED : BROV_LAG_THRUSTER;
+    if (thr && d->lag_in_host && d->lag_in_repr == BROV_LAG_PROJECTED && carry_repr == BROV_LAG_THRUSTER)
+        return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in");
+    const int nl_in = (thr && d->lag_in_repr == BROV_LAG_PROJECTED) ? 18 : NLAG;
+    const int nl_out = (thr && carry_repr == BROV_LAG_PROJECTED) ? 18 : NLAG;
     if (NLAG) {
-        if (d->lag_in_host) CUDA_TRY(cudaMemcpyAsync(h.d_lag, d->lag_in_host, (size_t)n * NLAG * sz, cudaMemcpyHostToDevice, h.s_compute));
+        if (d->lag_in_host) CUDA_TRY(cudaMemcpyAsync(h.d_lag, d->lag_in_host, (size_t)n * nl_in * sz, cudaMemcpyHostToDevice, h.s_compute));
         else CUDA_TRY(cudaMemsetAsync(h.d_lag, 0, (size_t)n * NLAG * sz, h.s_compute));
     }
     long long done = 0;
@@ -625,6 +640,8 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
         r.lag_in_dev = NLAG ? h.d_lag : nullptr; r.lag_out_dev = NLAG ? h.d_lag : nullptr;
         r.traj_dev = d->traj_host ? h.d_traj[b] : nullptr;
         r.stride = d->traj_host ? d->stride : 1; r.step0 = done; r.snap_base = first_snap;
+        r.lag_in_repr = (c == 0) ? (d->lag_in_host ? d->lag_in_repr : carry_repr) : carry_repr;
+        r.lag_out_repr = carry_repr;
         if ((rc = brov_rollout(e, &r, h.s_compute))) return rc;
         CUDA_TRY(cudaEventRecord(h.ev_done[b], h.s_compute));
         if (d->traj_host && last_snap > first_snap) {
@@ -635,7 +652,7 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
         done += len;
     }
     CUDA_TRY(cudaMemcpyAsync(d->xT_host, h.d_x, snap_bytes, cudaMemcpyDeviceToHost, h.s_compute));
-    if (NLAG && d->lag_out_host) CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag, (size_t)n * NLAG * sz, cudaMemcpyDeviceToHost, h.s_compute));
+    if (NLAG && d->lag_out_host) CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag, (size_t)n * nl_out * sz, cudaMemcpyDeviceToHost, h.s_compute));
     CUDA_TRY(cudaStreamSynchronize(h.s_in));
     CUDA_TRY(cudaStreamSynchronize(h.s_compute));
     CUDA_TRY(cudaStreamSynchronize(h.s_out));

@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace brov {
 
@@ -103,24 +104,28 @@ __device__ __forceinline__ void sincos_(float a, float* s, float* c) {
     *s = (q & 2) ? -ss : ss;
     *c = ((q + 1) & 2) ? -cc : cc;
 }
+// [0] 2/pi, [1..3] pi/2 in three parts, [4..9] sin coefficients S1..S6, [10..15] cos coefficients C1..C6 (fdlibm)
+static __constant__ double kSinCos64[16] = {
+    0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+    2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+    -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
 // fp64: same scheme with the fdlibm __kernel_sin/__kernel_cos coefficients.  The FMA makes each reduction step a
 // single rounding, so full-precision parts of pi/2 suffice.  Domain |a| < 2^30 rad (quadrant held in an int).
 __device__ __forceinline__ void sincos_(double a, double* s, double* c) {
-    double j = rint(a * 0.6366197723675814);
-    double r = fma(-j, 1.5707963267948966, a);
-    r = fma(-j, 6.123233995736766e-17, r);
-    r = fma(-j, -1.4973849048591698e-33, r);
+    const double* K = kSinCos64;  // constant bank: 64-bit literals would otherwise be rebuilt with UMOV pairs per use
+    double j = rint(a * K[0]);
+    double r = fma(-j, K[1], a);
+    r = fma(-j, K[2], r);
+    r = fma(-j, K[3], r);
     int q = (int)j;
     double z = r * r;
-    double ps = fma(fma(fma(fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08), z,
-                            2.75573137070700676789e-06), z, -1.98412698298579493134e-04), z,
-                    8.33333333332248946124e-03);
-    ps = fma(ps, z, -1.66666666666666324348e-01);
+    double ps = fma(fma(fma(fma(K[9], z, K[8]), z, K[7]), z, K[6]), z, K[5]);
+    ps = fma(ps, z, K[4]);
     double sn = fma(ps * z, r, r);
-    double pc = fma(fma(fma(fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09), z,
-                            -2.75573143513906633035e-07), z, 2.48015872894767294178e-05), z,
-                    -1.38888888888741095749e-03);
-    pc = fma(pc, z, 4.16666666666666019037e-02);
+    double pc = fma(fma(fma(fma(K[15], z, K[14]), z, K[13]), z, K[12]), z, K[11]);
+    pc = fma(pc, z, K[10]);
     double cs = fma(pc * z, z, fma(-0.5, z, 1.0));
     double ss = (q & 1) ? cs : sn;
     double cc = (q & 1) ? sn : cs;
@@ -267,16 +272,22 @@ template <typename T> __device__ __forceinline__ void quat_renorm(T* q) {
     else { T in = rcp_(n); q[0] *= in; q[1] *= in; q[2] *= in; q[3] *= in; }
 }
 
-// Thruster wrench seen by sub-step j of a step: y_i = G_j . lag_i + H_j F_i ; tau = alloc y.
+// ---------------------------------------------------------------------------------------------------------------
+// 3rd-order thruster lag, closed form over the sub-steps of one integrator step (input held).
+// The lag state lives either in registers (LS = 1) or in shared memory laid out [component][thread] (LS = block size).
+//
+// LAGW = false: thruster coordinates, lag[8][3] = ThrusterLag._x of each thruster (the reference's hidden state).
+//     y_i = G_j . lag_i + H_j F_i ; tau = alloc y                                   (128 + 124 ops per RK4 step)
+// LAGW = true : allocation-projected coordinates Z[6][3] = sum_i alloc[c][i] lag_i.  The eight lags are copies of ONE
+//     linear filter, so any fixed linear combination of their states obeys the same recurrence driven by the same
+//     combination of the inputs: tau_c = G_j . Z_c + H_j (alloc F)_c ; Z_c <- A Z_c + B (alloc F)_c.   (31 + 96 ops)
+//     Identical dynamics (rounding differs at 1e-16), 18 instead of 24 hidden values, but the per-thruster states
+//     cannot be recovered from Z — used when the caller does not ask for them.
+// ---------------------------------------------------------------------------------------------------------------
 template <typename T>
-__device__ __forceinline__ void thruster_tau(const Consts<T>& c, int j, const T* __restrict__ lag,
-                                             const T* __restrict__ F, T* __restrict__ tau) {
-    T y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        y[i] = c.lagG[j][0] * lag[3 * i] + c.lagG[j][1] * lag[3 * i + 1] + c.lagG[j][2] * lag[3 * i + 2] + c.lagH[j] * F[i];
-    // rows 0..2 and 5 of the allocation matrix are structurally sparse (horizontal thrusters have no z
-    // component, vertical ones only z); their zero entries are skipped at compile time below.
+__device__ __forceinline__ void allocate_wrench(const Consts<T>& c, const T* __restrict__ y, T* __restrict__ tau) {
+    // rows 0..2 and 5 of the allocation matrix are structurally sparse (horizontal thrusters have no z component,
+    // vertical ones only z); their zero entries are skipped at compile time (brov_set_allocation enforces them).
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
         T s = T(0);
@@ -289,62 +300,105 @@ __device__ __forceinline__ void thruster_tau(const Consts<T>& c, int j, const T*
     }
 }
 
-template <typename T>
-__device__ __forceinline__ void lag_advance(const Consts<T>& c, T* __restrict__ lag, const T* __restrict__ F) {
+template <typename T, int LS, bool LAGW, class LP>
+__device__ __forceinline__ void thruster_tau(const Consts<T>& c, int j, LP lag, const T* __restrict__ F,
+                                             T* __restrict__ tau) {
+    if constexpr (LAGW) {  // F holds alloc*F (6 values)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        T a = lag[3 * i], b = lag[3 * i + 1], d = lag[3 * i + 2];
-        lag[3 * i + 0] = c.lagA[0][0] * a + c.lagA[0][1] * b + c.lagA[0][2] * d + c.lagB[0] * F[i];
-        lag[3 * i + 1] = c.lagA[1][0] * a + c.lagA[1][1] * b + c.lagA[1][2] * d + c.lagB[1] * F[i];
-        lag[3 * i + 2] = c.lagA[2][0] * a + c.lagA[2][1] * b + c.lagA[2][2] * d + c.lagB[2] * F[i];
+        for (int r = 0; r < 6; ++r)
+            tau[r] = c.lagG[j][0] * lag[(3 * r) * LS] + c.lagG[j][1] * lag[(3 * r + 1) * LS] +
+                     c.lagG[j][2] * lag[(3 * r + 2) * LS] + c.lagH[j] * F[r];
+    } else {
+        T y[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            y[i] = c.lagG[j][0] * lag[(3 * i) * LS] + c.lagG[j][1] * lag[(3 * i + 1) * LS] +
+                   c.lagG[j][2] * lag[(3 * i + 2) * LS] + c.lagH[j] * F[i];
+        allocate_wrench<T>(c, y, tau);
+    }
+}
+
+template <typename T, int LS, bool LAGW, class LP>
+__device__ __forceinline__ void lag_advance(const Consts<T>& c, LP lag, const T* __restrict__ F) {
+#pragma unroll
+    for (int i = 0; i < (LAGW ? 6 : 8); ++i) {
+        T a = lag[(3 * i) * LS], b = lag[(3 * i + 1) * LS], d = lag[(3 * i + 2) * LS];
+        lag[(3 * i + 0) * LS] = c.lagA[0][0] * a + c.lagA[0][1] * b + c.lagA[0][2] * d + c.lagB[0] * F[i];
+        lag[(3 * i + 1) * LS] = c.lagA[1][0] * a + c.lagA[1][1] * b + c.lagA[1][2] * d + c.lagB[1] * F[i];
+        lag[(3 * i + 2) * LS] = c.lagA[2][0] * a + c.lagA[2][1] * b + c.lagA[2][2] * d + c.lagB[2] * F[i];
+    }
+}
+
+// thruster-coordinate lag state (registers) -> allocation-projected state Z[6][3] (storage stride LS)
+template <typename T, int LS, class LP>
+__device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restrict__ lag24, LP Z) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        T y[8], t[6];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = lag24[3 * i + k];
+        allocate_wrench<T>(c, y, t);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) Z[(3 * r + k) * LS] = t[r];
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// one integrator step of one vehicle, everything in registers
-//   x[NX]   state (in/out)
-//   lag[]   THRUSTER8: 8x3 lag state; wrench models with LAG1: the 6 filtered wrench components
+// one integrator step of one vehicle
+//   x[NX]   state (registers, in/out)
+//   lag     THRUSTER8: lag state, 8x3 (LAGW = false) or 6x3 (LAGW = true), storage stride LS;
+//           wrench models with LAG1: the 6 filtered wrench components (registers, LS = 1)
 //   u[NU]   input held over the step
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODEL, bool LAG1, class P>
+template <typename T, int MODEL, bool LAG1, int LS, bool LAGW, class P, class LP>
 __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int substep, const T* __restrict__ x,
-                                          const T* __restrict__ lag, const T* __restrict__ Fu,
+                                          LP lag, const T* __restrict__ Fu,
                                           T* __restrict__ xd, T* __restrict__ lagd) {
-    // Fu: THRUSTER8 -> static thrust F[8] of this step;  wrench models -> commanded wrench u[6]
+    // Fu: THRUSTER8 -> static thrust F[8] of this step (or alloc*F[6] when LAGW); wrench models -> commanded wrench
     if constexpr (MODEL == MODEL_THRUSTER8) {
         T tau[6];
-        thruster_tau<T>(c, substep, lag, Fu, tau);
+        thruster_tau<T, LS, LAGW, LP>(c, substep, lag, Fu, tau);
         rhs_euler12<T>(x, tau, p, c.has_current != 0, xd);
     } else {
+        T tl[6];
         const T* tau = Fu;
         if constexpr (LAG1) {
-            tau = lag;
             const T il = p[KP_ILAG1];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) lagd[i] = (Fu[i] - lag[i]) * il;
+            for (int i = 0; i < 6; ++i) { tl[i] = lag[i]; lagd[i] = (Fu[i] - tl[i]) * il; }
+            tau = tl;
         }
         if constexpr (MODEL == MODEL_WRENCH12) rhs_euler12<T>(x, tau, p, c.has_current != 0, xd);
         else rhs_quat13<T>(x, tau, p, c.has_current != 0, xd);
     }
 }
 
-template <typename T, int MODEL, int INTEG, bool LAG1, class P>
-__device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x,
-                                               T* __restrict__ lag, const T* __restrict__ u) {
+// AS: element stride of the RK4 accumulator: 1 = registers; otherwise `acc_sm` points at this thread's column of a
+// shared-memory array [NX][AS] (fp64 build: frees 24 registers so that 14 warps fit an SM without spilling).
+template <typename T, int MODEL, int INTEG, bool LAG1, int LS, bool LAGW, int AS, class P, class LP, class AP>
+__device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x, LP lag,
+                                               const T* __restrict__ u, AP acc_sm) {
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NL = LAG1 ? 6 : 1;  // continuous auxiliary states integrated with x
     const T dt = c.dt;
     T Fu[ModelDim<MODEL>::NU];
     if constexpr (MODEL == MODEL_THRUSTER8) {
+        T F[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) Fu[i] = thrust_poly<T>(u[i]);
+        for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(u[i]);
+        if constexpr (LAGW) {
+            allocate_wrench<T>(c, F, Fu);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) Fu[i] = F[i];
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 6; ++i) Fu[i] = u[i];
     }
     T k[NX], kl[NL];
     if constexpr (INTEG == INTEG_EULER) {
-        model_rhs<T, MODEL, LAG1>(c, p, 0, x, lag, Fu, k, kl);
+        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, lag, Fu, k, kl);
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt * k[i];
         if constexpr (LAG1) {
@@ -353,39 +407,44 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         }
     } else {
         // classic RK4 in low-storage form: acc accumulates k1 + 2 k2 + 2 k3 + k4, xs is the stage state
-        T acc[NX], xs[NX], accl[NL], ls[NL];
+        T acc_regs[AS == 1 ? NX : 1], xs[NX], accl[NL], ls[NL];
+        typename std::conditional<AS == 1, T*, AP>::type acc;
+        if constexpr (AS == 1) acc = acc_regs; else acc = acc_sm;
         const T hdt = T(0.5) * dt;
-        model_rhs<T, MODEL, LAG1>(c, p, 0, x, lag, Fu, k, kl);
+        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, lag, Fu, k, kl);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i] = k[i]; xs[i] = x[i] + hdt * k[i]; }
+        for (int i = 0; i < NX; ++i) { acc[i * AS] = k[i]; xs[i] = x[i] + hdt * k[i]; }
         if constexpr (LAG1) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) { accl[i] = kl[i]; ls[i] = lag[i] + hdt * kl[i]; }
         }
-        model_rhs<T, MODEL, LAG1>(c, p, 1, xs, LAG1 ? ls : lag, Fu, k, kl);
+        if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, 1, xs, ls, Fu, k, kl);
+        else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 1, xs, lag, Fu, k, kl);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i] += T(2) * k[i]; xs[i] = x[i] + hdt * k[i]; }
+        for (int i = 0; i < NX; ++i) { acc[i * AS] += T(2) * k[i]; xs[i] = x[i] + hdt * k[i]; }
         if constexpr (LAG1) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) { accl[i] += T(2) * kl[i]; ls[i] = lag[i] + hdt * kl[i]; }
         }
-        model_rhs<T, MODEL, LAG1>(c, p, 2, xs, LAG1 ? ls : lag, Fu, k, kl);
+        if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, 2, xs, ls, Fu, k, kl);
+        else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 2, xs, lag, Fu, k, kl);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i] += T(2) * k[i]; xs[i] = x[i] + dt * k[i]; }
+        for (int i = 0; i < NX; ++i) { acc[i * AS] += T(2) * k[i]; xs[i] = x[i] + dt * k[i]; }
         if constexpr (LAG1) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) { accl[i] += T(2) * kl[i]; ls[i] = lag[i] + dt * kl[i]; }
         }
-        model_rhs<T, MODEL, LAG1>(c, p, 3, xs, LAG1 ? ls : lag, Fu, k, kl);
+        if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, 3, xs, ls, Fu, k, kl);
+        else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 3, xs, lag, Fu, k, kl);
         const T dt6 = dt * T(1.0 / 6.0);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i] + k[i]);
+        for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i * AS] + k[i]);
         if constexpr (LAG1) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) lag[i] += dt6 * (accl[i] + kl[i]);
         }
     }
-    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T>(c, lag, Fu);
+    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LS, LAGW, LP>(c, lag, Fu);
     if constexpr (MODEL == MODEL_QUAT13) quat_renorm<T>(x + 3);
 }
 

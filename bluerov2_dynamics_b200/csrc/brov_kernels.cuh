@@ -18,9 +18,15 @@
 namespace brov {
 
 constexpr int MAX_H = 4;          // horizons per se launch
-constexpr int ROLLOUT_BLOCK = 128;
-constexpr int SE_BLOCK = 128;
+constexpr int RHS_BLOCK = 128;
 constexpr int RED9_BLOCK = 256;
+// Threads per block of the per-vehicle kernels.  fp32: 128.  fp64: 64 — with <= 144 registers seven such blocks fit
+// an SM (14 warps) and BASELINE's 65,536-vehicle ensemble is exactly ONE wave of 1024 blocks on 148 x 7 slots.
+template <typename T> struct BlockOf { static constexpr int N = sizeof(T) == 8 ? 64 : 128; };
+// fp64 keeps the thruster-lag state in shared memory ([component][thread]); fp32 keeps it in registers.
+template <typename T> struct LagInSmem { static constexpr bool V = sizeof(T) == 8; };
+// fp64 also keeps the RK4 accumulator in shared memory and does not hold next-step inputs in registers.
+template <typename T> struct AccInSmem { static constexpr bool V = sizeof(T) == 8; };
 
 template <typename T> struct RolloutArgs {
     Consts<T> c;
@@ -28,14 +34,15 @@ template <typename T> struct RolloutArgs {
     T* xT;              // [n][NX] (may alias x0)
     const T* U;         // element (k, i, j) at U[k*u_stride_t + i*u_stride_n + j]
     long long u_stride_t, u_stride_n;
-    const T* lag_in;    // [n][NLAG] or nullptr (zeros)
-    T* lag_out;         // [n][NLAG] or nullptr
+    const T* lag_in;    // [n][NLAG] or nullptr (zeros); thruster model: 24 values, or 18 if lag_in_w
+    T* lag_out;         // [n][NLAG] or nullptr; thruster model: 24 values (LAGW = false) or 18 (LAGW = true)
     const T* pv;        // [KP_COUNT][n] or nullptr
     T* traj;            // snapshot s (global step (s+1)*stride) at traj[(s - snap_base)*n*NX ...] or nullptr
     long long snap_base;
     long long step0;    // global index of the first step of this launch
     int n, steps, stride;
     int u_vec, traj_vec;
+    int lag_in_w;       // lag_in holds allocation-projected states [n][6][3]
 };
 
 template <typename T> struct RhsArgs {
@@ -122,45 +129,93 @@ __device__ __forceinline__ void snapshot_warp(T* __restrict__ tile, const T* __r
 // ---------------------------------------------------------------------------------------------------------------
 // rollout
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODEL, bool LAG1> struct LagRegs {
-    static constexpr int N = (MODEL == MODEL_THRUSTER8) ? 24 : (LAG1 ? 6 : 1);
+template <typename T, int MODEL, bool LAG1, bool LAGW = false> struct LagRegs {
+    static constexpr int N = (MODEL == MODEL_THRUSTER8) ? (LAGW ? 18 : 24) : (LAG1 ? 6 : 1);
     static constexpr bool HAS = (MODEL == MODEL_THRUSTER8) || LAG1;
+    static constexpr bool SMEM = (MODEL == MODEL_THRUSTER8) && LagInSmem<T>::V;
 };
 
-template <typename T, int MODEL, int INTEG, bool LAG1, bool PV>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
+// Loads the lag state of vehicle i into its storage (registers or shared memory, stride LS).
+template <typename T, int MODEL, bool LAG1, bool LAGW, int LS, class LP>
+__device__ __forceinline__ void load_lag(const Consts<T>& c, const T* __restrict__ src, bool src_is_w, long long i,
+                                         LP lag) {
+    constexpr int NL = LagRegs<T, MODEL, LAG1, LAGW>::N;
+    if (!LagRegs<T, MODEL, LAG1, LAGW>::HAS || src == nullptr) {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) lag[j * LS] = T(0);
+        return;
+    }
+    if constexpr (MODEL == MODEL_THRUSTER8 && LAGW) {
+        if (src_is_w) {
+#pragma unroll
+            for (int j = 0; j < 18; ++j) lag[j * LS] = __ldg(src + i * 18 + j);
+        } else {
+            T t[24];
+#pragma unroll
+            for (int j = 0; j < 24; ++j) t[j] = __ldg(src + i * 24 + j);
+            project_lag<T, LS, LP>(c, t, lag);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NL; ++j) lag[j * LS] = __ldg(src + i * NL + j);
+    }
+}
+
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool LAGW>
+__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(sizeof(T) == 8 ? 144 : 128)
+rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
+    constexpr int BLOCK = BlockOf<T>::N;
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NU = ModelDim<MODEL>::NU;
-    constexpr int NL = LagRegs<T, MODEL, LAG1>::N;
-    constexpr bool HASLAG = LagRegs<T, MODEL, LAG1>::HAS;
+    using LR = LagRegs<T, MODEL, LAG1, LAGW>;
+    constexpr int NL = LR::N;
+    constexpr int LS = LR::SMEM ? BLOCK : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const long long gi = (long long)blockIdx.x * ROLLOUT_BLOCK + tid;
+    const long long gi = (long long)blockIdx.x * BLOCK + tid;
     const bool live = gi < a.n;
     const long long i = live ? gi : (long long)a.n - 1;  // dead lanes shadow the last vehicle, never store
 
-    T* tiles = smem;
+    // shared memory: [per-vehicle coefficient table][lag state (fp64)][snapshot tiles]
     typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type p;
     if constexpr (PV) {
 #pragma unroll 4
-        for (int j = 0; j < KP_COUNT; ++j) smem[j * ROLLOUT_BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
-        __syncthreads();
+        for (int j = 0; j < KP_COUNT; ++j) smem[j * BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
         p.base = smem + tid;
-        p.pitch = ROLLOUT_BLOCK;
-        tiles = smem + KP_COUNT * ROLLOUT_BLOCK;
+        p.pitch = BLOCK;
+        smem += KP_COUNT * BLOCK;
     } else {
         p.kp = a.c.kp;
     }
+    // shared-memory residents are accessed through volatile pointers: without it the compiler promotes them back
+    // into registers for the whole step, which is exactly what the placement is meant to avoid
+    using LP = typename std::conditional<LR::SMEM, volatile T*, T*>::type;
+    T lag_regs[LR::SMEM ? 1 : NL];
+    LP lag;
+    if constexpr (LR::SMEM) {
+        lag = smem + tid;
+        smem += NL * BLOCK;
+    } else {
+        lag = lag_regs;
+    }
+    constexpr bool ACC_SM = AccInSmem<T>::V && INTEG == INTEG_RK4;
+    constexpr int AS = ACC_SM ? BLOCK : 1;
+    using AP = typename std::conditional<ACC_SM, volatile T*, T*>::type;
+    AP acc_sm = nullptr;
+    if constexpr (ACC_SM) {
+        acc_sm = smem + tid;
+        smem += NX * BLOCK;
+    }
+    T* tiles = smem;
+    if constexpr (PV) __syncthreads();
 
     T x[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) x[j] = __ldg(a.x0 + i * NX + j);
-    T lag[NL];
-#pragma unroll
-    for (int j = 0; j < NL; ++j) lag[j] = (HASLAG && a.lag_in) ? __ldg(a.lag_in + i * NL + j) : T(0);
+    load_lag<T, MODEL, LAG1, LAGW, LS, LP>(a.c, a.lag_in, a.lag_in_w != 0, i, lag);
 
     const T* up = a.U + i * a.u_stride_n;
     const bool uvec = a.u_vec != 0;
@@ -170,17 +225,22 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const __grid_con
 
     int countdown = a.traj ? (int)(a.stride - (a.step0 % a.stride)) : 0x7fffffff;
     long long snap = a.traj ? (a.step0 / a.stride - a.snap_base) : 0;
-    const long long warp_v0 = (long long)blockIdx.x * ROLLOUT_BLOCK + warp * 32;
+    const long long warp_v0 = (long long)blockIdx.x * BLOCK + warp * 32;
     const long long rem = (long long)a.n - warp_v0;
     const int n_valid = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem)) * NX;
 
+    constexpr bool PREFETCH = !AccInSmem<T>::V;  // fp32: next step's inputs ride in registers across the step
     for (int k = 0; k < a.steps; ++k) {
-        // prefetch the next step's inputs before the ~1e3 dependent FP ops of this step
         T un[NU];
-        const T* nxt = up + (long long)((k + 1 < a.steps) ? (k + 1) : k) * a.u_stride_t;
-        if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
+        if constexpr (PREFETCH) {
+            const T* nxt = up + (long long)((k + 1 < a.steps) ? (k + 1) : k) * a.u_stride_t;
+            if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
+        } else if (k > 0) {
+            const T* cur = up + (long long)k * a.u_stride_t;
+            if (stream) load_u<T, NU, true>(cur, uvec, u); else load_u<T, NU, false>(cur, uvec, u);
+        }
 
-        integrate_step<T, MODEL, INTEG, LAG1>(a.c, p, x, lag, u);
+        integrate_step<T, MODEL, INTEG, LAG1, LS, LAGW, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm);
 
         if (--countdown == 0) {
             countdown = a.stride;
@@ -188,16 +248,18 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const __grid_con
             snapshot_warp<T, NX>(tiles + warp * 32 * NX, x, dst, n_valid, a.traj_vec != 0, lane);
             ++snap;
         }
+        if constexpr (PREFETCH) {
 #pragma unroll
-        for (int j = 0; j < NU; ++j) u[j] = un[j];
+            for (int j = 0; j < NU; ++j) u[j] = un[j];
+        }
     }
 
     if (live) {
 #pragma unroll
         for (int j = 0; j < NX; ++j) a.xT[i * NX + j] = x[j];
-        if (HASLAG && a.lag_out) {
+        if (LR::HAS && a.lag_out) {
 #pragma unroll
-            for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j];
+            for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j * LS];
         }
     }
 }
@@ -206,7 +268,8 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rollout_kernel(const __grid_con
 // single state-derivative evaluation (the reference's dynamics(): the 3rd-order lag advances by ONE sub-step)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, bool LAG1, bool PV>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) rhs_kernel(const __grid_constant__ RhsArgs<T> a) {
+__global__ void __launch_bounds__(RHS_BLOCK) rhs_kernel(const __grid_constant__ RhsArgs<T> a) {
+    constexpr int ROLLOUT_BLOCK = RHS_BLOCK;
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NU = ModelDim<MODEL>::NU;
     constexpr int NL = LagRegs<T, MODEL, LAG1>::N;
@@ -234,7 +297,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rhs_kernel(const __grid_constan
     for (int j = 0; j < NL; ++j) lag[j] = (LagRegs<T, MODEL, LAG1>::HAS && a.lag) ? a.lag[i * NL + j] : T(0);
 #pragma unroll
     for (int j = 0; j < NU; ++j) Fu[j] = (MODEL == MODEL_THRUSTER8) ? thrust_poly<T>(u[j]) : u[j];
-    model_rhs<T, MODEL, LAG1>(a.c, p, 0, x, lag, Fu, xd, lagd);
+    model_rhs<T, MODEL, LAG1, 1, false, decltype(p), const T*>(a.c, p, 0, x, lag, Fu, xd, lagd);
     if (!live) return;
 #pragma unroll
     for (int j = 0; j < NX; ++j) a.xdot[i * (NX + (LAG1 ? 6 : 0)) + j] = xd[j];
@@ -244,7 +307,7 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) rhs_kernel(const __grid_constan
     }
     if constexpr (MODEL == MODEL_THRUSTER8) {
         if (a.lag) {
-            lag_advance<T>(a.c, lag, Fu);
+            lag_advance<T, 1, false, T*>(a.c, lag, Fu);
 #pragma unroll
             for (int j = 0; j < NL; ++j) a.lag[i * NL + j] = lag[j];
         }
@@ -264,8 +327,8 @@ template <typename T> struct ThrusterArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) thruster_wrench_kernel(const __grid_constant__ ThrusterArgs<T> a) {
-    const long long i = (long long)blockIdx.x * ROLLOUT_BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(RHS_BLOCK) thruster_wrench_kernel(const __grid_constant__ ThrusterArgs<T> a) {
+    const long long i = (long long)blockIdx.x * RHS_BLOCK + threadIdx.x;
     if (i >= a.n) return;
     T u[8], F[8], lag[24], tau[6];
     load_u<T, 8, false>(a.u + i * 8, (reinterpret_cast<uintptr_t>(a.u) & 15) == 0, u);
@@ -273,11 +336,11 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) thruster_wrench_kernel(const __
     for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
 #pragma unroll
     for (int j = 0; j < 24; ++j) lag[j] = a.lag ? a.lag[i * 24 + j] : T(0);
-    thruster_tau<T>(a.c, 0, lag, F, tau);
+    thruster_tau<T, 1, false, const T*>(a.c, 0, lag, F, tau);
 #pragma unroll
     for (int j = 0; j < 6; ++j) a.tau[i * 6 + j] = tau[j];
     if (a.lag) {
-        lag_advance<T>(a.c, lag, F);
+        lag_advance<T, 1, false, T*>(a.c, lag, F);
 #pragma unroll
         for (int j = 0; j < 24; ++j) a.lag[i * 24 + j] = lag[j];
     }
@@ -287,23 +350,38 @@ __global__ void __launch_bounds__(ROLLOUT_BLOCK) thruster_wrench_kernel(const __
 // multi-horizon endpoint squared error over sliding windows
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, int INTEG>
-__global__ void __launch_bounds__(SE_BLOCK) se_kernel(const __grid_constant__ SeArgs<T> a) {
+__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(sizeof(T) == 8 ? 144 : 128)
+se_kernel(const __grid_constant__ SeArgs<T> a) {
+    constexpr int BLOCK = BlockOf<T>::N;
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NU = ModelDim<MODEL>::NU;
-    constexpr int NL = LagRegs<T, MODEL, false>::N;
-    __shared__ double red[SE_BLOCK / 32][MAX_H];
+    // the evaluator never returns lag states: the thruster model always runs on the allocation-projected lag
+    using LR = LagRegs<T, MODEL, false, true>;
+    constexpr int NL = LR::N;
+    constexpr int LS = LR::SMEM ? BLOCK : 1;
+    __shared__ double red[BLOCK / 32][MAX_H];
+    __shared__ T lag_sm[LR::SMEM ? NL * BLOCK : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long gk = (long long)blockIdx.x * SE_BLOCK + tid;
+    const long long gk = (long long)blockIdx.x * BLOCK + tid;
     const bool live = gk < a.nwin;
     const long long k = live ? gk : 0;
     ParamsConst<T> p;
     p.kp = a.c.kp;
 
-    T x[NX], lag[NL];
+    T x[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + k * NX + j);
-#pragma unroll
-    for (int j = 0; j < NL; ++j) lag[j] = (MODEL == MODEL_THRUSTER8 && a.lag0) ? __ldg(a.lag0 + k * NL + j) : T(0);
+    using LP = typename std::conditional<LR::SMEM, volatile T*, T*>::type;
+    constexpr bool ACC_SM = AccInSmem<T>::V && INTEG == INTEG_RK4;
+    constexpr int AS = ACC_SM ? BLOCK : 1;
+    using AP = typename std::conditional<ACC_SM, volatile T*, T*>::type;
+    __shared__ T acc_store[ACC_SM ? NX * BLOCK : 1];
+    T lag_regs[LR::SMEM ? 1 : NL];
+    LP lag;
+    if constexpr (LR::SMEM) lag = lag_sm + tid; else lag = lag_regs;
+    AP acc_sm = nullptr;
+    if constexpr (ACC_SM) acc_sm = acc_store + tid;
+    load_lag<T, MODEL, false, true, LS, LP>(a.c, a.lag0, false, k, lag);
 
     double se[MAX_H];
 #pragma unroll
@@ -316,7 +394,7 @@ __global__ void __launch_bounds__(SE_BLOCK) se_kernel(const __grid_constant__ Se
     for (int j = 0; j < nsteps; ++j) {
         T u[NU];
         load_u<T, NU, false>(a.U + (k + j) * NU, uvec, u);
-        integrate_step<T, MODEL, INTEG, false>(a.c, p, x, lag, u);
+        integrate_step<T, MODEL, INTEG, false, LS, true, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm);
 #pragma unroll
         for (int h = 0; h < MAX_H; ++h) {
             if (h < a.nH && j + 1 == a.H[h]) {
@@ -342,7 +420,7 @@ __global__ void __launch_bounds__(SE_BLOCK) se_kernel(const __grid_constant__ Se
     if (tid < MAX_H) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < SE_BLOCK / 32; ++w) v += red[w][tid];
+        for (int w = 0; w < BLOCK / 32; ++w) v += red[w][tid];
         a.partial[(long long)blockIdx.x * MAX_H + tid] = v;
     }
 }
@@ -456,11 +534,12 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 // launchers (defined in brov_kernels_impl.cuh, instantiated per scalar type)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
-cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st);
+cudaError_t launch_rollout(int model, int integ, bool lag1, bool lagw, const RolloutArgs<T>& a, cudaStream_t st);
 template <typename T>
 cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t st);
 template <typename T>
-cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, int nblocks, double* se_out, cudaStream_t st);
+cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, double* se_out, cudaStream_t st);
+template <typename T> int se_blocks(long long nwin);
 template <typename T>
 cudaError_t launch_reduced9(const Red9Consts<T>& c, const T* X, const T* U, T* O, long long B, cudaStream_t st);
 template <typename T>

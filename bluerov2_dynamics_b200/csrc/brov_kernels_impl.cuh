@@ -1,55 +1,61 @@
-// brov_kernels_impl.cuh — runtime -> template dispatch.  Included by brov_kernels_f32.cu / brov_kernels_f64.cu with
-// BROV_SCALAR defined; each instantiates every (model, integrator, lag1, per-vehicle) combination for its type.
+// brov_kernels_impl.cuh — runtime -> template dispatch.  Included by brov_kernels_f32.cu / brov_kernels_f64.cu; each
+// instantiates every (model, integrator, lag1, per-vehicle, lag representation) combination for its scalar type.
 #pragma once
 #include "brov_kernels.cuh"
 
 namespace brov {
 
-template <typename T, int MODEL, int INTEG, bool LAG1>
+template <typename T, int MODEL, int INTEG, bool LAG1, bool LAGW>
 static cudaError_t rollout_go(const RolloutArgs<T>& a, cudaStream_t st) {
+    constexpr int BLOCK = BlockOf<T>::N;
     constexpr int NX = ModelDim<MODEL>::NX;
-    const int grid = (a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
-    size_t smem = a.traj ? (size_t)(ROLLOUT_BLOCK / 32) * 32 * NX * sizeof(T) : 0;
+    using LR = LagRegs<T, MODEL, LAG1, LAGW>;
+    const int grid = (a.n + BLOCK - 1) / BLOCK;
+    size_t smem = a.traj ? (size_t)(BLOCK / 32) * 32 * NX * sizeof(T) : 0;
+    if (LR::SMEM) smem += (size_t)LR::N * BLOCK * sizeof(T);
+    if (AccInSmem<T>::V && INTEG == INTEG_RK4) smem += (size_t)NX * BLOCK * sizeof(T);
     if (a.pv) {
-        smem += (size_t)KP_COUNT * ROLLOUT_BLOCK * sizeof(T);
-        auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, true>;
+        smem += (size_t)KP_COUNT * BLOCK * sizeof(T);
+        auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, true, LAGW>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<grid, ROLLOUT_BLOCK, smem, st>>>(a);
+        kern<<<grid, BLOCK, smem, st>>>(a);
     } else {
-        rollout_kernel<T, MODEL, INTEG, LAG1, false><<<grid, ROLLOUT_BLOCK, smem, st>>>(a);
+        rollout_kernel<T, MODEL, INTEG, LAG1, false, LAGW><<<grid, BLOCK, smem, st>>>(a);
     }
     return cudaGetLastError();
 }
 
-template <typename T, int MODEL, bool LAG1>
+template <typename T, int MODEL, bool LAG1, bool LAGW>
 static cudaError_t rollout_integ(int integ, const RolloutArgs<T>& a, cudaStream_t st) {
-    return integ == INTEG_RK4 ? rollout_go<T, MODEL, INTEG_RK4, LAG1>(a, st)
-                              : rollout_go<T, MODEL, INTEG_EULER, LAG1>(a, st);
+    return integ == INTEG_RK4 ? rollout_go<T, MODEL, INTEG_RK4, LAG1, LAGW>(a, st)
+                              : rollout_go<T, MODEL, INTEG_EULER, LAG1, LAGW>(a, st);
 }
 
 template <typename T>
-cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st) {
+cudaError_t launch_rollout(int model, int integ, bool lag1, bool lagw, const RolloutArgs<T>& a, cudaStream_t st) {
     if (a.n <= 0 || a.steps <= 0) return cudaSuccess;
     switch (model) {
-        case MODEL_THRUSTER8: return rollout_integ<T, MODEL_THRUSTER8, false>(integ, a, st);
+        case MODEL_THRUSTER8:
+            return lagw ? rollout_integ<T, MODEL_THRUSTER8, false, true>(integ, a, st)
+                        : rollout_integ<T, MODEL_THRUSTER8, false, false>(integ, a, st);
         case MODEL_WRENCH12:
-            return lag1 ? rollout_integ<T, MODEL_WRENCH12, true>(integ, a, st)
-                        : rollout_integ<T, MODEL_WRENCH12, false>(integ, a, st);
+            return lag1 ? rollout_integ<T, MODEL_WRENCH12, true, false>(integ, a, st)
+                        : rollout_integ<T, MODEL_WRENCH12, false, false>(integ, a, st);
         case MODEL_QUAT13:
-            return lag1 ? rollout_integ<T, MODEL_QUAT13, true>(integ, a, st)
-                        : rollout_integ<T, MODEL_QUAT13, false>(integ, a, st);
+            return lag1 ? rollout_integ<T, MODEL_QUAT13, true, false>(integ, a, st)
+                        : rollout_integ<T, MODEL_QUAT13, false, false>(integ, a, st);
     }
     return cudaErrorInvalidValue;
 }
 
 template <typename T, int MODEL, bool LAG1>
 static cudaError_t rhs_go(const RhsArgs<T>& a, cudaStream_t st) {
-    const int grid = (a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
+    const int grid = (a.n + RHS_BLOCK - 1) / RHS_BLOCK;
     if (a.pv) {
-        size_t smem = (size_t)KP_COUNT * ROLLOUT_BLOCK * sizeof(T);
-        rhs_kernel<T, MODEL, LAG1, true><<<grid, ROLLOUT_BLOCK, smem, st>>>(a);
+        size_t smem = (size_t)KP_COUNT * RHS_BLOCK * sizeof(T);
+        rhs_kernel<T, MODEL, LAG1, true><<<grid, RHS_BLOCK, smem, st>>>(a);
     } else {
-        rhs_kernel<T, MODEL, LAG1, false><<<grid, ROLLOUT_BLOCK, 0, st>>>(a);
+        rhs_kernel<T, MODEL, LAG1, false><<<grid, RHS_BLOCK, 0, st>>>(a);
     }
     return cudaGetLastError();
 }
@@ -65,23 +71,28 @@ cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t s
     return cudaErrorInvalidValue;
 }
 
+template <typename T> int se_blocks(long long nwin) {
+    return (int)((nwin + BlockOf<T>::N - 1) / BlockOf<T>::N);
+}
+
 template <typename T, int MODEL>
-static cudaError_t se_go(int integ, const SeArgs<T>& a, int nblocks, cudaStream_t st) {
-    if (integ == INTEG_RK4) se_kernel<T, MODEL, INTEG_RK4><<<nblocks, SE_BLOCK, 0, st>>>(a);
-    else se_kernel<T, MODEL, INTEG_EULER><<<nblocks, SE_BLOCK, 0, st>>>(a);
+static cudaError_t se_go(int integ, const SeArgs<T>& a, cudaStream_t st) {
+    const int nblocks = se_blocks<T>(a.nwin);
+    if (integ == INTEG_RK4) se_kernel<T, MODEL, INTEG_RK4><<<nblocks, BlockOf<T>::N, 0, st>>>(a);
+    else se_kernel<T, MODEL, INTEG_EULER><<<nblocks, BlockOf<T>::N, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, int nblocks, double* se_out, cudaStream_t st) {
+cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, double* se_out, cudaStream_t st) {
     cudaError_t e = cudaErrorInvalidValue;
     switch (model) {
-        case MODEL_THRUSTER8: e = se_go<T, MODEL_THRUSTER8>(integ, a, nblocks, st); break;
-        case MODEL_WRENCH12: e = se_go<T, MODEL_WRENCH12>(integ, a, nblocks, st); break;
-        case MODEL_QUAT13: e = se_go<T, MODEL_QUAT13>(integ, a, nblocks, st); break;
+        case MODEL_THRUSTER8: e = se_go<T, MODEL_THRUSTER8>(integ, a, st); break;
+        case MODEL_WRENCH12: e = se_go<T, MODEL_WRENCH12>(integ, a, st); break;
+        case MODEL_QUAT13: e = se_go<T, MODEL_QUAT13>(integ, a, st); break;
     }
     if (e != cudaSuccess) return e;
-    se_finish_kernel<<<1, 256, 0, st>>>(a.partial, nblocks, se_out);
+    se_finish_kernel<<<1, 256, 0, st>>>(a.partial, se_blocks<T>(a.nwin), se_out);
     return cudaGetLastError();
 }
 
@@ -103,14 +114,15 @@ cudaError_t launch_fma_peak(int iters, int blocks, T* scratch, cudaStream_t st) 
 template <typename T>
 cudaError_t launch_thruster_wrench(const ThrusterArgs<T>& a, cudaStream_t st) {
     if (a.n <= 0) return cudaSuccess;
-    thruster_wrench_kernel<T><<<(a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK, ROLLOUT_BLOCK, 0, st>>>(a);
+    thruster_wrench_kernel<T><<<(a.n + RHS_BLOCK - 1) / RHS_BLOCK, RHS_BLOCK, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 #define BROV_INSTANTIATE(T)                                                                                         \
-    template cudaError_t launch_rollout<T>(int, int, bool, const RolloutArgs<T>&, cudaStream_t);                   \
+    template cudaError_t launch_rollout<T>(int, int, bool, bool, const RolloutArgs<T>&, cudaStream_t);             \
     template cudaError_t launch_rhs<T>(int, bool, const RhsArgs<T>&, cudaStream_t);                                \
-    template cudaError_t launch_se<T>(int, int, const SeArgs<T>&, int, double*, cudaStream_t);                     \
+    template cudaError_t launch_se<T>(int, int, const SeArgs<T>&, double*, cudaStream_t);                          \
+    template int se_blocks<T>(long long);                                                                          \
     template cudaError_t launch_reduced9<T>(const Red9Consts<T>&, const T*, const T*, T*, long long, cudaStream_t); \
     template cudaError_t launch_fma_peak<T>(int, int, T*, cudaStream_t);                                           \
     template cudaError_t launch_thruster_wrench<T>(const ThrusterArgs<T>&, cudaStream_t);

@@ -179,7 +179,7 @@ class Engine:
     def rollout(self, x0, U, dt: float = 0.02, integrator: str = "rk4", lag0=None, stride: int = 0,
                 u_layout: str = "auto", step0: int = 0, xT_out: Optional[torch.Tensor] = None,
                 lag_out: Optional[torch.Tensor] = None, traj_out: Optional[torch.Tensor] = None,
-                want_lag: bool = True) -> RolloutResult:
+                want_lag: bool = True, lag_repr: str = "thruster") -> RolloutResult:
         """Open-loop rollout of N vehicles (`simulate_physics` batched).
 
         x0 [N,NX]; U is one of
@@ -188,6 +188,11 @@ class Engine:
           [N,NU]    one constant input per vehicle     (u_layout "const", needs `steps` via U.shape... see below)
         With u_layout="auto" a 3-D U is "tnc" and a 2-D U is "shared".  For "const" pass U=(tensor [N,NU], steps).
         stride > 0 stores the state after every stride-th step into traj [T//stride, N, NX].
+
+        Thruster model: lag_repr="thruster" exchanges the per-thruster lag states [N,24] (the reference's hidden
+        state); lag_repr="projected" exchanges the allocation-projected states [N,18] (see include/brov.h) — same
+        dynamics, fewer operations, the natural carry between the chunks of a long rollout.  With want_lag=False no
+        lag state is returned and the kernels use the projected form internally.
         """
         x0 = self.tensor(x0)
         self._check_rows(x0, self.nx, "x0")
@@ -213,7 +218,10 @@ class Engine:
             steps = Ut.shape[0]
         integ = INTEGRATORS[integrator]
         xT = xT_out if xT_out is not None else torch.empty_like(x0)
-        nlag = self.nlag
+        if lag_repr not in ("thruster", "projected"):
+            raise ValueError("lag_repr must be 'thruster' or 'projected'")
+        proj = lag_repr == "projected" and self.model == "thruster8"
+        nlag = 18 if proj else self.nlag
         lag_in = None
         if nlag and lag0 is not None:
             lag_in = self.tensor(lag0).reshape(n, nlag)
@@ -235,9 +243,17 @@ class Engine:
         d.stride = max(int(stride), 1)
         d.step0 = int(step0)
         d.snap_base = int(step0) // max(int(stride), 1)
+        d.lag_in_repr = d.lag_out_repr = L.LAG_PROJECTED if proj else L.LAG_THRUSTER
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_rollout(self._h, C.byref(d), self._stream()))
-        return RolloutResult(xT=xT, lag=lag_out if nlag else None, traj=traj if stride else None)
+        return RolloutResult(xT=xT, lag=lag_out if (nlag and want_lag) else None, traj=traj if stride else None)
+
+    def project_lag(self, lag24) -> torch.Tensor:
+        """Per-thruster lag states [N,8,3] -> allocation-projected states [N,18] (Z[c][k] = sum_i alloc[c][i] lag[i][k])."""
+        kp = np.zeros((6, 8))
+        L.check(L.lib.brov_default_allocation(L.dptr(kp), None, None))
+        A = self.tensor(kp)
+        return torch.einsum("ci,nik->nck", A, self.tensor(lag24).reshape(-1, 8, 3)).reshape(-1, 18).contiguous()
 
     def step(self, x, u, lag=None, dt: float = 0.02, integrator: str = "rk4") -> RolloutResult:
         """One integrator step for N vehicles (u [N,NU])."""
@@ -301,7 +317,7 @@ class Engine:
     def rollout_host(self, x0: np.ndarray, U: np.ndarray, dt: float = 0.02, integrator: str = "rk4",
                      lag0: Optional[np.ndarray] = None, stride: int = 0, chunk_steps: int = 0,
                      out_xT: Optional[np.ndarray] = None, out_traj: Optional[np.ndarray] = None,
-                     out_lag: Optional[np.ndarray] = None):
+                     out_lag: Optional[np.ndarray] = None, lag_repr: str = "thruster", want_lag: bool = True):
         """Rollout with every array in HOST memory (numpy, engine dtype, C-contiguous; pinned memory overlaps the
         copies).  Inputs stream to the device in time chunks, double buffered against the kernels.
         U [T,N,NU] or [T,NU] (shared).  Returns (xT, lag or None, traj or None) as numpy arrays."""
@@ -319,9 +335,10 @@ class Engine:
             raise ValueError("U must be [T, N, NU] or [T, NU]")
         steps = U.shape[0]
         xT = out_xT if out_xT is not None else np.empty_like(x0)
-        nlag = self.nlag
+        proj = lag_repr == "projected" and self.model == "thruster8"
+        nlag = 18 if proj else self.nlag
         lag_out = None
-        if nlag:
+        if nlag and want_lag:
             lag_out = out_lag if out_lag is not None else np.empty((n, nlag), dtype=self.ndtype)
         traj = None
         if stride:
@@ -337,6 +354,7 @@ class Engine:
         d.traj_host = host(traj, "out_traj").ctypes.data if traj is not None else None
         d.stride = max(int(stride), 1)
         d.chunk_steps = int(chunk_steps)
+        d.lag_in_repr = d.lag_out_repr = L.LAG_PROJECTED if proj else L.LAG_THRUSTER
         L.check(L.lib.brov_rollout_host(self._h, C.byref(d)))
         return xT, lag_out, traj
 

@@ -325,6 +325,41 @@ def test_chunking_strides_and_host_path_are_bit_identical(B):
         assert torch.equal(half.xT, full.xT[100:200])
 
 
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-13), ("f32", 2e-5)])
+def test_projected_lag_representation(B, golden, dtype, tol):
+    """Allocation-projected lag state (18 values) == per-thruster lag state (24 values) up to rounding: same
+    trajectories, Z_out = alloc . lag_out, chunks carry Z, un-projection is refused."""
+    rng = np.random.default_rng(16)
+    n, T = 200, 90
+    x0 = rng.uniform(-1, 1, (n, 12)) * 0.3
+    U = O.smooth_inputs(rng, T, 8, n=n, sigma=0.05)
+    lag0 = rng.uniform(-0.5, 0.5, (n, 24))
+    e = B.Engine("thruster8", dtype)
+    thr = e.rollout(x0, U, dt=DT, lag0=lag0, stride=30)
+    z0 = e.project_lag(lag0)
+    prj = e.rollout(x0, U, dt=DT, lag0=z0, stride=30, lag_repr="projected")
+    assert prj.lag.shape == (n, 18)
+    assert normwise(cpu(prj.xT), cpu(thr.xT)) < tol and normwise(cpu(prj.traj), cpu(thr.traj)) < tol
+    assert normwise(cpu(prj.lag), cpu(e.project_lag(thr.lag))) < tol
+    # no lag wanted back: thruster-coordinate lag_in is projected inside the kernel
+    nol = e.rollout(x0, U, dt=DT, lag0=lag0, want_lag=False)
+    assert nol.lag is None and normwise(cpu(nol.xT), cpu(thr.xT)) < tol
+    # chunked carry of Z is bit-identical to one launch
+    a = e.rollout(x0, U[:40], dt=DT, lag0=z0, lag_repr="projected")
+    b = e.rollout(a.xT, U[40:], dt=DT, lag0=a.lag, lag_repr="projected", step0=40)
+    assert torch.equal(b.xT, prj.xT) and torch.equal(b.lag, prj.lag)
+    # host path with the projected carry
+    x0h, Uh = x0.astype(e.ndtype), np.ascontiguousarray(U.astype(e.ndtype))
+    xT, lagT, _ = e.rollout_host(x0h, Uh, dt=DT, lag0=cpu(z0).astype(e.ndtype), chunk_steps=16, lag_repr="projected")
+    assert np.array_equal(xT, prj.xT.cpu().numpy()) and np.array_equal(lagT, prj.lag.cpu().numpy())
+    xT2, lag2, _ = e.rollout_host(x0h, Uh, dt=DT, lag0=lag0.astype(e.ndtype), chunk_steps=16, want_lag=False)
+    assert lag2 is None and normwise(xT2, cpu(thr.xT)) < tol
+    # against the reference's golden ensemble too
+    Ug = np.ascontiguousarray(np.transpose(golden["ens_U8"], (1, 0, 2)))
+    r = e.rollout(golden["ens_x0"], Ug, dt=DT, stride=20, lag_repr="projected")
+    assert normwise(cpu(r.traj), np.transpose(golden["ens_thr_rk4_s20"], (1, 0, 2))[1:]) < (TOL64 if dtype == "f64" else TOL32)
+
+
 def test_quat13_odd_n_unaligned_snapshots(B):
     rng = np.random.default_rng(15)
     n, T = 37, 12

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrov.so")
+LIB_PATH = os.environ.get("BROV_LIB") or os.path.join(_HERE, "libbrov.so")  # BROV_LIB: a tuning variant
 
 ABI_VERSION = 2
 THRUSTER8_LAG3, WRENCH_EULER12, WRENCH_QUAT13 = 0, 1, 2

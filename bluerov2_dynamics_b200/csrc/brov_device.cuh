@@ -189,13 +189,45 @@ __device__ __forceinline__ void nu_dot(const T* __restrict__ nu, const T* __rest
 }
 
 // Euler-angle models: xdot[12] from x[12] and the body wrench tau[6].
+template <typename T> struct Trig { T sphi, cphi, sth, cth, spsi, cpsi; };
+
+template <typename T> __device__ __forceinline__ void trig_full(const T* __restrict__ ang, Trig<T>& t) {
+    sincos_(ang[0], &t.sphi, &t.cphi);
+    sincos_(ang[1], &t.sth, &t.cth);
+    sincos_(ang[2], &t.spsi, &t.cpsi);
+}
+
+// fp32 RK4 stages 2..4: the stage angles are base + d with a small increment d = c*dt*k, so their sines/cosines
+// follow from the step's base values by the angle-addition formulas with a short Taylor series for sin d, cos d
+// (|d| <= 1/8: truncation < 1e-9 relative, i.e. below float rounding): 11 instructions per angle instead of ~26 for
+// a full range-reduced sincos.  Larger increments (angular rate > 6 rad/s at dt = 0.02) take the full path.
+// It evaluates sin/cos of the UNROUNDED sum base + d, which is closer to exact arithmetic than sin(fl(base + d)).
+__device__ __forceinline__ void rotate_sc(float s, float c, float d, float* so, float* co) {
+    float z = d * d;
+    float sd = fmaf(d * z, fmaf(z, 8.3333333e-3f, -1.6666667e-1f), d);
+    float cd = fmaf(z, fmaf(z, fmaf(z, -1.3888889e-3f, 4.1666667e-2f), -0.5f), 1.0f);
+    *so = fmaf(s, cd, c * sd);
+    *co = fmaf(c, cd, -(s * sd));
+}
+__device__ __forceinline__ void trig_stage(const Trig<float>& b, const float* __restrict__ d,
+                                           const float* __restrict__ ang, Trig<float>& t) {
+    if (fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) > 0.125f) {
+        trig_full<float>(ang, t);
+    } else {
+        rotate_sc(b.sphi, b.cphi, d[0], &t.sphi, &t.cphi);
+        rotate_sc(b.sth, b.cth, d[1], &t.sth, &t.cth);
+        rotate_sc(b.spsi, b.cpsi, d[2], &t.spsi, &t.cpsi);
+    }
+}
+__device__ __forceinline__ void trig_stage(const Trig<double>&, const double*, const double* __restrict__ ang,
+                                           Trig<double>& t) {
+    trig_full<double>(ang, t);  // fp64 keeps the full evaluation: 1e-10 parity with the reference's libm calls
+}
+
 template <typename T, class P>
-__device__ __forceinline__ void rhs_euler12(const T* __restrict__ x, const T* __restrict__ tau, const P& p,
-                                            bool has_current, T* __restrict__ xd) {
-    T sphi, cphi, sth, cth, spsi, cpsi;
-    sincos_(x[3], &sphi, &cphi);
-    sincos_(x[4], &sth, &cth);
-    sincos_(x[5], &spsi, &cpsi);
+__device__ __forceinline__ void rhs_euler12(const T* __restrict__ x, const Trig<T>& tr, const T* __restrict__ tau,
+                                            const P& p, bool has_current, T* __restrict__ xd) {
+    const T sphi = tr.sphi, cphi = tr.cphi, sth = tr.sth, cth = tr.cth, spsi = tr.spsi, cpsi = tr.cpsi;
     const T* nu = x + 6;
     // p_dot = Rz(psi) Ry(theta) Rx(phi) nu_1 as three planar rotations
     {
@@ -352,13 +384,13 @@ __device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restr
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, bool LAG1, int LS, bool LAGW, class P, class LP>
 __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int substep, const T* __restrict__ x,
-                                          LP lag, const T* __restrict__ Fu,
+                                          const Trig<T>& tr, LP lag, const T* __restrict__ Fu,
                                           T* __restrict__ xd, T* __restrict__ lagd) {
     // Fu: THRUSTER8 -> static thrust F[8] of this step (or alloc*F[6] when LAGW); wrench models -> commanded wrench
     if constexpr (MODEL == MODEL_THRUSTER8) {
         T tau[6];
         thruster_tau<T, LS, LAGW, LP>(c, substep, lag, Fu, tau);
-        rhs_euler12<T>(x, tau, p, c.has_current != 0, xd);
+        rhs_euler12<T>(x, tr, tau, p, c.has_current != 0, xd);
     } else {
         T tl[6];
         const T* tau = Fu;
@@ -368,7 +400,7 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
             for (int i = 0; i < 6; ++i) { tl[i] = lag[i]; lagd[i] = (Fu[i] - tl[i]) * il; }
             tau = tl;
         }
-        if constexpr (MODEL == MODEL_WRENCH12) rhs_euler12<T>(x, tau, p, c.has_current != 0, xd);
+        if constexpr (MODEL == MODEL_WRENCH12) rhs_euler12<T>(x, tr, tau, p, c.has_current != 0, xd);
         else rhs_quat13<T>(x, tau, p, c.has_current != 0, xd);
     }
 }
@@ -397,8 +429,11 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         for (int i = 0; i < 6; ++i) Fu[i] = u[i];
     }
     T k[NX], kl[NL];
+    constexpr bool EULER_ANGLES = MODEL != MODEL_QUAT13;
+    Trig<T> tr0;
+    if constexpr (EULER_ANGLES) trig_full<T>(x + 3, tr0);
     if constexpr (INTEG == INTEG_EULER) {
-        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, lag, Fu, k, kl);
+        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, tr0, lag, Fu, k, kl);
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt * k[i];
         if constexpr (LAG1) {
@@ -411,31 +446,33 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         typename std::conditional<AS == 1, T*, AP>::type acc;
         if constexpr (AS == 1) acc = acc_regs; else acc = acc_sm;
         const T hdt = T(0.5) * dt;
-        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, lag, Fu, k, kl);
+        Trig<T> trs;
+        T dang[3];
+        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, tr0, lag, Fu, k, kl);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i * AS] = k[i]; xs[i] = x[i] + hdt * k[i]; }
-        if constexpr (LAG1) {
+        for (int s = 1; s <= 3; ++s) {
+            const T w = (s == 1) ? T(1) : T(2);   // weight of the stage just evaluated
+            const T h = (s == 3) ? dt : hdt;      // offset of the next stage
 #pragma unroll
-            for (int i = 0; i < 6; ++i) { accl[i] = kl[i]; ls[i] = lag[i] + hdt * kl[i]; }
+            for (int i = 0; i < NX; ++i) {
+                if (s == 1) acc[i * AS] = k[i]; else acc[i * AS] += w * k[i];
+                xs[i] = x[i] + h * k[i];
+            }
+            if constexpr (LAG1) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    if (s == 1) accl[i] = kl[i]; else accl[i] += w * kl[i];
+                    ls[i] = lag[i] + h * kl[i];
+                }
+            }
+            if constexpr (EULER_ANGLES) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) dang[i] = h * k[3 + i];
+                trig_stage(tr0, dang, xs + 3, trs);
+            }
+            if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, s, xs, trs, ls, Fu, k, kl);
+            else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, s, xs, trs, lag, Fu, k, kl);
         }
-        if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, 1, xs, ls, Fu, k, kl);
-        else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 1, xs, lag, Fu, k, kl);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i * AS] += T(2) * k[i]; xs[i] = x[i] + hdt * k[i]; }
-        if constexpr (LAG1) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { accl[i] += T(2) * kl[i]; ls[i] = lag[i] + hdt * kl[i]; }
-        }
-        if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, 2, xs, ls, Fu, k, kl);
-        else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 2, xs, lag, Fu, k, kl);
-#pragma unroll
-        for (int i = 0; i < NX; ++i) { acc[i * AS] += T(2) * k[i]; xs[i] = x[i] + dt * k[i]; }
-        if constexpr (LAG1) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { accl[i] += T(2) * kl[i]; ls[i] = lag[i] + dt * kl[i]; }
-        }
-        if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, 3, xs, ls, Fu, k, kl);
-        else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 3, xs, lag, Fu, k, kl);
         const T dt6 = dt * T(1.0 / 6.0);
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i * AS] + k[i]);

@@ -22,11 +22,31 @@ constexpr int RHS_BLOCK = 128;
 constexpr int RED9_BLOCK = 256;
 // Threads per block of the per-vehicle kernels.  fp32: 128.  fp64: 64 — with <= 144 registers seven such blocks fit
 // an SM (14 warps) and BASELINE's 65,536-vehicle ensemble is exactly ONE wave of 1024 blocks on 148 x 7 slots.
-template <typename T> struct BlockOf { static constexpr int N = sizeof(T) == 8 ? 64 : 128; };
+#ifndef BROV_F64_BLOCK
+#define BROV_F64_BLOCK 128
+#endif
+#ifndef BROV_F64_MAXREG
+#define BROV_F64_MAXREG 255
+#endif
+#ifndef BROV_F64_LAG_SMEM
+#define BROV_F64_LAG_SMEM 0
+#endif
+#ifndef BROV_F64_ACC_SMEM
+#define BROV_F64_ACC_SMEM 0
+#endif
+#ifndef BROV_F64_PREFETCH
+#define BROV_F64_PREFETCH 1
+#endif
+#ifndef BROV_F32_MAXREG
+#define BROV_F32_MAXREG 128
+#endif
+template <typename T> struct BlockOf { static constexpr int N = sizeof(T) == 8 ? BROV_F64_BLOCK : 128; };
+template <typename T> struct MaxReg { static constexpr int N = sizeof(T) == 8 ? BROV_F64_MAXREG : BROV_F32_MAXREG; };
+template <typename T> struct Prefetch { static constexpr bool V = sizeof(T) == 8 ? (BROV_F64_PREFETCH != 0) : true; };
 // fp64 keeps the thruster-lag state in shared memory ([component][thread]); fp32 keeps it in registers.
-template <typename T> struct LagInSmem { static constexpr bool V = sizeof(T) == 8; };
+template <typename T> struct LagInSmem { static constexpr bool V = sizeof(T) == 8 && BROV_F64_LAG_SMEM; };
 // fp64 also keeps the RK4 accumulator in shared memory and does not hold next-step inputs in registers.
-template <typename T> struct AccInSmem { static constexpr bool V = sizeof(T) == 8; };
+template <typename T> struct AccInSmem { static constexpr bool V = sizeof(T) == 8 && BROV_F64_ACC_SMEM; };
 
 template <typename T> struct RolloutArgs {
     Consts<T> c;
@@ -162,7 +182,7 @@ __device__ __forceinline__ void load_lag(const Consts<T>& c, const T* __restrict
 }
 
 template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool LAGW>
-__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(sizeof(T) == 8 ? 144 : 128)
+__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(MaxReg<T>::N)
 rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     constexpr int BLOCK = BlockOf<T>::N;
     constexpr int NX = ModelDim<MODEL>::NX;
@@ -229,7 +249,7 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const long long rem = (long long)a.n - warp_v0;
     const int n_valid = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem)) * NX;
 
-    constexpr bool PREFETCH = !AccInSmem<T>::V;  // fp32: next step's inputs ride in registers across the step
+    constexpr bool PREFETCH = Prefetch<T>::V;  // next step's inputs ride in registers across the step
     for (int k = 0; k < a.steps; ++k) {
         T un[NU];
         if constexpr (PREFETCH) {
@@ -297,7 +317,9 @@ __global__ void __launch_bounds__(RHS_BLOCK) rhs_kernel(const __grid_constant__ 
     for (int j = 0; j < NL; ++j) lag[j] = (LagRegs<T, MODEL, LAG1>::HAS && a.lag) ? a.lag[i * NL + j] : T(0);
 #pragma unroll
     for (int j = 0; j < NU; ++j) Fu[j] = (MODEL == MODEL_THRUSTER8) ? thrust_poly<T>(u[j]) : u[j];
-    model_rhs<T, MODEL, LAG1, 1, false, decltype(p), const T*>(a.c, p, 0, x, lag, Fu, xd, lagd);
+    Trig<T> tr;
+    if constexpr (MODEL != MODEL_QUAT13) trig_full<T>(x + 3, tr);
+    model_rhs<T, MODEL, LAG1, 1, false, decltype(p), const T*>(a.c, p, 0, x, tr, lag, Fu, xd, lagd);
     if (!live) return;
 #pragma unroll
     for (int j = 0; j < NX; ++j) a.xdot[i * (NX + (LAG1 ? 6 : 0)) + j] = xd[j];
@@ -350,7 +372,7 @@ __global__ void __launch_bounds__(RHS_BLOCK) thruster_wrench_kernel(const __grid
 // multi-horizon endpoint squared error over sliding windows
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, int INTEG>
-__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(sizeof(T) == 8 ? 144 : 128)
+__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(MaxReg<T>::N)
 se_kernel(const __grid_constant__ SeArgs<T> a) {
     constexpr int BLOCK = BlockOf<T>::N;
     constexpr int NX = ModelDim<MODEL>::NX;

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BROV_LIB") or os.path.join(_HERE, "libbrov.so")  # BROV_LIB: a tuning variant
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 THRUSTER8_LAG3, WRENCH_EULER12, WRENCH_QUAT13 = 0, 1, 2
 F64, F32 = 0, 1
 RK4, EULER = 0, 1
@@ -38,7 +38,8 @@ class SeDesc(C.Structure):
                 ("n_windows", C.c_longlong), ("dt", C.c_double), ("X_dev", C.c_void_p), ("U_dev", C.c_void_p),
                 ("lag0_dev", C.c_void_p), ("n_horizons", C.c_int32), ("horizons", C.c_int32 * MAX_H),
                 ("se_out_dev", C.c_void_p), ("count_out", C.POINTER(C.c_longlong)), ("workspace_dev", C.c_void_p),
-                ("workspace_bytes", C.c_size_t)]
+                ("workspace_bytes", C.c_size_t), ("lag_carry", C.c_int32), ("reserved", C.c_int32),
+                ("window0", C.c_longlong), ("row0", C.c_longlong)]
 
 
 class RolloutHostDesc(C.Structure):
@@ -70,6 +71,7 @@ _PROTOS = {
     "brov_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutDesc), C.c_void_p]),
     "brov_se_workspace_bytes": (C.c_size_t, [C.c_longlong]),
     "brov_multistep_se": (C.c_int, [C.c_void_p, C.POINTER(SeDesc), C.c_void_p]),
+    "brov_se_carry_steps": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_longlong)]),
     "brov_reduced9_rhs": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "brov_rollout_host": (C.c_int, [C.c_void_p, C.POINTER(RolloutHostDesc)]),
     "brov_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -475,6 +475,39 @@ extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* 
     return e->dtype == BROV_F32 ? rollout_impl<float>(e, d, (cudaStream_t)stream) : rollout_impl<double>(e, d, (cudaStream_t)stream);
 }
 
+// Replay depth of the carried lag: smallest m with ||A^m||_inf * (1 + ||b||) below 1e-22 (A, b: lag map of ONE
+// integrator step, i.e. Ad^nsub and S_nsub Bd).  Thrust magnitudes are O(10^2), states O(1): far below 1 ulp.
+static int carry_depth(brov_engine* e, double dt, int nsub, long long* out) {
+    const LagDisc* d = lag_for_dt(e, dt);
+    if (!d) return BROV_EINVAL;
+    typedef long double ld;
+    ld A[3][3], P[3][3], tmp[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { A[i][j] = (i == j); }
+    for (int s = 0; s < nsub; ++s) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { ld v = 0; for (int q = 0; q < 3; ++q) v += A[i][q] * (ld)d->Ad[3 * q + j]; tmp[i][j] = v; }
+        memcpy(A, tmp, sizeof(A));
+    }
+    memcpy(P, A, sizeof(P));
+    long long m = 1;
+    for (; m < 100000; ++m) {
+        ld nrm = 0;
+        for (int i = 0; i < 3; ++i) { ld r = 0; for (int j = 0; j < 3; ++j) r += fabsl(P[i][j]); if (r > nrm) nrm = r; }
+        if (nrm < 1e-22L) break;
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { ld v = 0; for (int q = 0; q < 3; ++q) v += P[i][q] * A[q][j]; tmp[i][j] = v; }
+        memcpy(P, tmp, sizeof(P));
+    }
+    if (m >= 100000) return fail(BROV_EUNSUPPORTED, "thruster lag is not contractive at dt = %g: no finite replay depth", dt);
+    *out = m;
+    return BROV_OK;
+}
+
+extern "C" int brov_se_carry_steps(brov_engine_t* e, double dt, int integrator, long long* steps_out) {
+    if (!e || !steps_out) return fail(BROV_EINVAL, "NULL argument");
+    if (e->model != BROV_THRUSTER8_LAG3) { *steps_out = 0; return BROV_OK; }
+    if (!(dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
+    return carry_depth(e, dt, integrator == BROV_RK4 ? 4 : 1, steps_out);
+}
+
 extern "C" size_t brov_se_workspace_bytes(long long n_windows) {
     if (n_windows < 1) n_windows = 1;
     return (size_t)((n_windows + 63) / 64) * MAX_H * sizeof(double);  // the smaller (fp64) block size
@@ -489,6 +522,12 @@ static int se_impl(brov_engine* e, const brov_se_desc* d, cudaStream_t st) {
     a.partial = (double*)d->workspace_dev;
     a.rows = (int)d->rows; a.nwin = (int)d->n_windows; a.nH = d->n_horizons;
     for (int h = 0; h < MAX_H; ++h) a.H[h] = h < d->n_horizons ? d->horizons[h] : 0x7fffffff;
+    a.carry_steps = 0; a.win0 = d->window0; a.row0 = d->row0;
+    if (d->lag_carry && e->model == BROV_THRUSTER8_LAG3) {
+        long long m = 0;
+        if ((rc = carry_depth(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &m))) return rc;
+        a.carry_steps = (int)m;
+    }
     CUDA_TRY(launch_se<T>(e->model, d->integrator, a, d->se_out_dev, st));
     return BROV_OK;
 }
@@ -500,6 +539,9 @@ extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* 
     if (e->use_lag1) return fail(BROV_EUNSUPPORTED, "the evaluator does not support the first-order wrench lag");
     if (e->pv) return fail(BROV_EUNSUPPORTED, "the evaluator scores one vehicle; clear the per-vehicle table first");
     if (d->n_horizons < 1 || d->n_horizons > MAX_H) return fail(BROV_EINVAL, "n_horizons must be 1..%d", MAX_H);
+    if (d->lag_carry && (d->n_horizons != 1 || d->lag0_dev)) return fail(BROV_EINVAL, "lag_carry scores one horizon per call and excludes lag0");
+    if (d->window0 < 0 || d->row0 < 0 || d->row0 > d->window0) return fail(BROV_EINVAL, "window0 / row0 out of range");
+    if (!d->lag_carry && (d->window0 != d->row0)) return fail(BROV_EINVAL, "rows before the first window are only meaningful with lag_carry");
     for (int h = 0; h < d->n_horizons; ++h)
         if (d->horizons[h] < 1 || (h && d->horizons[h] <= d->horizons[h - 1])) return fail(BROV_EINVAL, "horizons must be >= 1 and strictly ascending");
     if (d->rows < 0 || d->rows > 0x7fffffffLL || d->n_windows < 0 || d->n_windows > d->rows) return fail(BROV_EINVAL, "rows / n_windows out of range");
@@ -509,7 +551,7 @@ extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* 
     for (int h = 0; h < MAX_H; ++h) {
         long long cnt = 0;
         if (h < d->n_horizons) {
-            cnt = d->rows - d->horizons[h];
+            cnt = d->rows - (d->window0 - d->row0) - d->horizons[h];
             if (cnt > d->n_windows) cnt = d->n_windows;
             if (cnt < 0) cnt = 0;
         }

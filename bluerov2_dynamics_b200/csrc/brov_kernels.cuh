@@ -83,6 +83,12 @@ template <typename T> struct SeArgs {
     double* partial;  // [gridDim.x][MAX_H]
     int rows, nwin, nH;
     int H[MAX_H];   // ascending
+    // lag carry (thruster model, one horizon): window k starts from the lag state the reference's single model object
+    // holds after windows 0..k-1 (SURVEY trap T3).  The lag is a stable linear filter, so only the last carry_steps
+    // integrator steps of that history are distinguishable from zero in floating point; each thread replays them.
+    int carry_steps;      // 0 = off
+    long long win0;       // global index of local window 0
+    long long row0;       // global index of local row 0 of X / U
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -387,12 +393,13 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     const long long gk = (long long)blockIdx.x * BLOCK + tid;
     const bool live = gk < a.nwin;
     const long long k = live ? gk : 0;
+    const long long kr = k + (a.win0 - a.row0);  // local row of the window's start (rows before it: carry history)
     ParamsConst<T> p;
     p.kp = a.c.kp;
 
     T x[NX];
 #pragma unroll
-    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + k * NX + j);
+    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + kr * NX + j);
     using LP = typename std::conditional<LR::SMEM, volatile T*, T*>::type;
     constexpr bool ACC_SM = AccInSmem<T>::V && INTEG == INTEG_RK4;
     constexpr int AS = ACC_SM ? BLOCK : 1;
@@ -404,23 +411,41 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     AP acc_sm = nullptr;
     if constexpr (ACC_SM) acc_sm = acc_store + tid;
     load_lag<T, MODEL, false, true, LS, LP>(a.c, a.lag0, false, k, lag);
+    const bool uvec = ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && (sizeof(T) * NU % 16 == 0);
+    if constexpr (MODEL == MODEL_THRUSTER8) {
+        if (a.carry_steps > 0 && live) {
+            // history of the shared model object: windows w = 0..kg-1, each feeding U[w..w+H-1]; replay its tail
+            const long long H0 = a.H[0];
+            const long long total = (a.win0 + k) * H0;
+            const long long m = total < a.carry_steps ? total : a.carry_steps;
+            for (long long s = total - m; s < total; ++s) {
+                const long long w = s / H0;
+                const long long row = w + (s - w * H0) - a.row0;
+                T u[NU], F[8], TF[6];
+                load_u<T, NU, false>(a.U + row * NU, uvec, u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(u[i]);
+                allocate_wrench<T>(a.c, F, TF);
+                lag_advance<T, LS, true, LP>(a.c, lag, TF);
+            }
+        }
+    }
 
     double se[MAX_H];
 #pragma unroll
     for (int h = 0; h < MAX_H; ++h) se[h] = 0.0;
     const int hmax = a.H[a.nH - 1];
     // window k may run j steps while row k + j exists
-    long long room = (long long)a.rows - 1 - k;
+    long long room = (long long)a.rows - 1 - kr;
     const int nsteps = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
-    const bool uvec = ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && (sizeof(T) * NU % 16 == 0);
     for (int j = 0; j < nsteps; ++j) {
         T u[NU];
-        load_u<T, NU, false>(a.U + (k + j) * NU, uvec, u);
+        load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
         integrate_step<T, MODEL, INTEG, false, LS, true, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm);
 #pragma unroll
         for (int h = 0; h < MAX_H; ++h) {
             if (h < a.nH && j + 1 == a.H[h]) {
-                const T* tgt = a.X + (k + j + 1) * NX;
+                const T* tgt = a.X + (kr + j + 1) * NX;
                 double s = 0.0;
 #pragma unroll
                 for (int q = 0; q < NX; ++q) {

@@ -259,10 +259,20 @@ class Engine:
         """One integrator step for N vehicles (u [N,NU])."""
         return self.rollout(x, (u, 1), dt=dt, integrator=integrator, lag0=lag, u_layout="const")
 
+    def carry_steps(self, dt: float = 0.02, integrator: str = "rk4") -> int:
+        """Replay depth (integrator steps) of the carried-lag evaluator for this dt / integrator."""
+        out = C.c_longlong()
+        L.check(L.lib.brov_se_carry_steps(self._h, float(dt), INTEGRATORS[integrator], C.byref(out)))
+        return int(out.value)
+
     def multistep_se(self, X, U, horizons: Sequence[int], dt: float = 0.02, integrator: str = "rk4",
-                     lag0=None, n_windows: Optional[int] = None):
+                     lag0=None, n_windows: Optional[int] = None, lag_mode: str = "reset", window0: int = 0,
+                     row0: int = 0):
         """Sum of squared endpoint errors per horizon over sliding windows of one recorded series.
-        Returns (se [MAX_H] float64 device tensor, counts list).  See brov_multistep_se in include/brov.h."""
+        Returns (se [MAX_H] float64 device tensor, counts list).  See brov_multistep_se in include/brov.h.
+        lag_mode="carry" (thruster model, one horizon): the reference's literal semantics — the lag state left by
+        windows 0..k-1 is what window k starts from.  window0 / row0: global indices of the first local window / row
+        when X, U are a shard of a longer series."""
         X = self.tensor(X)
         U = self.tensor(U)
         self._check_rows(X, self.nx, "X")
@@ -273,7 +283,11 @@ class Engine:
         hs = [int(h) for h in horizons]
         if not 1 <= len(hs) <= L.MAX_H or any(h < 1 for h in hs) or sorted(set(hs)) != hs:
             raise ValueError(f"horizons must be 1..{L.MAX_H} strictly ascending positive integers")
-        nwin = max(rows - hs[0], 0) if n_windows is None else int(n_windows)
+        if lag_mode not in ("reset", "carry"):
+            raise ValueError("lag_mode must be 'reset' or 'carry'")
+        carry = lag_mode == "carry" and self.model == "thruster8"
+        off = int(window0) - int(row0)
+        nwin = max(rows - off - hs[0], 0) if n_windows is None else int(n_windows)
         nbytes = L.lib.brov_se_workspace_bytes(nwin)
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
@@ -295,19 +309,29 @@ class Engine:
         d.count_out = counts
         d.workspace_dev = self._ws.data_ptr()
         d.workspace_bytes = nbytes
+        d.lag_carry = int(carry)
+        d.window0, d.row0 = (int(window0), int(row0)) if carry else (0, 0)
+        if not carry and off:
+            raise ValueError("window0 != row0 needs lag_mode='carry'")
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_multistep_se(self._h, C.byref(d), self._stream()))
         return se, [int(counts[i]) for i in range(len(hs))]
 
-    def multistep_rmse(self, X, U, horizons, dt: float = 0.02, integrator: str = "rk4", lag0=None):
-        """RMSE per horizon, `sqrt(se / (n_windows * n_states))`, NaN where no window fits (reference semantics)."""
+    def multistep_rmse(self, X, U, horizons, dt: float = 0.02, integrator: str = "rk4", lag0=None,
+                       lag_mode: str = "reset"):
+        """RMSE per horizon, `sqrt(se / (n_windows * n_states))`, NaN where no window fits (reference semantics).
+        lag_mode="reset": every window starts from `lag0` (default zero), all horizons share one pass.
+        lag_mode="carry": thruster-lag state carried from window to window as in the reference (one pass per horizon)."""
         single = np.isscalar(horizons)
         hs = [int(horizons)] if single else [int(h) for h in horizons]
         order = sorted(set(hs))
         out = {}
-        for i in range(0, len(order), L.MAX_H):
-            part = order[i:i + L.MAX_H]
-            se, cnt = self.multistep_se(X, U, part, dt, integrator, lag0)
+        group = 1 if (lag_mode == "carry" and self.model == "thruster8") else L.MAX_H
+        X = self.tensor(X)
+        U = self.tensor(U)
+        for i in range(0, len(order), group):
+            part = order[i:i + group]
+            se, cnt = self.multistep_se(X, U, part, dt, integrator, lag0, lag_mode=lag_mode)
             se = se.cpu().numpy()
             for j, h in enumerate(part):
                 out[h] = float(np.sqrt(se[j] / (cnt[j] * self.nx))) if cnt[j] > 0 else float("nan")

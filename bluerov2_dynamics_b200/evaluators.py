@@ -49,20 +49,25 @@ def _engine_for(X_test, model, dtype, engine):
 
 
 def multistep_rmse_endpoint_physics(X_test: np.ndarray, U_test: np.ndarray, H, dt: float, model: str = None,
-                                    integrator: str = "rk4", dtype: str = "f64", engine: Engine = None):
+                                    integrator: str = "rk4", dtype: str = "f64", engine: Engine = None,
+                                    lag_mode: str = "carry"):
     """Strict H-step-ahead endpoint RMSE over all sliding windows of a recorded series:
-    sqrt(sum_k |sim(X[k], U[k:k+H])[-1] - X[k+H]|^2 / ((T-H) * n_states)), NaN if T <= H.
-    `H` may be a list: all horizons share one pass.  Every window starts from zero thruster-lag state (the reference
-    lets the lag state leak from window to window because it reuses one model object — SURVEY trap T3)."""
+    sqrt(sum_k |sim(X[k], U[k:k+H])[-1] - X[k+H]|^2 / ((T-H) * n_states)), NaN if T <= H.  `H` may be a list.
+
+    lag_mode="carry" (default) is the reference's literal behaviour for the 8-thruster model: ONE model object scores
+    all windows in order, so the thruster-lag state leaks from window to window (SURVEY trap T3).
+    lag_mode="reset" starts every window from zero lag state, and scores all horizons in a single pass.
+    The wrench-input models have no hidden state: both modes coincide."""
     eng = _engine_for(X_test, model, dtype, engine)
-    return eng.multistep_rmse(X_test, U_test, H, dt=dt, integrator=integrator)
+    return eng.multistep_rmse(X_test, U_test, H, dt=dt, integrator=integrator, lag_mode=lag_mode)
 
 
 def one_step_rmse_physics(X_test: np.ndarray, U_test: np.ndarray, dt: float, model: str = None, dtype: str = "f64",
-                          engine: Engine = None) -> float:
-    """Teacher-forced one-step Euler prediction RMSE, rmse(X[1:], X[:-1] + dt f(X[:-1], U[:-1]))."""
+                          engine: Engine = None, lag_mode: str = "carry") -> float:
+    """Teacher-forced one-step Euler prediction RMSE, rmse(X[1:], X[:-1] + dt f(X[:-1], U[:-1])); with
+    lag_mode="carry" the thruster lag runs on through the rows as in the reference's loop over one model object."""
     eng = _engine_for(X_test, model, dtype, engine)
-    return eng.multistep_rmse(X_test, U_test, 1, dt=dt, integrator="euler")
+    return eng.multistep_rmse(X_test, U_test, 1, dt=dt, integrator="euler", lag_mode=lag_mode)
 
 
 def rmse(y_true: np.ndarray, y_pred: np.ndarray) -> float:

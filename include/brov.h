@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BROV_ABI_VERSION 2
+#define BROV_ABI_VERSION 3
 
 enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2 };
 enum { BROV_F64 = 0, BROV_F32 = 1 };
@@ -176,7 +176,22 @@ typedef struct brov_se_desc {
     long long* count_out;           /* host [BROV_MAX_H] or NULL */
     void* workspace_dev;
     size_t workspace_bytes;
+    /* lag_carry != 0 (thruster model, n_horizons must be 1, lag0_dev must be NULL): reproduce the reference's literal
+     * behaviour — ONE model object scores all windows in order, so window k starts from the lag state left by windows
+     * 0..k-1 (each feeding U[w..w+H-1], every step advancing the lag 4x under RK4, 1x under Euler).  The lag is a
+     * stable linear filter of the inputs only; each window replays the tail of that history that is distinguishable
+     * from zero in floating point (about 45 RK4 / 180 Euler steps), so windows stay independent and the result agrees
+     * with the sequential reference to rounding.  window0 / row0: global indices of local window 0 and local row 0
+     * when the series is a shard (rows before the shard's first window must then be present back to the replay depth,
+     * brov_se_carry_rows). */
+    int32_t lag_carry;
+    int32_t reserved;
+    long long window0;
+    long long row0;
 } brov_se_desc;
+/* Number of integrator steps of history a carried-lag window replays for this dt / integrator (also the number of
+ * rows a shard must hold before its first window, plus one). */
+int brov_se_carry_steps(brov_engine_t* e, double dt, int integrator, long long* steps_out);
 size_t brov_se_workspace_bytes(long long n_windows);
 int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* stream);
 

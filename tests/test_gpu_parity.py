@@ -205,6 +205,41 @@ def test_multistep_rmse_lag_carry_via_lag0(B, golden):
     assert np.isclose(got, golden["rmse_thr_rk4_carry"][1], rtol=1e-10)
 
 
+def test_multistep_rmse_lag_carry_matches_unmodified_reference(B, golden):
+    """lag_mode="carry": the evaluator reproduces the numbers of the reference's OWN functions (one model object for
+    all windows, trap T3): train_tank_brov2_rk4.multistep_rmse_endpoint_physics (RK4),
+    train_tank_brov2_full_comparison.multistep_rmse_endpoint_physics (Euler),
+    train_tank_brov2_koopmanEDMDc.one_step_rmse_physics."""
+    X, U = golden["rmse_X12"], golden["rmse_U8"]
+    HS = [int(h) for h in golden["rmse_H"]]
+    e = B.Engine("thruster8", "f64")
+    assert 30 < e.carry_steps(DT, "rk4") < 80 and 120 < e.carry_steps(DT, "euler") < 320
+    got = e.multistep_rmse(X, U, HS, dt=DT, integrator="rk4", lag_mode="carry")
+    assert np.allclose(got, golden["rmse_thr_rk4_carry"], rtol=1e-10), (got, golden["rmse_thr_rk4_carry"])
+    got = e.multistep_rmse(X, U, HS, dt=DT, integrator="euler", lag_mode="carry")
+    assert np.allclose(got, golden["rmse_thr_euler_carry"], rtol=1e-10)
+    got = e.multistep_rmse(X, U, 1, dt=DT, integrator="euler", lag_mode="carry")
+    assert np.isclose(got, golden["rmse_thr_onestep_carry"], rtol=1e-10)
+    # the carried and the reset semantics really differ on this series
+    assert not np.allclose(golden["rmse_thr_rk4_carry"], golden["rmse_thr_rk4_reset"], rtol=1e-6)
+    # a shard of the windows (global window / row offsets, history rows before the first window) adds up to the whole
+    H = 10
+    ns = len(X) - H
+    se_all, _ = e.multistep_se(X, U, [H], dt=DT, integrator="rk4", lag_mode="carry")
+    depth = e.carry_steps(DT, "rk4")
+    w0 = 57
+    r0 = max(0, w0 - depth - 1)
+    se_a, ca = e.multistep_se(X[:w0 + H], U[:w0 + H], [H], dt=DT, integrator="rk4", lag_mode="carry", n_windows=w0)
+    se_b, cb = e.multistep_se(X[r0:], U[r0:], [H], dt=DT, integrator="rk4", lag_mode="carry", n_windows=ns - w0,
+                              window0=w0, row0=r0)
+    assert ca[0] + cb[0] == ns
+    assert np.isclose(se_a[0].item() + se_b[0].item(), se_all[0].item(), rtol=1e-12)
+    # wrench models have no hidden state: carry == reset
+    w = B.Engine("wrench12", "f64")
+    assert w.multistep_rmse(X, golden["rmse_W6"], HS, dt=DT, integrator="euler", lag_mode="carry") == \
+        w.multistep_rmse(X, golden["rmse_W6"], HS, dt=DT, integrator="euler")
+
+
 def test_sim_data_generator(B, golden):
     """training/train_sim_brov2_koopmanEDMDc.py:179-182: Euler rollout, dt = 0.05, 1500 stored inputs."""
     e = B.Engine("thruster8", "f64")
@@ -472,7 +507,10 @@ def test_fossen_mirror_classes(B, golden):
     # evaluators
     HS = [int(h) for h in golden["rmse_H"]]
     got = multistep_rmse_endpoint_physics(golden["rmse_X12"], golden["rmse_U8"], HS, DT, integrator="rk4")
+    assert np.allclose(got, golden["rmse_thr_rk4_carry"], rtol=1e-10)  # default = the reference's literal semantics
+    got = multistep_rmse_endpoint_physics(golden["rmse_X12"], golden["rmse_U8"], HS, DT, integrator="rk4", lag_mode="reset")
     assert np.allclose(got, golden["rmse_thr_rk4_reset"], rtol=1e-10)
+    assert np.isclose(one_step_rmse_physics(golden["rmse_X12"], golden["rmse_U8"], DT), golden["rmse_thr_onestep_carry"], rtol=1e-10)
     assert np.isclose(one_step_rmse_physics(golden["rmse_X12"], golden["rmse_W6"], DT, model="wrench12"),
                       golden["rmse_w12_onestep"], rtol=1e-10)
     # helpers

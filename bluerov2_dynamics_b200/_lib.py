@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BROV_LIB") or os.path.join(_HERE, "libbrov.so")  # BROV_LIB: a tuning variant
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 THRUSTER8_LAG3, WRENCH_EULER12, WRENCH_QUAT13 = 0, 1, 2
 F64, F32 = 0, 1
 RK4, EULER = 0, 1
@@ -30,7 +30,7 @@ class RolloutDesc(C.Structure):
                 ("u_stride_t", C.c_longlong), ("u_stride_n", C.c_longlong), ("lag_in_dev", C.c_void_p),
                 ("lag_out_dev", C.c_void_p), ("traj_dev", C.c_void_p), ("stride", C.c_longlong),
                 ("step0", C.c_longlong), ("snap_base", C.c_longlong), ("lag_in_repr", C.c_int32),
-                ("lag_out_repr", C.c_int32)]
+                ("lag_out_repr", C.c_int32), ("time_slices", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class SeDesc(C.Structure):

@@ -68,6 +68,9 @@ struct brov_engine {
     std::vector<LagDisc> lag_overrides;
     LagDisc lag_cache;
     HostStage hs;
+    int num_sms;
+    int* d_sched;        // [1 + nvblocks] ticket counter + per-vehicle-block progress flags (temporal tiling)
+    size_t cap_sched;    // in ints
 };
 
 static const double LAG_AC[9] = {-89.0, -72.33, -26.54, 128.0, 0.0, 0.0, 0.0, 32.0, 0.0};  // fossen/BlueROV2.py:476-478
@@ -282,6 +285,7 @@ extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out
     e->model = model; e->dtype = dtype; e->device = device;
     e->use_lag1 = 0; e->pv = nullptr; e->pv_n = 0;
     e->lag_cache.dt = -1.0;
+    e->num_sms = prop.multiProcessorCount; e->d_sched = nullptr; e->cap_sched = 0;
     double ph[BROV_NPHYS];
     brov_default_physical(1000.0, ph);
     brov_derive_params(ph, e->kp);
@@ -309,6 +313,7 @@ static void hs_release(brov_engine* e) {
 extern "C" void brov_destroy(brov_engine_t* e) {
     if (!e) return;
     hs_release(e);
+    if (e->d_sched) cudaFree(e->d_sched);
     delete e;
 }
 
@@ -430,6 +435,40 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
     const size_t ualign = (sizeof(T) == 4 && NU == 6) ? 8 : 16;
     a.u_vec = aligned(d->u_dev, ualign) && (d->u_stride_t * sizeof(T)) % ualign == 0 && (d->u_stride_n * sizeof(T)) % ualign == 0;
     a.traj_vec = d->traj_dev && aligned(d->traj_dev, 16) && ((size_t)d->n * NX * sizeof(T)) % 16 == 0;
+    // Temporal tiling: when the vehicle blocks do not fill a whole number of waves of resident slots, cut the launch
+    // into time slices so that ceil(blocks*Q/slots) rounds of steps/Q replace ceil(blocks/slots) rounds of steps.
+    const int bt = rollout_block_threads<T>();
+    a.nvblocks = (a.n + bt - 1) / bt;
+    a.quanta = 1; a.ticket = nullptr; a.progress = nullptr;
+    const bool has_lag = (e->model == BROV_THRUSTER8_LAG3) || e->use_lag1;
+    const bool can_slice = a.steps >= 16 && (!has_lag || d->lag_out_dev != nullptr);
+    int Q = d->time_slices;
+    if (Q == 0 && can_slice) {
+        const int per_sm = rollout_blocks_per_sm<T>(e->model, d->integrator, e->use_lag1 != 0, lagw, e->pv != nullptr, d->traj_dev != nullptr);
+        const long long slots = (long long)per_sm * e->num_sms;
+        Q = 1;
+        if (slots > 0 && a.nvblocks > slots) {
+            double best = (double)a.nvblocks / (double)(((a.nvblocks + slots - 1) / slots) * slots);
+            for (int q = 2; q <= 8 && a.steps / q >= 8; ++q) {
+                const long long items = (long long)a.nvblocks * q;
+                const double eff = (double)items / (double)(((items + slots - 1) / slots) * slots);
+                if (eff > best + 0.03) { best = eff; Q = q; }
+            }
+        }
+    }
+    if (Q > 1 && can_slice) {
+        if (Q > a.steps) Q = a.steps;
+        const size_t need = 1 + (size_t)a.nvblocks;
+        if (need > e->cap_sched) {
+            if (e->d_sched) cudaFree(e->d_sched);
+            e->d_sched = nullptr; e->cap_sched = 0;
+            cudaError_t er = cudaMalloc(&e->d_sched, need * sizeof(int));
+            if (er != cudaSuccess) return fail(BROV_ENOMEM, "cudaMalloc(%zu): %s", need * sizeof(int), cudaGetErrorString(er));
+            e->cap_sched = need;
+        }
+        CUDA_TRY(cudaMemsetAsync(e->d_sched, 0, need * sizeof(int), st));
+        a.quanta = Q; a.ticket = e->d_sched; a.progress = e->d_sched + 1;
+    }
     CUDA_TRY(launch_rollout<T>(e->model, d->integrator, e->use_lag1 != 0, lagw, a, st));
     return BROV_OK;
 }
@@ -453,6 +492,7 @@ extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* 
     if (d->steps > 0 && !d->u_dev) return fail(BROV_EINVAL, "u is NULL");
     if (d->u_stride_t < 0 || d->u_stride_n < 0) return fail(BROV_EINVAL, "negative input stride");
     if (d->traj_dev && d->stride < 1) return fail(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
+    if (d->time_slices < 0 || d->time_slices > 64) return fail(BROV_EINVAL, "time_slices must be 0 (auto) .. 64");
     if (d->lag_in_repr < 0 || d->lag_in_repr > 1 || d->lag_out_repr < 0 || d->lag_out_repr > 1) return fail(BROV_EINVAL, "unknown lag representation");
     if (e->model == BROV_THRUSTER8_LAG3 && d->lag_in_dev && d->lag_in_repr == BROV_LAG_PROJECTED && d->lag_out_dev && d->lag_out_repr == BROV_LAG_THRUSTER)
         return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in");
@@ -684,6 +724,7 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
         r.stride = d->traj_host ? d->stride : 1; r.step0 = done; r.snap_base = first_snap;
         r.lag_in_repr = (c == 0) ? (d->lag_in_host ? d->lag_in_repr : carry_repr) : carry_repr;
         r.lag_out_repr = carry_repr;
+        r.time_slices = 0;
         if ((rc = brov_rollout(e, &r, h.s_compute))) return rc;
         CUDA_TRY(cudaEventRecord(h.ev_done[b], h.s_compute));
         if (d->traj_host && last_snap > first_snap) {

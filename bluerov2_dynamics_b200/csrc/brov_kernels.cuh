@@ -63,6 +63,13 @@ template <typename T> struct RolloutArgs {
     int n, steps, stride;
     int u_vec, traj_vec;
     int lag_in_w;       // lag_in holds allocation-projected states [n][6][3]
+    // Temporal tiling against wave quantisation (see rollout_kernel): the launch is cut into `quanta` time slices
+    // per vehicle block; blocks take (slice, vehicle-block) work items from `ticket` in slice-major order and wait on
+    // `progress[vehicle-block]` for their predecessor slice.  quanta <= 1: plain one-block-per-vehicle-block launch.
+    int quanta;
+    int nvblocks;       // vehicle blocks = ceil(n / BLOCK)
+    int* ticket;        // [1], zero before the launch
+    int* progress;      // [nvblocks], zero before the launch
 };
 
 template <typename T> struct RhsArgs {
@@ -174,16 +181,16 @@ __device__ __forceinline__ void load_lag(const Consts<T>& c, const T* __restrict
     if constexpr (MODEL == MODEL_THRUSTER8 && LAGW) {
         if (src_is_w) {
 #pragma unroll
-            for (int j = 0; j < 18; ++j) lag[j * LS] = __ldg(src + i * 18 + j);
+            for (int j = 0; j < 18; ++j) lag[j * LS] = __ldcg(src + i * 18 + j);
         } else {
             T t[24];
 #pragma unroll
-            for (int j = 0; j < 24; ++j) t[j] = __ldg(src + i * 24 + j);
+            for (int j = 0; j < 24; ++j) t[j] = __ldcg(src + i * 24 + j);
             project_lag<T, LS, LP>(c, t, lag);
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) lag[j * LS] = __ldg(src + i * NL + j);
+        for (int j = 0; j < NL; ++j) lag[j * LS] = __ldcg(src + i * NL + j);
     }
 }
 
@@ -201,7 +208,35 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const long long gi = (long long)blockIdx.x * BLOCK + tid;
+
+    // Work item of this block.  Plain launch: vehicle block = blockIdx.x, all steps.  Temporal tiling: vehicles are
+    // independent but a launch of B vehicle blocks on S resident slots costs ceil(B/S) rounds of the FULL step
+    // count (65,536 fp64 vehicles: 512 blocks on 296 slots = 2 rounds for 1.73 rounds of work).  Cutting the steps
+    // into Q slices turns that into ceil(B*Q/S) rounds of steps/Q (Q = 4: 7 rounds of 25 instead of 2 of 100).
+    // Items are handed out by an atomic ticket in slice-major order, so the predecessor slice of a vehicle block
+    // was always claimed earlier by a block that is resident and will finish: the wait below cannot deadlock.
+    int vb = blockIdx.x, slice = 0;
+    int k_begin = 0, k_end = a.steps;
+    if (a.quanta > 1) {
+        __shared__ int s_item;
+        if (tid == 0) s_item = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int item = s_item;
+        slice = item / a.nvblocks;
+        vb = item - slice * a.nvblocks;
+        const int per = (a.steps + a.quanta - 1) / a.quanta;
+        k_begin = slice * per;
+        k_end = k_begin + per < a.steps ? k_begin + per : a.steps;
+        if (slice > 0) {
+            if (tid == 0) {
+                const volatile int* flag = a.progress + vb;
+                while (*flag < slice) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+    const long long gi = (long long)vb * BLOCK + tid;
     const bool live = gi < a.n;
     const long long i = live ? gi : (long long)a.n - 1;  // dead lanes shadow the last vehicle, never store
 
@@ -238,28 +273,36 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     T* tiles = smem;
     if constexpr (PV) __syncthreads();
 
+    // slice 0 starts from (x0, lag_in); later slices continue from what the predecessor left in (xT, lag_out).
+    // L2-only loads: another SM may have written these lines during this launch.
+    const T* xsrc = slice > 0 ? a.xT : a.x0;
     T x[NX];
 #pragma unroll
-    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.x0 + i * NX + j);
-    load_lag<T, MODEL, LAG1, LAGW, LS, LP>(a.c, a.lag_in, a.lag_in_w != 0, i, lag);
+    for (int j = 0; j < NX; ++j) x[j] = __ldcg(xsrc + i * NX + j);
+    if (slice > 0) load_lag<T, MODEL, LAG1, LAGW, LS, LP>(a.c, a.lag_out, LAGW, i, lag);
+    else load_lag<T, MODEL, LAG1, LAGW, LS, LP>(a.c, a.lag_in, a.lag_in_w != 0, i, lag);
 
-    const T* up = a.U + i * a.u_stride_n;
+    const T* up = a.U + i * a.u_stride_n + (long long)k_begin * a.u_stride_t;
     const bool uvec = a.u_vec != 0;
     const bool stream = a.u_stride_n != 0;  // per-vehicle inputs are read exactly once: evict-first
+    const int nsteps = k_end - k_begin;
     T u[NU];
-    if (stream) load_u<T, NU, true>(up, uvec, u); else load_u<T, NU, false>(up, uvec, u);
+    if (nsteps > 0) {
+        if (stream) load_u<T, NU, true>(up, uvec, u); else load_u<T, NU, false>(up, uvec, u);
+    }
 
-    int countdown = a.traj ? (int)(a.stride - (a.step0 % a.stride)) : 0x7fffffff;
-    long long snap = a.traj ? (a.step0 / a.stride - a.snap_base) : 0;
-    const long long warp_v0 = (long long)blockIdx.x * BLOCK + warp * 32;
+    const long long gstep0 = a.step0 + k_begin;
+    int countdown = a.traj ? (int)(a.stride - (gstep0 % a.stride)) : 0x7fffffff;
+    long long snap = a.traj ? (gstep0 / a.stride - a.snap_base) : 0;
+    const long long warp_v0 = (long long)vb * BLOCK + warp * 32;
     const long long rem = (long long)a.n - warp_v0;
     const int n_valid = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem)) * NX;
 
     constexpr bool PREFETCH = Prefetch<T>::V;  // next step's inputs ride in registers across the step
-    for (int k = 0; k < a.steps; ++k) {
+    for (int k = 0; k < nsteps; ++k) {
         T un[NU];
         if constexpr (PREFETCH) {
-            const T* nxt = up + (long long)((k + 1 < a.steps) ? (k + 1) : k) * a.u_stride_t;
+            const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
             if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
         } else if (k > 0) {
             const T* cur = up + (long long)k * a.u_stride_t;
@@ -287,6 +330,11 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
 #pragma unroll
             for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j * LS];
         }
+    }
+    if (a.quanta > 1) {  // publish this slice: state stores first, then the flag
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(a.progress + vb, slice + 1);
     }
 }
 
@@ -582,6 +630,8 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 cudaError_t launch_rollout(int model, int integ, bool lag1, bool lagw, const RolloutArgs<T>& a, cudaStream_t st);
+template <typename T> int rollout_blocks_per_sm(int model, int integ, bool lag1, bool lagw, bool pv, bool traj);
+template <typename T> int rollout_block_threads();
 template <typename T>
 cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t st);
 template <typename T>

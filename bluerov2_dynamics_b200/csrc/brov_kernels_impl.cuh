@@ -10,7 +10,7 @@ static cudaError_t rollout_go(const RolloutArgs<T>& a, cudaStream_t st) {
     constexpr int BLOCK = BlockOf<T>::N;
     constexpr int NX = ModelDim<MODEL>::NX;
     using LR = LagRegs<T, MODEL, LAG1, LAGW>;
-    const int grid = (a.n + BLOCK - 1) / BLOCK;
+    const int grid = ((a.n + BLOCK - 1) / BLOCK) * (a.quanta > 1 ? a.quanta : 1);
     size_t smem = a.traj ? (size_t)(BLOCK / 32) * 32 * NX * sizeof(T) : 0;
     if (LR::SMEM) smem += (size_t)LR::N * BLOCK * sizeof(T);
     if (AccInSmem<T>::V && INTEG == INTEG_RK4) smem += (size_t)NX * BLOCK * sizeof(T);
@@ -24,6 +24,40 @@ static cudaError_t rollout_go(const RolloutArgs<T>& a, cudaStream_t st) {
     }
     return cudaGetLastError();
 }
+
+// resident blocks per SM of the kernel that launch_rollout would pick (for the temporal-tiling heuristic)
+template <typename T, int MODEL, int INTEG, bool LAG1, bool LAGW>
+static int rollout_occ(bool pv, bool traj) {
+    constexpr int BLOCK = BlockOf<T>::N;
+    constexpr int NX = ModelDim<MODEL>::NX;
+    using LR = LagRegs<T, MODEL, LAG1, LAGW>;
+    size_t smem = traj ? (size_t)(BLOCK / 32) * 32 * NX * sizeof(T) : 0;
+    if (LR::SMEM) smem += (size_t)LR::N * BLOCK * sizeof(T);
+    if (AccInSmem<T>::V && INTEG == INTEG_RK4) smem += (size_t)NX * BLOCK * sizeof(T);
+    if (pv) smem += (size_t)KP_COUNT * BLOCK * sizeof(T);
+    int nb = 0;
+    cudaError_t e = pv ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, true, LAGW>, BLOCK, smem)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, false, LAGW>, BLOCK, smem);
+    return e == cudaSuccess ? nb : 0;
+}
+
+template <typename T>
+int rollout_blocks_per_sm(int model, int integ, bool lag1, bool lagw, bool pv, bool traj) {
+    const bool rk4 = integ == INTEG_RK4;
+    switch (model) {
+        case MODEL_THRUSTER8:
+            if (lagw) return rk4 ? rollout_occ<T, MODEL_THRUSTER8, INTEG_RK4, false, true>(pv, traj) : rollout_occ<T, MODEL_THRUSTER8, INTEG_EULER, false, true>(pv, traj);
+            return rk4 ? rollout_occ<T, MODEL_THRUSTER8, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_THRUSTER8, INTEG_EULER, false, false>(pv, traj);
+        case MODEL_WRENCH12:
+            if (lag1) return rk4 ? rollout_occ<T, MODEL_WRENCH12, INTEG_RK4, true, false>(pv, traj) : rollout_occ<T, MODEL_WRENCH12, INTEG_EULER, true, false>(pv, traj);
+            return rk4 ? rollout_occ<T, MODEL_WRENCH12, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_WRENCH12, INTEG_EULER, false, false>(pv, traj);
+        case MODEL_QUAT13:
+            if (lag1) return rk4 ? rollout_occ<T, MODEL_QUAT13, INTEG_RK4, true, false>(pv, traj) : rollout_occ<T, MODEL_QUAT13, INTEG_EULER, true, false>(pv, traj);
+            return rk4 ? rollout_occ<T, MODEL_QUAT13, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_QUAT13, INTEG_EULER, false, false>(pv, traj);
+    }
+    return 0;
+}
+template <typename T> int rollout_block_threads() { return BlockOf<T>::N; }
 
 template <typename T, int MODEL, bool LAG1, bool LAGW>
 static cudaError_t rollout_integ(int integ, const RolloutArgs<T>& a, cudaStream_t st) {
@@ -120,6 +154,8 @@ cudaError_t launch_thruster_wrench(const ThrusterArgs<T>& a, cudaStream_t st) {
 
 #define BROV_INSTANTIATE(T)                                                                                         \
     template cudaError_t launch_rollout<T>(int, int, bool, bool, const RolloutArgs<T>&, cudaStream_t);             \
+    template int rollout_blocks_per_sm<T>(int, int, bool, bool, bool, bool);                                      \
+    template int rollout_block_threads<T>();                                                                       \
     template cudaError_t launch_rhs<T>(int, bool, const RhsArgs<T>&, cudaStream_t);                                \
     template cudaError_t launch_se<T>(int, int, const SeArgs<T>&, double*, cudaStream_t);                          \
     template int se_blocks<T>(long long);                                                                          \

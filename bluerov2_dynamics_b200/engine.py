@@ -179,7 +179,7 @@ class Engine:
     def rollout(self, x0, U, dt: float = 0.02, integrator: str = "rk4", lag0=None, stride: int = 0,
                 u_layout: str = "auto", step0: int = 0, xT_out: Optional[torch.Tensor] = None,
                 lag_out: Optional[torch.Tensor] = None, traj_out: Optional[torch.Tensor] = None,
-                want_lag: bool = True, lag_repr: str = "thruster") -> RolloutResult:
+                want_lag: bool = True, lag_repr: str = "thruster", time_slices: int = 0) -> RolloutResult:
         """Open-loop rollout of N vehicles (`simulate_physics` batched).
 
         x0 [N,NX]; U is one of
@@ -244,6 +244,7 @@ class Engine:
         d.step0 = int(step0)
         d.snap_base = int(step0) // max(int(stride), 1)
         d.lag_in_repr = d.lag_out_repr = L.LAG_PROJECTED if proj else L.LAG_THRUSTER
+        d.time_slices = int(time_slices)  # 0 = automatic temporal tiling (bit-identical results for every value)
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_rollout(self._h, C.byref(d), self._stream()))
         return RolloutResult(xT=xT, lag=lag_out if (nlag and want_lag) else None, traj=traj if stride else None)

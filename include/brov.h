@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BROV_ABI_VERSION 3
+#define BROV_ABI_VERSION 4
 
 enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2 };
 enum { BROV_F64 = 0, BROV_F32 = 1 };
@@ -147,6 +147,13 @@ typedef struct brov_rollout_desc {
     long long snap_base;
     int32_t lag_in_repr;        /* BROV_LAG_* (thruster model only) */
     int32_t lag_out_repr;
+    /* Temporal tiling of the launch (results are bit-identical for every value): 0 = automatic, 1 = off, Q > 1 = cut
+     * the steps of this call into Q slices per block of vehicles.  Vehicles are independent, but B vehicle blocks on S
+     * resident slots cost ceil(B/S) rounds of the full step count; slicing makes it ceil(B*Q/S) rounds of steps/Q
+     * (cfg2: 512 blocks on 296 slots, Q = 4 -> 7 rounds of 25 steps instead of 2 rounds of 100).  Slices of one
+     * vehicle block hand their state over through xT / lag_out, so lag_out must be given for models with lag state. */
+    int32_t time_slices;
+    int32_t reserved0;
 } brov_rollout_desc;
 int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* stream);
 

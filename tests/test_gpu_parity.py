@@ -395,6 +395,40 @@ def test_projected_lag_representation(B, golden, dtype, tol):
     assert normwise(cpu(r.traj), np.transpose(golden["ens_thr_rk4_s20"], (1, 0, 2))[1:]) < (TOL64 if dtype == "f64" else TOL32)
 
 
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_temporal_tiling_is_bit_identical(B, dtype):
+    """time_slices (ticketed time slices per vehicle block, hand-over through xT / lag_out) never changes a bit."""
+    rng = np.random.default_rng(17)
+    n, T = 5000, 53   # ragged: partial last block, steps not divisible by the slice counts
+    x0 = rng.uniform(-1, 1, (n, 12)) * 0.2
+    U = O.smooth_inputs(rng, T, 8, n=n, sigma=0.03)
+    e = B.Engine("thruster8", dtype)
+    for repr_ in ("thruster", "projected"):
+        ref = e.rollout(x0, U, dt=DT, stride=7, time_slices=1, lag_repr=repr_)
+        for q in (2, 3, 4, 7, 53):
+            r = e.rollout(x0, U, dt=DT, stride=7, time_slices=q, lag_repr=repr_)
+            assert torch.equal(r.xT, ref.xT) and torch.equal(r.lag, ref.lag) and torch.equal(r.traj, ref.traj), (repr_, q)
+    # in place (x0 aliases xT, lag_in aliases lag_out), as the chunked bench loop runs it
+    x = e.tensor(x0).clone()
+    lag = torch.zeros((n, 18), device="cuda", dtype=e.tdtype)
+    e.rollout(x, U, dt=DT, lag0=lag, xT_out=x, lag_out=lag, lag_repr="projected", time_slices=4)
+    ref = e.rollout(x0, U, dt=DT, lag_repr="projected", time_slices=1)
+    assert torch.equal(x, ref.xT) and torch.equal(lag, ref.lag)
+    # wrench model (no lag buffers) and the automatic choice at BASELINE cfg2 width
+    w = B.Engine("quat13", dtype)
+    xq = np.zeros((n, 13)); xq[:, 3] = 1.0
+    W = O.smooth_inputs(rng, T, 6, n=n, scale=5.0)
+    a, b = w.rollout(xq, W, dt=DT, time_slices=1), w.rollout(xq, W, dt=DT, time_slices=5)
+    assert torch.equal(a.xT, b.xT)
+    if dtype == "f64":
+        n2 = 65536
+        g = torch.Generator(device="cuda").manual_seed(9)
+        U2 = (torch.rand((32, n2, 8), device="cuda", dtype=torch.float64, generator=g) * 0.8 - 0.4)
+        x2 = torch.zeros((n2, 12), device="cuda", dtype=torch.float64)
+        a, b = e.rollout(x2, U2, dt=DT, time_slices=0), e.rollout(x2, U2, dt=DT, time_slices=1)
+        assert torch.equal(a.xT, b.xT) and torch.equal(a.lag, b.lag)
+
+
 def test_quat13_odd_n_unaligned_snapshots(B):
     rng = np.random.default_rng(15)
     n, T = 37, 12

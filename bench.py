@@ -350,12 +350,19 @@ def main_ours(args):
         return
     clocks = sampler.stop(windows)
 
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        traffic = {}
+
     def roof(leg, cfg, peak):
         per_gpu_steps = leg["vehicle_steps"] / world
+        tr = traffic.get("rollout_" + cfg["dtype"], {})
         tf = FLOP_PER_STEP[cfg["model"]] * per_gpu_steps / (leg["ms_total"] * 1e-3) / 1e12
         gbs = leg["bytes_per_launch"] / (leg["ms_per_step"] * 1e-3) / 1e9
         return {"bound": "fp64_pipe" if cfg["dtype"] == "f64" else "fp32_pipe", "achieved": tf, "peak": peak,
-                "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": tf / peak, "traffic": tr.get("bytes"), "traffic_source": tr.get("capture"),
                 "kernel": f"brov::rollout_kernel<{'double' if cfg['dtype'] == 'f64' else 'float'}, THRUSTER8, RK4>",
                 "flop_per_vehicle_step": FLOP_PER_STEP[cfg["model"]],
                 "peak_source": "in-run FMA-chain microbenchmark (brov_fma_peak), 2 flop per FMA",

@@ -18,7 +18,12 @@
 #include <stdint.h>
 #include <type_traits>
 
+#ifndef BROV_STAGE_UNROLL
+#define BROV_STAGE_UNROLL 3
+#endif
+
 namespace brov {
+constexpr int kStageUnroll = BROV_STAGE_UNROLL;
 
 // ---------------------------------------------------------------------------------------------------------------
 // kernel-parameter vector (derived coefficients; see brov_derive_params in brov_api.cu and include/brov.h)
@@ -474,7 +479,9 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         Trig<T> trs;
         T dang[3];
         model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, tr0, lag, Fu, k, kl);
-#pragma unroll
+        // stages 2..4 share one body; BROV_STAGE_UNROLL = 1 keeps it a real loop (a third of the code size: the fully
+        // unrolled step does not fit the 32 KB instruction cache), 3 unrolls it completely
+#pragma unroll kStageUnroll
         for (int s = 1; s <= 3; ++s) {
             const T w = (s == 1) ? T(1) : T(2);   // weight of the stage just evaluated
             const T h = (s == 3) ? dt : hdt;      // offset of the next stage

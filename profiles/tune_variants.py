@@ -4,17 +4,8 @@ import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "A_b128_r255_regs_pf": ["BROV_F64_BLOCK=128", "BROV_F64_MAXREG=255", "BROV_F64_LAG_SMEM=0", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=1"],
-    "B_b64_r255_regs": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=255", "BROV_F64_LAG_SMEM=0", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "C_b64_r144_lagsm": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=144", "BROV_F64_LAG_SMEM=1", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "D_b64_r144_regs": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=144", "BROV_F64_LAG_SMEM=0", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "E_b64_r144_lagsm_accsm": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=144", "BROV_F64_LAG_SMEM=1", "BROV_F64_ACC_SMEM=1", "BROV_F64_PREFETCH=0"],
-    "F_b64_r168_regs": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=168", "BROV_F64_LAG_SMEM=0", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "G_b128_r128_lagsm": ["BROV_F64_BLOCK=128", "BROV_F64_MAXREG=128", "BROV_F64_LAG_SMEM=1", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "H_b64_r200_regs": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=200", "BROV_F64_LAG_SMEM=0", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "I_b32_r144_lagsm": ["BROV_F64_BLOCK=32", "BROV_F64_MAXREG=144", "BROV_F64_LAG_SMEM=1", "BROV_F64_ACC_SMEM=0", "BROV_F64_PREFETCH=0"],
-    "J_f32_r168": ["BROV_F32_MAXREG=168"],
-    "K_f32_r96": ["BROV_F32_MAXREG=96"],
+    "U1_stage_loop": ["BROV_STAGE_UNROLL=1"],
+    "U3_stage_unrolled": ["BROV_STAGE_UNROLL=3"],
 }
 VDIR = os.path.join(ROOT, "bluerov2_dynamics_b200", "variants")
 

@@ -89,6 +89,22 @@ def cpu_batched_rate(n: int = 4096, steps: int = 20):
     return n * steps / (time.perf_counter() - t0)
 
 
+def cpu_c_oracle_rate(n: int = 8192, steps: int = 400):
+    """The plain-C oracle (oracle/brov_oracle.c: scalar float64, reference operation structure, OpenMP over vehicles)
+    on all host cores: the strongest CPU baseline — compiled code instead of the reference's Python."""
+    from oracle import c_oracle as CO
+    if not CO.available():
+        return None, 0
+    rng = np.random.default_rng(2)
+    x = np.zeros((n, 12))
+    x[:, 2] = 1.0
+    U = rng.uniform(-0.4, 0.4, (steps, n, 8))
+    CO.rollout("thruster8", "rk4", DT, x[:64], U[:10, :64])
+    t0 = time.perf_counter()
+    CO.rollout("thruster8", "rk4", DT, x, U)
+    return n * steps / (time.perf_counter() - t0), CO.threads()
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -248,6 +264,7 @@ def run_e2e_leg(torch, dist, B, cfg, leg, steps, warmup, world, windows):
     d2h = xh.nbytes + lagh.nbytes
     return dict(value=float(n) * world * CHUNK * steps / sec, unit=UNIT, h2d_bytes_per_step=int(h2d),
                 d2h_bytes_per_step=int(d2h), steps=steps, ms_per_step=1e3 * sec / steps,
+                h2d_gbs=h2d * steps / sec / 1e9,
                 api="Engine.rollout_host -> brov_rollout_host (C ABI), pinned host buffers, 4 sub-chunks per call "
                     "double-buffered on a copy stream")
 
@@ -303,6 +320,37 @@ def run_rmse_leg(torch, dist, B, local, rank, world, windows, T=1_000_100, horiz
                 vehicle_steps_per_s=vsteps / (ms * 1e-3), rmse=rm)
 
 
+def run_reduced9_leg(torch, B, local, peaks, peak_src, steps, warmup, windows, rows=1 << 24, traffic=None):
+    """bluerov_compute (fossen/bluerov_torch.py:20-67) batched over `rows` states: 13 scalars in, 9 out per row —
+    38 FLOP per 88 B in fp32, HBM-bound.  Two input/output sets (1.48 GB each, far larger than L2) used alternately."""
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(9)
+    X = [torch.randn((rows, 9), device=dev, dtype=torch.float32, generator=g) for _ in range(2)]
+    U = [torch.randn((rows, 4), device=dev, dtype=torch.float32, generator=g) for _ in range(2)]
+    O = [torch.empty((rows, 9), device=dev, dtype=torch.float32) for _ in range(2)]
+    for k in range(max(warmup, 3)):
+        B.reduced9_rhs(X[k % 2], U[k % 2], out=O[k % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(10, min(steps, 50))
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(n):
+        B.reduced9_rhs(X[k % 2], U[k % 2], out=O[k % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t0, time.perf_counter()))
+    ms = e0.elapsed_time(e1) / n
+    nbytes = rows * (9 + 4 + 9) * 4
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"workload": f"bluerov_compute RHS, {rows} rows fp32, 88 B algorithmic per row", "ms": ms,
+            "evals_per_s": rows / (ms * 1e-3), "launches": n,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": (traffic or {}).get("bytes"),
+                         "traffic_source": (traffic or {}).get("capture"), "kernel": "brov::reduced9_kernel<float>",
+                         "bytes_per_launch": nbytes, "peak_source": peak_src}}
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -325,6 +373,12 @@ def main_ours(args):
                          f"oracle executed one vehicle per call as the reference does; wall {wall:.1f} s",
                "batched_numpy_value": cpu_batched_rate(),
                "batched_numpy_sample": "same oracle vectorised over 4096 vehicles x 20 RK4 steps in one process"}
+        c_rate, c_thr = cpu_c_oracle_rate()
+        if c_rate is not None:
+            cpu["c_port_value"] = c_rate
+            cpu["c_port_threads"] = c_thr
+            cpu["c_port_sample"] = ("oracle/brov_oracle.c (scalar float64 C restatement, gcc -O2, OpenMP over vehicles): "
+                                    "8192 vehicles x 400 RK4 steps")
 
     sampler = ClockSampler(local) if rank == 0 else None
     windows = []
@@ -342,6 +396,13 @@ def main_ours(args):
     del leg3["U"], leg3["x0"], leg3["eng"]
     torch.cuda.empty_cache()
     rmse = run_rmse_leg(torch, dist, B, local, rank, world, windows) if not args.no_rmse else None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except OSError:
+        traffic = {}
+    red9 = run_reduced9_leg(torch, B, local, peaks, peak_src, args.steps, args.warmup, windows,
+                            traffic=traffic.get("reduced9_f32")) if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -349,12 +410,6 @@ def main_ours(args):
             dist.destroy_process_group()
         return
     clocks = sampler.stop(windows)
-
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)
-    except OSError:
-        traffic = {}
 
     def roof(leg, cfg, peak):
         per_gpu_steps = leg["vehicle_steps"] / world
@@ -394,6 +449,7 @@ def main_ours(args):
                             "l2_policy": "two 3.36 GB input chunks used alternately"},
                  "roofline": roof(leg3, CFG3, fp32_peak), "gpu_launches": args.steps},
         "rmse": rmse,
+        "reduced9": red9,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

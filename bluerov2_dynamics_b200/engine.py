@@ -384,15 +384,18 @@ class Engine:
         return xT, lag_out, traj
 
 
-def reduced9_rhs(x: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
-    """bluerov_compute RHS on CUDA tensors x [B,9], u [B,4] (float32 or float64)."""
+def reduced9_rhs(x: torch.Tensor, u: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bluerov_compute RHS on CUDA tensors x [B,9], u [B,4] (float32 or float64); `out` [B,9] is reused if given."""
     if x.dtype not in (torch.float32, torch.float64) or u.dtype != x.dtype:
         raise TypeError("x and u must both be float32 or both float64")
     if not x.is_cuda or not u.is_cuda:
         raise RuntimeError("reduced9_rhs expects CUDA tensors")
     x = x.contiguous()
     u = u.contiguous()
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != x.dtype or out.device != x.device or not out.is_contiguous():
+        raise ValueError("out must be a contiguous tensor like x")
     with torch.cuda.device(x.device):
         L.check(L.lib.brov_reduced9_rhs(L.F32 if x.dtype == torch.float32 else L.F64, x.data_ptr(), u.data_ptr(),
                                         out.data_ptr(), x.shape[0], torch.cuda.current_stream(x.device).cuda_stream))

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/brov.h"
+#include "brov_internal.cuh"
 #include "brov_kernels.cuh"
 
 using namespace brov;
@@ -23,6 +24,13 @@ static_assert(BROV_MAX_H == MAX_H, "horizon count");
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int brov::fail_msg(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -77,8 +85,9 @@ static const double LAG_AC[9] = {-89.0, -72.33, -26.54, 128.0, 0.0, 0.0, 0.0, 32
 static const double LAG_BC[3] = {8.0, 0.0, 0.0};                                             // :479
 static const double LAG_CC[3] = {0.0, 5.992, 3.317};                                         // :480
 
-static int model_nx(int m) { return m == BROV_WRENCH_QUAT13 ? 13 : 12; }
-static int model_nu(int m) { return m == BROV_THRUSTER8_LAG3 ? 8 : 6; }
+static int model_nx(int m) { return (m == BROV_WRENCH_QUAT13 || m == BROV_DI_QUAT13_U6) ? 13 : 12; }
+static int model_nu(int m) { return (m == BROV_THRUSTER8_LAG3 || m == BROV_DI_EULER12_U8) ? 8 : 6; }
+static bool model_is_di(int m) { return m >= BROV_DI_EULER12_U8 && m <= BROV_DI_QUAT13_U6; }
 static int model_nlag(const brov_engine* e) {
     return e->model == BROV_THRUSTER8_LAG3 ? 24 : (e->use_lag1 ? 6 : 0);
 }
@@ -272,7 +281,7 @@ static int make_consts(brov_engine* e, double dt, int nsub, Consts<T>* c) {
 extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out) {
     if (!out) return fail(BROV_EINVAL, "out is NULL");
     *out = nullptr;
-    if (model < 0 || model > 2) return fail(BROV_EINVAL, "unknown model %d", model);
+    if (model < 0 || model > BROV_DI_QUAT13_U6) return fail(BROV_EINVAL, "unknown model %d", model);
     if (dtype != BROV_F64 && dtype != BROV_F32) return fail(BROV_EINVAL, "unknown dtype %d", dtype);
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
@@ -290,6 +299,7 @@ extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out
     brov_default_physical(1000.0, ph);
     brov_derive_params(ph, e->kp);
     brov_default_allocation(&e->alloc[0][0], nullptr, nullptr);
+    if (model_is_di(model)) memset(e->alloc, 0, sizeof(e->alloc));  // gains arrive through brov_set_di_gains
     *out = e;
     return BROV_OK;
 }
@@ -330,8 +340,22 @@ extern "C" int brov_get_params(const brov_engine_t* e, double* kp) {
     memcpy(kp, e->kp, sizeof(e->kp));
     return BROV_OK;
 }
+extern "C" int brov_set_di_gains(brov_engine_t* e, const double* K_lin, const double* K_ang) {
+    if (!e || !K_lin || !K_ang) return fail(BROV_EINVAL, "NULL argument");
+    if (!model_is_di(e->model)) return fail(BROV_EUNSUPPORTED, "brov_set_di_gains needs a BROV_DI_* engine");
+    const int nu = model_nu(e->model);
+    memset(e->alloc, 0, sizeof(e->alloc));
+    for (int i = 0; i < nu; ++i)
+        for (int r = 0; r < 3; ++r) {
+            if (!std::isfinite(K_lin[i * 3 + r]) || !std::isfinite(K_ang[i * 3 + r])) return fail(BROV_EINVAL, "gain [%d][%d] is not finite", i, r);
+            e->alloc[r][i] = K_lin[i * 3 + r];
+            e->alloc[3 + r][i] = K_ang[i * 3 + r];
+        }
+    return BROV_OK;
+}
 extern "C" int brov_set_allocation(brov_engine_t* e, const double* alloc) {
     if (!e || !alloc) return fail(BROV_EINVAL, "NULL argument");
+    if (model_is_di(e->model)) return fail(BROV_EUNSUPPORTED, "double-integrator engines take brov_set_di_gains");
     // the kernel skips the structural zeros of the BlueROV2 heavy layout (4 horizontal + 4 vertical thrusters)
     for (int r = 0; r < 6; ++r)
         for (int i = 0; i < 8; ++i) {
@@ -345,14 +369,15 @@ extern "C" int brov_set_allocation(brov_engine_t* e, const double* alloc) {
 extern "C" int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n) {
     if (!e) return fail(BROV_EINVAL, "NULL engine");
     if (kp_soa_dev && n <= 0) return fail(BROV_EINVAL, "vehicle table with n = %lld", n);
+    if (kp_soa_dev && model_is_di(e->model)) return fail(BROV_EUNSUPPORTED, "double-integrator engines have no per-vehicle coefficient table");
     e->pv = kp_soa_dev;
     e->pv_n = kp_soa_dev ? n : 0;
     return BROV_OK;
 }
 extern "C" int brov_set_wrench_lag1(brov_engine_t* e, int enable) {
     if (!e) return fail(BROV_EINVAL, "NULL engine");
-    if (enable && e->model == BROV_THRUSTER8_LAG3)
-        return fail(BROV_EUNSUPPORTED, "the first-order wrench lag applies to the wrench-input models only");
+    if (enable && (e->model == BROV_THRUSTER8_LAG3 || model_is_di(e->model)))
+        return fail(BROV_EUNSUPPORTED, "the first-order wrench lag applies to the wrench-input Fossen models only");
     e->use_lag1 = enable ? 1 : 0;
     return BROV_OK;
 }

@@ -45,20 +45,28 @@ enum : int {
 constexpr int MODEL_THRUSTER8 = 0;
 constexpr int MODEL_WRENCH12 = 1;
 constexpr int MODEL_QUAT13 = 2;
+// Double-integrator comparison model (training/train_tank_brov2_rk4.py:461-528 and the Euler twins): kinematics as the
+// Fossen models (position through R(eta); Euler angles integrated from the body rates DIRECTLY, no J2), accelerations
+// a learned linear map of the input, [v_dot, w_dot] = u [K_lin | K_ang].
+constexpr int MODEL_DI12_U8 = 3;    // 12-state, 8 thruster inputs
+constexpr int MODEL_DI12_U6 = 4;    // 12-state, 6 wrench inputs
+constexpr int MODEL_DIQ13_U6 = 5;   // 13-state quaternion, 6 wrench inputs
 constexpr int INTEG_RK4 = 0;
 constexpr int INTEG_EULER = 1;
 
 template <int MODEL> struct ModelDim {
-    static constexpr int NX = (MODEL == MODEL_QUAT13) ? 13 : 12;
-    static constexpr int NU = (MODEL == MODEL_THRUSTER8) ? 8 : 6;
+    static constexpr bool QUAT = (MODEL == MODEL_QUAT13) || (MODEL == MODEL_DIQ13_U6);
+    static constexpr bool DI = (MODEL == MODEL_DI12_U8) || (MODEL == MODEL_DI12_U6) || (MODEL == MODEL_DIQ13_U6);
+    static constexpr int NX = QUAT ? 13 : 12;
+    static constexpr int NU = (MODEL == MODEL_THRUSTER8 || MODEL == MODEL_DI12_U8) ? 8 : 6;
     static constexpr int NLAG = (MODEL == MODEL_THRUSTER8) ? 24 : 6;  // hidden state per vehicle
-    static constexpr int VOFF = (MODEL == MODEL_QUAT13) ? 7 : 6;      // offset of nu in the state
+    static constexpr int VOFF = QUAT ? 7 : 6;                          // offset of nu in the state
 };
 
 // Constants shared by every vehicle of a launch.  Lives in the kernel argument => constant bank 0.
 template <typename T> struct Consts {
     T kp[KP_COUNT];
-    T alloc[6][8];   // tau = alloc * F
+    T alloc[6][8];   // tau = alloc * F; double-integrator engines: alloc[r][i] = [K_lin | K_ang][i][r] (dense)
     // closed-form 3rd-order lag over the NSUB dynamics() calls of one integrator step with the input held:
     //   y_j = lagG[j] . x + lagH[j] * F   (output seen by sub-step j, j = 0..NSUB-1)
     //   x  <- lagA x + lagB F             (state after all NSUB sub-steps)
@@ -335,6 +343,59 @@ template <typename T> __device__ __forceinline__ void quat_renorm(T* q) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// double-integrator comparison model
+// ---------------------------------------------------------------------------------------------------------------
+// [v_dot, w_dot] = u [K_lin | K_ang]   (dense; the input is held over the step, so this is evaluated once per step)
+template <typename T, int NU>
+__device__ __forceinline__ void di_accel(const Consts<T>& c, const T* __restrict__ u, T* __restrict__ acc) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+        T s = T(0);
+#pragma unroll
+        for (int i = 0; i < NU; ++i) s += c.alloc[r][i] * u[i];
+        acc[r] = s;
+    }
+}
+// _di_rhs (training/train_tank_brov2_rk4.py:461-496): pos_dot = R_b2n(phi,theta,psi) v, ang_dot = w.
+template <typename T>
+__device__ __forceinline__ void rhs_di12(const T* __restrict__ x, const Trig<T>& tr, const T* __restrict__ acc,
+                                         T* __restrict__ xd) {
+    const T* nu = x + 6;
+    T v1 = tr.cphi * nu[1] - tr.sphi * nu[2];
+    T w1 = tr.sphi * nu[1] + tr.cphi * nu[2];
+    T u2 = tr.cth * nu[0] + tr.sth * w1;
+    xd[2] = tr.cth * w1 - tr.sth * nu[0];
+    xd[0] = tr.cpsi * u2 - tr.spsi * v1;
+    xd[1] = tr.spsi * u2 + tr.cpsi * v1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) xd[3 + i] = nu[3 + i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xd[6 + i] = acc[i];
+}
+// quaternion twin (training/train_tank_brov2_wrench_quat.py:324-373): pos_dot = R(q) v, q_dot = 1/2 q (x) [0, w]
+// with q normalised first.
+template <typename T>
+__device__ __forceinline__ void rhs_diq13(const T* __restrict__ x, const T* __restrict__ acc, T* __restrict__ xd) {
+    T q[4] = {x[3], x[4], x[5], x[6]};
+    quat_renorm<T>(q);
+    const T qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    const T* nu = x + 7;
+    T R00 = T(1) - T(2) * (qy * qy + qz * qz), R01 = T(2) * (qx * qy - qz * qw), R02 = T(2) * (qx * qz + qy * qw);
+    T R10 = T(2) * (qx * qy + qz * qw), R11 = T(1) - T(2) * (qx * qx + qz * qz), R12 = T(2) * (qy * qz - qx * qw);
+    T R20 = T(2) * (qx * qz - qy * qw), R21 = T(2) * (qy * qz + qx * qw), R22 = T(1) - T(2) * (qx * qx + qy * qy);
+    xd[0] = R00 * nu[0] + R01 * nu[1] + R02 * nu[2];
+    xd[1] = R10 * nu[0] + R11 * nu[1] + R12 * nu[2];
+    xd[2] = R20 * nu[0] + R21 * nu[1] + R22 * nu[2];
+    const T wp = nu[3], wq = nu[4], wr = nu[5];
+    xd[3] = T(0.5) * (-qx * wp - qy * wq - qz * wr);
+    xd[4] = T(0.5) * (qw * wp + qy * wr - qz * wq);
+    xd[5] = T(0.5) * (qw * wq - qx * wr + qz * wp);
+    xd[6] = T(0.5) * (qw * wr + qx * wq - qy * wp);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xd[7 + i] = acc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 3rd-order thruster lag, closed form over the sub-steps of one integrator step (input held).
 // The lag state lives either in registers (LS = 1) or in shared memory laid out [component][thread] (LS = block size).
 //
@@ -421,6 +482,10 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
         T tau[6];
         thruster_tau<T, LS, LAGW, LP>(c, substep, lag, Fu, tau);
         rhs_euler12<T>(x, tr, tau, p, c.has_current != 0, xd);
+    } else if constexpr (MODEL == MODEL_DIQ13_U6) {
+        rhs_diq13<T>(x, Fu, xd);     // Fu = accelerations
+    } else if constexpr (ModelDim<MODEL>::DI) {
+        rhs_di12<T>(x, tr, Fu, xd);
     } else {
         T tl[6];
         const T* tau = Fu;
@@ -454,12 +519,16 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
 #pragma unroll
             for (int i = 0; i < 8; ++i) Fu[i] = F[i];
         }
+    } else if constexpr (ModelDim<MODEL>::DI) {
+        di_accel<T, ModelDim<MODEL>::NU>(c, u, Fu);
+        // the quaternion twin normalises the stored quaternion BEFORE the step (wrench_quat.py:345)
+        if constexpr (MODEL == MODEL_DIQ13_U6) quat_renorm<T>(x + 3);
     } else {
 #pragma unroll
         for (int i = 0; i < 6; ++i) Fu[i] = u[i];
     }
     T k[NX], kl[NL];
-    constexpr bool EULER_ANGLES = MODEL != MODEL_QUAT13;
+    constexpr bool EULER_ANGLES = !ModelDim<MODEL>::QUAT;
     Trig<T> tr0;
     if constexpr (EULER_ANGLES) trig_full<T>(x + 3, tr0);
     if constexpr (INTEG == INTEG_EULER) {
@@ -514,7 +583,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         }
     }
     if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LS, LAGW, LP>(c, lag, Fu);
-    if constexpr (MODEL == MODEL_QUAT13) quat_renorm<T>(x + 3);
+    if constexpr (ModelDim<MODEL>::QUAT) quat_renorm<T>(x + 3);
 }
 
 }  // namespace brov

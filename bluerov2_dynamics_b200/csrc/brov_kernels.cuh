@@ -371,8 +371,9 @@ __global__ void __launch_bounds__(RHS_BLOCK) rhs_kernel(const __grid_constant__ 
     for (int j = 0; j < NL; ++j) lag[j] = (LagRegs<T, MODEL, LAG1>::HAS && a.lag) ? a.lag[i * NL + j] : T(0);
 #pragma unroll
     for (int j = 0; j < NU; ++j) Fu[j] = (MODEL == MODEL_THRUSTER8) ? thrust_poly<T>(u[j]) : u[j];
+    if constexpr (ModelDim<MODEL>::DI) di_accel<T, NU>(a.c, u, Fu);
     Trig<T> tr;
-    if constexpr (MODEL != MODEL_QUAT13) trig_full<T>(x + 3, tr);
+    if constexpr (!ModelDim<MODEL>::QUAT) trig_full<T>(x + 3, tr);
     model_rhs<T, MODEL, LAG1, 1, false, decltype(p), const T*>(a.c, p, 0, x, tr, lag, Fu, xd, lagd);
     if (!live) return;
 #pragma unroll

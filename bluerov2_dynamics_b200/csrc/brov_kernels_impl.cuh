@@ -54,6 +54,12 @@ int rollout_blocks_per_sm(int model, int integ, bool lag1, bool lagw, bool pv, b
         case MODEL_QUAT13:
             if (lag1) return rk4 ? rollout_occ<T, MODEL_QUAT13, INTEG_RK4, true, false>(pv, traj) : rollout_occ<T, MODEL_QUAT13, INTEG_EULER, true, false>(pv, traj);
             return rk4 ? rollout_occ<T, MODEL_QUAT13, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_QUAT13, INTEG_EULER, false, false>(pv, traj);
+        case MODEL_DI12_U8:
+            return rk4 ? rollout_occ<T, MODEL_DI12_U8, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_DI12_U8, INTEG_EULER, false, false>(pv, traj);
+        case MODEL_DI12_U6:
+            return rk4 ? rollout_occ<T, MODEL_DI12_U6, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_DI12_U6, INTEG_EULER, false, false>(pv, traj);
+        case MODEL_DIQ13_U6:
+            return rk4 ? rollout_occ<T, MODEL_DIQ13_U6, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_DIQ13_U6, INTEG_EULER, false, false>(pv, traj);
     }
     return 0;
 }
@@ -78,6 +84,9 @@ cudaError_t launch_rollout(int model, int integ, bool lag1, bool lagw, const Rol
         case MODEL_QUAT13:
             return lag1 ? rollout_integ<T, MODEL_QUAT13, true, false>(integ, a, st)
                         : rollout_integ<T, MODEL_QUAT13, false, false>(integ, a, st);
+        case MODEL_DI12_U8: return rollout_integ<T, MODEL_DI12_U8, false, false>(integ, a, st);
+        case MODEL_DI12_U6: return rollout_integ<T, MODEL_DI12_U6, false, false>(integ, a, st);
+        case MODEL_DIQ13_U6: return rollout_integ<T, MODEL_DIQ13_U6, false, false>(integ, a, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -101,6 +110,9 @@ cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t s
         case MODEL_THRUSTER8: return rhs_go<T, MODEL_THRUSTER8, false>(a, st);
         case MODEL_WRENCH12: return lag1 ? rhs_go<T, MODEL_WRENCH12, true>(a, st) : rhs_go<T, MODEL_WRENCH12, false>(a, st);
         case MODEL_QUAT13: return lag1 ? rhs_go<T, MODEL_QUAT13, true>(a, st) : rhs_go<T, MODEL_QUAT13, false>(a, st);
+        case MODEL_DI12_U8: return rhs_go<T, MODEL_DI12_U8, false>(a, st);
+        case MODEL_DI12_U6: return rhs_go<T, MODEL_DI12_U6, false>(a, st);
+        case MODEL_DIQ13_U6: return rhs_go<T, MODEL_DIQ13_U6, false>(a, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -124,6 +136,9 @@ cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, double* se_out, 
         case MODEL_THRUSTER8: e = se_go<T, MODEL_THRUSTER8>(integ, a, st); break;
         case MODEL_WRENCH12: e = se_go<T, MODEL_WRENCH12>(integ, a, st); break;
         case MODEL_QUAT13: e = se_go<T, MODEL_QUAT13>(integ, a, st); break;
+        case MODEL_DI12_U8: e = se_go<T, MODEL_DI12_U8>(integ, a, st); break;
+        case MODEL_DI12_U6: e = se_go<T, MODEL_DI12_U6>(integ, a, st); break;
+        case MODEL_DIQ13_U6: e = se_go<T, MODEL_DIQ13_U6>(integ, a, st); break;
     }
     if (e != cudaSuccess) return e;
     se_finish_kernel<<<1, 256, 0, st>>>(a.partial, se_blocks<T>(a.nwin), se_out);

@@ -17,7 +17,11 @@ import torch
 
 from . import _lib as L
 
-MODELS = {"thruster8": L.THRUSTER8_LAG3, "wrench12": L.WRENCH_EULER12, "quat13": L.WRENCH_QUAT13}
+MODELS = {"thruster8": L.THRUSTER8_LAG3, "wrench12": L.WRENCH_EULER12, "quat13": L.WRENCH_QUAT13,
+          # double-integrator comparison model: 12-state with 8 thruster / 6 wrench inputs, 13-state quaternion
+          "di12_u8": L.DI_EULER12_U8, "di12_u6": L.DI_EULER12_U6, "diq13_u6": L.DI_QUAT13_U6}
+_NX13 = ("quat13", "diq13_u6")
+_NU8 = ("thruster8", "di12_u8")
 DTYPES = {"f64": (L.F64, torch.float64, np.float64), "f32": (L.F32, torch.float32, np.float32)}
 INTEGRATORS = {"rk4": L.RK4, "euler": L.EULER}
 
@@ -73,8 +77,9 @@ class Engine:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         self._code, self.tdtype, self.ndtype = DTYPES[dtype]
-        self.nx = 13 if model == "quat13" else 12
-        self.nu = 8 if model == "thruster8" else 6
+        self.nx = 13 if model in _NX13 else 12
+        self.nu = 8 if model in _NU8 else 6
+        self.is_di = model.startswith("di")
         self._lag1 = False
         h = C.c_void_p()
         L.check(L.lib.brov_create(MODELS[model], self._code, self.device_index, C.byref(h)))
@@ -121,6 +126,15 @@ class Engine:
         if T_lag is not None:
             self.phys[L.PH_TLAG1] = float(T_lag)
             self.set_physical(self.phys)
+
+    def set_di_gains(self, K_lin: np.ndarray, K_ang: np.ndarray) -> None:
+        """Gains of the double-integrator model as `estimate_di_gains` returns them: v_dot = u K_lin, w_dot = u K_ang,
+        both [NU, 3]."""
+        K_lin = np.ascontiguousarray(K_lin, dtype=np.float64)
+        K_ang = np.ascontiguousarray(K_ang, dtype=np.float64)
+        if K_lin.shape != (self.nu, 3) or K_ang.shape != (self.nu, 3):
+            raise ValueError(f"K_lin and K_ang must have shape ({self.nu}, 3)")
+        L.check(L.lib.brov_set_di_gains(self._h, L.dptr(K_lin), L.dptr(K_ang)))
 
     def set_allocation(self, alloc: np.ndarray) -> None:
         a = np.ascontiguousarray(alloc, dtype=np.float64).reshape(6, 8)

@@ -32,9 +32,17 @@
 extern "C" {
 #endif
 
-#define BROV_ABI_VERSION 4
+#define BROV_ABI_VERSION 5
 
-enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2 };
+enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2,
+       /* double-integrator comparison model of the reference's evaluation tables (kinematics + a learned linear map
+        * input -> body accelerations); every rollout / evaluator entry point below serves it as well:
+        *   simulate_double_integrator / multistep_rmse_endpoint_di
+        *   RK4, 8 thruster inputs        training/train_tank_brov2_rk4.py:461-547
+        *   Euler, 8 thruster inputs      training/train_tank_brov2_full_comparison.py:531-598
+        *   Euler, 6 wrench inputs        training/train_tank_brov2_wrench_comp.py:293-366
+        *   quaternion Euler, 6 inputs    training/train_tank_brov2_wrench_quat.py:324-397 */
+       BROV_DI_EULER12_U8 = 3, BROV_DI_EULER12_U6 = 4, BROV_DI_QUAT13_U6 = 5 };
 enum { BROV_F64 = 0, BROV_F32 = 1 };
 enum { BROV_RK4 = 0, BROV_EULER = 1 };
 /* representation of the thruster model's hidden lag state in lag_in / lag_out arrays */
@@ -85,6 +93,9 @@ int brov_default_allocation(double* alloc /*[6][8]*/, double* r /*[8][3] or NULL
 int brov_set_params(brov_engine_t* e, const double* kp /*[BROV_NKP]*/);
 int brov_get_params(const brov_engine_t* e, double* kp /*[BROV_NKP]*/);
 int brov_set_allocation(brov_engine_t* e, const double* alloc /*[6][8]*/);
+/* Gains of a BROV_DI_* engine as estimate_di_gains returns them (training/train_tank_brov2_rk4.py:438-458):
+ * v_dot = u K_lin, w_dot = u K_ang; K_lin, K_ang are [NU][3] row-major, NU = 8 or 6 by engine model. */
+int brov_set_di_gains(brov_engine_t* e, const double* K_lin, const double* K_ang);
 /* Per-vehicle (Monte-Carlo) coefficient table, dev, engine scalar type, layout [BROV_NKP][n]; NULL clears it.
  * The table is borrowed, not copied: it must outlive the calls that use it. */
 int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n);

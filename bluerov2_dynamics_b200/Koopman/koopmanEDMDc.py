@@ -1,0 +1,192 @@
+"""`Koopman.koopmanEDMDc` mirror: EDMD-with-control on a lifted state [x, Gaussian RBFs(x)] (reference:
+Koopman/koopmanEDMDc.py).
+
+Same class name, fields and methods as the reference.  `evaluate`, `multistep_rmse`, `simulate` and `_lift` — the
+scoring loop of the reference's comparison tables — run in libbrov.so (brov_koopman_* of include/brov.h, float64).
+`fit` / `fit_multi` stay on the host like the reference's (scikit-learn k-means for the centres, one ridge
+normal-equation solve); only their lifting step uses the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+
+
+@dataclass
+class KoopmanEDMDc:
+    state_dim: int
+    input_dim: int
+    n_rbfs: int = 200
+    gamma: float = 1.0
+    ridge: float = 1e-8
+    centers_: Optional[np.ndarray] = None   # (n_rbfs, n)
+    A_: Optional[np.ndarray] = None         # (d, d)
+    B_: Optional[np.ndarray] = None         # (d, r)
+    lift_dim_: Optional[int] = None
+
+    # ------------------------------------------------------------------ device handle
+    def _handle(self, need_model: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("bluerov2_dynamics_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if self.centers_ is None:
+            raise RuntimeError("model has no centres: call fit() or set centers_ / A_ / B_")
+        n, k = self.state_dim, int(np.shape(self.centers_)[0])
+        d = n + k
+        if self.A_ is None or self.B_ is None:
+            if need_model:
+                raise RuntimeError("model is not fitted: A_ / B_ are missing")
+            A, B = np.zeros((d, d)), np.zeros((d, self.input_dim))
+        else:
+            A, B = self.A_, self.B_
+        key = (id(self.centers_), id(A) if self.A_ is not None else 0, id(B) if self.B_ is not None else 0,
+               float(self.gamma), torch.cuda.current_device())
+        cached = self.__dict__.get("_h")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        self._release()
+        Cc = np.ascontiguousarray(self.centers_, dtype=np.float64)
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        B = np.ascontiguousarray(B, dtype=np.float64)
+        if Cc.shape != (k, n) or A.shape != (d, d) or B.shape != (d, self.input_dim):
+            raise ValueError("centers_ / A_ / B_ have inconsistent shapes")
+        h = C.c_void_p()
+        L.check(L.lib.brov_koopman_create(key[4], n, self.input_dim, k, float(self.gamma), L.dptr(Cc), L.dptr(A),
+                                          L.dptr(B), C.byref(h)))
+        self.__dict__["_h"] = (key, h, torch.device("cuda", key[4]))
+        return h
+
+    def _release(self):
+        cached = self.__dict__.pop("_h", None)
+        if cached is not None:
+            L.lib.brov_koopman_destroy(cached[1])
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _dev(self, a, cols):
+        t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)) if not torch.is_tensor(a) else a
+        t = t.to(self.__dict__["_h"][2], torch.float64).contiguous()
+        if t.ndim != 2 or t.shape[1] != cols:
+            raise ValueError(f"expected an array with {cols} columns, got shape {tuple(t.shape)}")
+        return t
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    # ------------------------------------------------------------------ fit (host, as in the reference)
+    def _fit_from_blocks(self, blocks):
+        Z = np.vstack([self._lift(X[:-1]) for X, _ in blocks])
+        Zp = np.vstack([self._lift(X[1:]) for X, _ in blocks])
+        Uc = np.vstack([U[:-1] for _, U in blocks])
+        Gm = np.hstack([Z, Uc])
+        M = (np.linalg.pinv(Gm.T @ Gm + self.ridge * np.eye(Gm.shape[1])) @ (Gm.T @ Zp)).T
+        d = Z.shape[1]
+        self.A_, self.B_, self.lift_dim_ = np.ascontiguousarray(M[:, :d]), np.ascontiguousarray(M[:, d:]), d
+
+    def _pick_centres(self, X_all):
+        from sklearn.cluster import KMeans
+        self.centers_ = KMeans(n_clusters=self.n_rbfs, n_init="auto", random_state=0).fit(X_all).cluster_centers_
+        self.A_ = self.B_ = None
+
+    def fit(self, X: np.ndarray, U: np.ndarray) -> None:
+        """Learn (A, B) from one series: k-means centres on the state cloud, then Z+ = A Z + B U by ridge-regularised
+        normal equations (Koopman/koopmanEDMDc.py:72-111)."""
+        X, U = np.asarray(X, float), np.asarray(U, float)
+        assert U.shape[0] == X.shape[0] and U.shape[1] == self.input_dim
+        self._pick_centres(X)
+        self._fit_from_blocks([(X, U)])
+
+    def fit_multi(self, X_list: Sequence[np.ndarray], U_list: Sequence[np.ndarray]) -> None:
+        """Same from several independent series; no transition crosses a series boundary (:113-152)."""
+        assert len(X_list) == len(U_list) and len(X_list) > 0
+        pairs = [(np.asarray(X, float), np.asarray(U, float)) for X, U in zip(X_list, U_list)]
+        for X, U in pairs:
+            assert X.shape[1] == self.state_dim and U.shape[1] == self.input_dim
+        self._pick_centres(np.vstack([X for X, _ in pairs if len(X) > 0]))
+        self._fit_from_blocks([(X, U) for X, U in pairs if len(X) >= 2])
+
+    # ------------------------------------------------------------------ scoring (GPU)
+    def _se(self, X, U, H: int):
+        h = self._handle()
+        Xd, Ud = self._dev(X, self.state_dim), self._dev(U, self.input_dim)
+        rows = Xd.shape[0]
+        n_start = rows - H
+        if Ud.shape[0] != rows:
+            raise ValueError("X and U must have the same number of rows")
+        if n_start <= 0:
+            return float("nan"), 0
+        se = torch.zeros(1, device=Xd.device, dtype=torch.float64)
+        L.check(L.lib.brov_koopman_multistep_se(h, Xd.data_ptr(), Ud.data_ptr(), rows, n_start, int(H), se.data_ptr(),
+                                                self._stream()))
+        return float(se.item()), n_start
+
+    def evaluate(self, X, U) -> float:
+        """One-step prediction RMSE in state space (:157-170)."""
+        se, ns = self._se(X, U, 1)
+        return float(np.sqrt(se / (ns * self.state_dim))) if ns else float("nan")
+
+    def multistep_rmse(self, X, U, H: int = 10) -> float:
+        """RMSE after propagating every window k = 0..N-H-1 for H steps without re-initialising (:172-200)."""
+        se, ns = self._se(X, U, int(H))
+        return float(np.sqrt(se / (ns * self.state_dim))) if ns else float("nan")
+
+    def simulate(self, x0, U_seq) -> np.ndarray:
+        """Open-loop rollout from x0 under U_seq -> predicted states [T+1, n], row 0 = x0 (:202-216)."""
+        h = self._handle()
+        x0 = np.asarray(x0, dtype=float).reshape(1, self.state_dim)
+        T = len(U_seq)
+        out = np.zeros((T + 1, self.state_dim))
+        out[0] = x0[0]
+        if T == 0:
+            return out
+        X0, Ud = self._dev(x0, self.state_dim), self._dev(U_seq, self.input_dim)
+        res = torch.empty((T, 1, self.state_dim), device=X0.device, dtype=torch.float64)
+        L.check(L.lib.brov_koopman_simulate(h, X0.data_ptr(), Ud.data_ptr(), T, 1, 1, res.data_ptr(), self._stream()))
+        out[1:] = res[:, 0, :].cpu().numpy()
+        return out
+
+    def simulate_batch(self, X0, U) -> torch.Tensor:
+        """Batched rollout (engine extension): X0 [N, n]; U [T, N, r] or [T, r] -> CUDA tensor [T, N, n]."""
+        h = self._handle()
+        X0 = self._dev(X0, self.state_dim)
+        Ut = torch.as_tensor(np.asarray(U, dtype=np.float64)) if not torch.is_tensor(U) else U
+        Ut = Ut.to(X0.device, torch.float64).contiguous()
+        shared = Ut.ndim == 2
+        T, nb = Ut.shape[0], X0.shape[0]
+        if Ut.shape[-1] != self.input_dim or (not shared and Ut.shape[1] != nb):
+            raise ValueError("U must be [T, N, r] or [T, r]")
+        res = torch.empty((T, nb, self.state_dim), device=X0.device, dtype=torch.float64)
+        L.check(L.lib.brov_koopman_simulate(h, X0.data_ptr(), Ut.data_ptr(), T, nb, int(shared), res.data_ptr(),
+                                            self._stream()))
+        return res
+
+    # ------------------------------------------------------------------ lifting
+    def _lift(self, x: np.ndarray) -> np.ndarray:
+        """phi(x) = [x, RBF_1(x), ..., RBF_k(x)] for one state (n,) or a batch (N, n) (:221-238)."""
+        x = np.asarray(x, dtype=float)
+        if x.ndim not in (1, 2):
+            raise ValueError("x must have ndim 1 or 2")
+        h = self._handle(need_model=False)
+        Xd = self._dev(x.reshape(-1, self.state_dim), self.state_dim)
+        d = self.state_dim + int(np.shape(self.centers_)[0])
+        Z = torch.empty((Xd.shape[0], d), device=Xd.device, dtype=torch.float64)
+        L.check(L.lib.brov_koopman_lift(h, Xd.data_ptr(), Xd.shape[0], Z.data_ptr(), self._stream()))
+        Z = Z.cpu().numpy()
+        return Z[0] if x.ndim == 1 else Z
+
+    def _lift_inverse(self, z: np.ndarray) -> np.ndarray:
+        """The lifted state carries the state itself in its first n coordinates (:240-247)."""
+        z = np.asarray(z)
+        if hasattr(self, "decoder_"):
+            return z @ self.decoder_.T
+        return z[..., :self.state_dim]

@@ -2,7 +2,7 @@
 
     python -m bluerov2_dynamics_b200.build [--force]
 
-The three translation units are compiled in parallel and linked into bluerov2_dynamics_b200/libbrov.so, which
+The translation units are compiled in parallel and linked into bluerov2_dynamics_b200/libbrov.so, which
 travels to the GPU box with the repository snapshot (it is git-ignored, not gpurun-ignored).
 """
 from __future__ import annotations
@@ -17,8 +17,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libbrov.so")
 BUILD = os.path.join(PKG, "build")
-SOURCES = ["brov_api.cu", "brov_kernels_f32.cu", "brov_kernels_f64.cu"]
-HEADERS = ["brov_device.cuh", "brov_kernels.cuh", "brov_kernels_impl.cuh", os.path.join("..", "..", "include", "brov.h")]
+SOURCES = ["brov_api.cu", "brov_kernels_f32.cu", "brov_kernels_f64.cu", "brov_koopman.cu"]
+HEADERS = ["brov_device.cuh", "brov_kernels.cuh", "brov_kernels_impl.cuh", "brov_internal.cuh", os.path.join("..", "..", "include", "brov.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -217,6 +217,28 @@ int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* stream);
  * x [B][9], u [B][4], out [B][9]. */
 int brov_reduced9_rhs(int dtype, const void* x_dev, const void* u_dev, void* out_dev, long long B, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Koopman EDMDc comparison model — scoring and simulation of a FITTED model (Koopman/koopmanEDMDc.py; the fit itself,
+ * k-means centres + a ridge normal-equation solve, stays host work as in the reference).  All arithmetic float64.
+ *   phi(x) = [x, exp(-gamma (|x|^2 + |c_j|^2 - 2 x.c_j))_j], d = n + k          _lift / _rbf_mat  :41-49, 221-238
+ * create: centers [k][n], A [d][d], B [d][r] are HOST arrays (row-major double), copied to the device.
+ * Supported (n, r): (12, 8), (12, 6), (13, 6); d limited by shared memory (d = 512 fits). */
+typedef struct brov_koopman brov_koopman_t;
+int brov_koopman_create(int device, int n, int r, int k, double gamma, const double* centers, const double* A,
+                        const double* B, brov_koopman_t** out);
+void brov_koopman_destroy(brov_koopman_t* h);
+/* Z[rows][d] = phi(X[rows][n])                                                    _lift :221-238 */
+int brov_koopman_lift(brov_koopman_t* h, const double* X_dev, long long rows, double* Z_dev, void* stream);
+/* Sum over windows w in [0, n_windows) of |x_hat_w - X[w+H]|^2 with x_hat_w = first n coordinates of the lifted state
+ * propagated H steps from phi(X[w]) under U[w..w+H-1] — `multistep_rmse(X, U, H)` :172-200 with n_windows = rows - H
+ * (rmse = sqrt(se / (n_windows n))), and `evaluate(X, U)` :157-170 for H = 1.  se_out_dev: double[1], dev. */
+int brov_koopman_multistep_se(brov_koopman_t* h, const double* X_dev, const double* U_dev, long long rows,
+                              long long n_windows, int H, double* se_out_dev, void* stream);
+/* `simulate(x0, U_seq)` :202-216 for nb trajectories at once: X0 [nb][n]; U time-major [T][nb][r] (u_shared = 0) or
+ * [T][r] (u_shared = 1); out [T][nb][n] = predicted states after steps 1..T (row 0 of the reference's array is x0). */
+int brov_koopman_simulate(brov_koopman_t* h, const double* X0_dev, const double* U_dev, long long T, long long nb,
+                          int u_shared, double* out_dev, void* stream);
+
 /* Host-buffer rollout: the same operation as brov_rollout with every array in HOST memory (pinned memory gives
  * asynchronous copies).  The engine streams the inputs to the device in time chunks on a copy stream, double
  * buffered against the rollout kernels, and copies snapshots and final state back; it returns after everything has

@@ -82,3 +82,61 @@ def test_di_ensemble_against_oracle(B, cg, model, kind, integ, nx, nu):
         e.set_di_gains(K_lin, K_ang)
         r = e.rollout(x0, U, dt=dt, integrator=integ, stride=20)
         assert normwise(cpu(r.xT), xT) < tol and normwise(cpu(r.traj), snaps) < tol
+
+
+# ------------------------------------------------------------------------------------------------------ Koopman
+@pytest.fixture(scope="module")
+def KM(cg):
+    from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc
+    K = KoopmanEDMDc(state_dim=12, input_dim=8, n_rbfs=116, gamma=float(cg["koop_gamma"]), ridge=1e-1)
+    K.centers_, K.A_, K.B_ = cg["koop_centers"], cg["koop_A"], cg["koop_B"]
+    return K
+
+
+def test_koopman_against_reference(KM, cg):
+    X, U = cg["koop_X"], cg["koop_U"]
+    assert normwise(KM._lift(X[:16]), cg["koop_lift"]) < 1e-13
+    assert KM._lift(X[3]).shape == (128,)
+    assert np.isclose(KM.evaluate(X, U), float(cg["koop_evaluate"]), rtol=TOL64)
+    got = [KM.multistep_rmse(X, U, int(h)) for h in cg["cmp_H"]]
+    assert np.allclose(got, cg["koop_rmse"], rtol=TOL64)
+    sim = KM.simulate(X[0], U[:160])
+    assert sim.shape == cg["koop_simulate"].shape and normwise(sim, cg["koop_simulate"]) < TOL64
+    assert np.isnan(KM.multistep_rmse(X[:5], U[:5], 10))
+
+
+def test_koopman_full_size_against_oracle():
+    """d = 512 (500 RBFs, the reference's configuration), H = 100: oracle = sequential propagation of the lifted state."""
+    from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc
+    rng = np.random.default_rng(8)
+    n, r, k, T = 12, 8, 500, 700
+    C = rng.uniform(-1, 1, (k, n))
+    X = np.cumsum(0.02 * rng.standard_normal((T, n)), axis=0)
+    U = rng.uniform(-1, 1, (T, r))
+    A = 0.98 * np.linalg.qr(rng.standard_normal((n + k, n + k)))[0] + 0.01 * rng.standard_normal((n + k, n + k)) / np.sqrt(n + k)
+    Bm = 0.05 * rng.standard_normal((n + k, r))
+    K = KoopmanEDMDc(state_dim=n, input_dim=r, n_rbfs=k, gamma=0.7)
+    K.centers_, K.A_, K.B_ = C, A, Bm
+    for H in (1, 10, 100):
+        ref = CN.koop_multistep_se(X, U, H, C, 0.7, A, Bm)[2]
+        assert np.isclose(K.multistep_rmse(X, U, H), ref, rtol=TOL64), H
+    ref = CN.koop_simulate(X[0], U[:300], C, 0.7, A, Bm)
+    assert normwise(K.simulate(X[0], U[:300]), ref) < TOL64
+    sims = K.simulate_batch(X[:5], U[:50])
+    for b in range(5):
+        assert normwise(cpu(sims[:, b]), CN.koop_simulate(X[b], U[:50], C, 0.7, A, Bm)[1:]) < TOL64
+
+
+def test_koopman_fit_matches_reference(cg):
+    """fit() = scikit-learn k-means + ridge normal equations on the host: same centres, (A, B) to solver rounding."""
+    from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc
+    # the golden model was fitted on rows 0..599 of a series whose rows 600.. are stored; refit on the stored part
+    X, U = cg["koop_X"], cg["koop_U"]
+    K = KoopmanEDMDc(state_dim=12, input_dim=8, n_rbfs=20, gamma=3.0, ridge=1e-1)
+    K.fit(X, U)
+    assert K.A_.shape == (32, 32) and K.B_.shape == (32, 8) and K.lift_dim_ == 32
+    Z, Zp = CN.koop_lift(X[:-1], K.centers_, 3.0), CN.koop_lift(X[1:], K.centers_, 3.0)
+    Gm = np.hstack([Z, U[:-1]])
+    M = (np.linalg.pinv(Gm.T @ Gm + 0.1 * np.eye(40)) @ (Gm.T @ Zp)).T
+    assert np.allclose(K.A_, M[:, :32], atol=1e-9) and np.allclose(K.B_, M[:, 32:], atol=1e-9)
+    assert K.evaluate(X, U) < 0.5

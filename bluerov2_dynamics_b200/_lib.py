@@ -51,6 +51,26 @@ class RolloutHostDesc(C.Structure):
                 ("chunk_steps", C.c_longlong), ("lag_in_repr", C.c_int32), ("lag_out_repr", C.c_int32)]
 
 
+class PincWeights(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_hidden_layers", C.c_int32), ("hidden", C.c_int32),
+                ("reserved", C.c_int32), ("W", C.c_void_p * 5), ("b", C.c_void_p * 5), ("beta", C.c_float * 4),
+                ("ln_w", C.c_void_p * 4), ("ln_b", C.c_void_p * 4)]
+
+
+class PincRolloutDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_int32), ("n", C.c_longlong), ("steps", C.c_longlong),
+                ("x0_dev", C.c_void_p), ("u_dev", C.c_void_p), ("u_stride_t", C.c_longlong),
+                ("u_stride_n", C.c_longlong), ("lag_in_dev", C.c_void_p), ("lag_out_dev", C.c_void_p),
+                ("traj_dev", C.c_void_p), ("stride", C.c_longlong), ("x9T_dev", C.c_void_p)]
+
+
+class PincSeDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("n_horizons", C.c_int32), ("horizons", C.c_int32 * MAX_H),
+                ("rows", C.c_longlong), ("n_windows", C.c_longlong), ("X_dev", C.c_void_p), ("U_dev", C.c_void_p),
+                ("se_out_dev", C.c_void_p), ("carry_steps", C.c_int32), ("reserved", C.c_int32),
+                ("window0", C.c_longlong), ("row0", C.c_longlong), ("carry_lag0_dev", C.c_void_p)]
+
+
 _DP = C.POINTER(C.c_double)
 _PROTOS = {
     "brov_abi_version": (C.c_int, []),
@@ -80,6 +100,12 @@ _PROTOS = {
     "brov_koopman_lift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "brov_koopman_multistep_se": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "brov_koopman_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "brov_pinc_create": (C.c_int, [C.c_int, C.POINTER(PincWeights), C.POINTER(C.c_void_p)]),
+    "brov_pinc_destroy": (None, [C.c_void_p]),
+    "brov_pinc_set_thruster_map": (C.c_int, [C.c_void_p, C.c_double, _DP, _DP, _DP]),
+    "brov_pinc_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "brov_pinc_rollout": (C.c_int, [C.c_void_p, C.POINTER(PincRolloutDesc), C.c_void_p]),
+    "brov_pinc_multistep_se": (C.c_int, [C.c_void_p, C.POINTER(PincSeDesc), C.c_void_p]),
     "brov_rollout_host": (C.c_int, [C.c_void_p, C.POINTER(RolloutHostDesc)]),
     "brov_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "brov_host_free": (C.c_int, [C.c_void_p]),

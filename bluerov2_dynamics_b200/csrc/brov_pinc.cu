@@ -1,0 +1,610 @@
+// brov_pinc.cu — inference rollout of the reference's PINc residual network on sm_100a.
+//
+// Reference (ViktorNfa/bluerov2_dynamics, training/train_tank_brov2_rk4.py):
+//   thrusters_to_body_wrenches  :553-562   u8 -> compute_thruster_forces (polynomial + ONE lag step) -> [X, Y, Z, Mz]
+//   dataset12_to_9 / state9_to_12 :565-596 [x y z cos(psi) sin(psi) u v w r] <-> 12-state rows
+//   AdaptiveSoftplus            :596-604   softplus(beta x) / (beta + 1e-12)
+//   PINcNet                     :607-673   14 -> 64 -> 64 -> 64 -> 64 -> 9, (Linear, AdaptiveSoftplus, LayerNorm) x 4 +
+//                                          Linear; x_next = x + dx with dx_xy rotated by the current yaw and
+//                                          (cos, sin) re-normalised
+//   simulate_pinc               :789-812   per step: thruster map (float64) -> float32 network
+//   multistep_rmse_endpoint_pinc :815-840  sliding windows, endpoint error in the 12-state projection
+//
+// One thread per window.  The 55 KB of network weights sit in shared memory once per block and are read as
+// broadcast 128-bit loads; a thread keeps the 64 pre-activations of the layer being built in registers and its
+// activations in a private shared-memory column ([unit][thread], conflict-free).  The thruster map runs inline in
+// float64 on the four allocation-projected lag filters the network input needs (rows X, Y, Z, Mz of the allocation
+// matrix: 12 hidden values instead of the reference's 24), exactly one lag step per rollout step like the reference.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "brov_internal.cuh"
+
+namespace {
+
+constexpr int HID = 64;
+constexpr int NIN = 14;
+constexpr int PB = 128;   // threads per block
+
+// packed weight blob (floats), see brov_pinc_create
+constexpr int OFF_W0 = 0;                         // [14][64]  (input-major: the 64 weights of one input contiguous)
+constexpr int OFF_B0 = OFF_W0 + NIN * HID;        // b, ln_w, ln_b of layer 0: 3 x [64]
+constexpr int OFF_L1 = OFF_B0 + 3 * HID;          // layers 1..3: [64][64] + 3 x [64] each
+constexpr int LSTRIDE = HID * HID + 3 * HID;
+constexpr int OFF_W4 = OFF_L1 + 3 * LSTRIDE;      // [64][12]  (hidden-major, 9 outputs padded to 12)
+constexpr int OFF_B4 = OFF_W4 + HID * 12;         // [12]
+constexpr int NW = OFF_B4 + 12;
+
+struct ThrMap {   // single-step thruster map constants (float64)
+    double Ad[9], Bd[3], Cc[3];
+    double a4[4][8];   // rows X, Y, Z, Mz of the allocation matrix
+    double dt;
+};
+
+struct PincParams {
+    const float* w;     // packed blob, device
+    float beta[4];
+};
+
+__device__ __forceinline__ float softplus_f(float x) {
+    // torch.nn.functional.softplus(beta = 1, threshold = 20)
+    return x > 20.0f ? x : log1pf(expf(x));
+}
+
+// activation + LayerNorm of the 64 pre-activations in `a`, result to the thread's shared-memory column
+__device__ __forceinline__ void act_norm_store(float* a, float beta, const float* __restrict__ lnw,
+                                               const float* __restrict__ lnb, float* __restrict__ hcol) {
+    const float ib = 1.0f / (beta + 1e-12f);
+    float mean = 0.0f;
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
+        a[j] = softplus_f(beta * a[j]) * ib;
+        mean += a[j];
+    }
+    mean *= (1.0f / HID);
+    float var = 0.0f;
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
+        const float d = a[j] - mean;
+        var = fmaf(d, d, var);
+    }
+    const float rstd = rsqrtf(var * (1.0f / HID) + 1e-5f);
+#pragma unroll
+    for (int q = 0; q < HID / 4; ++q) {
+        const float4 g = *reinterpret_cast<const float4*>(lnw + 4 * q);
+        const float4 b = *reinterpret_cast<const float4*>(lnb + 4 * q);
+        hcol[(4 * q + 0) * PB] = fmaf((a[4 * q + 0] - mean) * rstd, g.x, b.x);
+        hcol[(4 * q + 1) * PB] = fmaf((a[4 * q + 1] - mean) * rstd, g.y, b.y);
+        hcol[(4 * q + 2) * PB] = fmaf((a[4 * q + 2] - mean) * rstd, g.z, b.z);
+        hcol[(4 * q + 3) * PB] = fmaf((a[4 * q + 3] - mean) * rstd, g.w, b.w);
+    }
+}
+
+__device__ __forceinline__ void bias_init(float* a, const float* __restrict__ b) {
+#pragma unroll
+    for (int q = 0; q < HID / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(b + 4 * q);
+        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+}
+
+__device__ __forceinline__ void axpy64(float* a, const float* __restrict__ wrow, float x) {
+#pragma unroll
+    for (int q = 0; q < HID / 4; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * q);
+        a[4 * q + 0] = fmaf(w.x, x, a[4 * q + 0]);
+        a[4 * q + 1] = fmaf(w.y, x, a[4 * q + 1]);
+        a[4 * q + 2] = fmaf(w.z, x, a[4 * q + 2]);
+        a[4 * q + 3] = fmaf(w.w, x, a[4 * q + 3]);
+    }
+}
+
+// PINcNet.forward: z[14] -> x9_next[9].  sw: weights in shared memory, hcol: this thread's activation column.
+__device__ __forceinline__ void pinc_forward(const float* __restrict__ sw, const float* beta, float* __restrict__ hcol,
+                                             const float* __restrict__ z, float* __restrict__ xn) {
+    float a[HID];
+    bias_init(a, sw + OFF_B0);
+#pragma unroll
+    for (int i = 0; i < NIN; ++i) axpy64(a, sw + OFF_W0 + i * HID, z[i]);
+    act_norm_store(a, beta[0], sw + OFF_B0 + HID, sw + OFF_B0 + 2 * HID, hcol);
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {
+        const float* L = sw + OFF_L1 + l * LSTRIDE;
+        bias_init(a, L + HID * HID);
+#pragma unroll 4
+        for (int i = 0; i < HID; ++i) axpy64(a, L + i * HID, hcol[i * PB]);
+        act_norm_store(a, beta[l + 1], L + HID * HID + HID, L + HID * HID + 2 * HID, hcol);
+    }
+    float dx[12];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(sw + OFF_B4 + 4 * q);
+        dx[4 * q] = v.x; dx[4 * q + 1] = v.y; dx[4 * q + 2] = v.z; dx[4 * q + 3] = v.w;
+    }
+#pragma unroll 4
+    for (int i = 0; i < HID; ++i) {
+        const float h = hcol[i * PB];
+        const float* wr = sw + OFF_W4 + i * 12;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + 4 * q);
+            dx[4 * q + 0] = fmaf(w.x, h, dx[4 * q + 0]);
+            dx[4 * q + 1] = fmaf(w.y, h, dx[4 * q + 1]);
+            dx[4 * q + 2] = fmaf(w.z, h, dx[4 * q + 2]);
+            dx[4 * q + 3] = fmaf(w.w, h, dx[4 * q + 3]);
+        }
+    }
+    // residual update; body-frame (dx, dy) rotated by the CURRENT yaw; (cos, sin) re-normalised (:639-673)
+    const float c = z[3], s = z[4];
+    float base[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) base[j] = z[j] + dx[j];
+    xn[0] = (c * dx[0] - s * dx[1]) + z[0];
+    xn[1] = (s * dx[0] + c * dx[1]) + z[1];
+    xn[2] = base[2];
+    const float nrm = fmaxf(sqrtf(base[3] * base[3] + base[4] * base[4]), 1e-6f);
+    xn[3] = base[3] / nrm;
+    xn[4] = base[4] / nrm;
+#pragma unroll
+    for (int j = 5; j < 9; ++j) xn[j] = base[j];
+}
+
+__device__ __forceinline__ double poly_t200(double V) {
+    const double z = V * V;
+    double p = fma(-140.3, z, 389.9);
+    p = fma(p, z, -404.1);
+    p = fma(p, z, 176.0);
+    p = fma(p, z, 8.9);
+    return p * V;
+}
+
+// one thruster-map step on the projected lag Z[4][3]: returns u4 = [X, Y, Z, Mz] AFTER the lag update (the reference's
+// ThrusterLag.step returns C x of the updated state)
+__device__ __forceinline__ void thruster_map4(const ThrMap& m, const double* __restrict__ u8, double* __restrict__ Z,
+                                              double* __restrict__ u4) {
+    double F[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) F[i] = poly_t200(u8[i]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double tf = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool nz = (r < 2 || r == 3) ? (i < 4) : (i >= 4);  // rows X, Y, Mz: horizontal thrusters; Z: vertical
+            if (nz) tf = fma(m.a4[r][i], F[i], tf);
+        }
+        const double a = Z[3 * r], b = Z[3 * r + 1], c = Z[3 * r + 2];
+        const double n0 = m.Ad[0] * a + m.Ad[1] * b + m.Ad[2] * c + m.Bd[0] * tf;
+        const double n1 = m.Ad[3] * a + m.Ad[4] * b + m.Ad[5] * c + m.Bd[1] * tf;
+        const double n2 = m.Ad[6] * a + m.Ad[7] * b + m.Ad[8] * c + m.Bd[2] * tf;
+        Z[3 * r] = n0; Z[3 * r + 1] = n1; Z[3 * r + 2] = n2;
+        u4[r] = m.Cc[0] * n0 + m.Cc[1] * n1 + m.Cc[2] * n2;
+    }
+}
+
+// lag state [8][3] of the reference -> projected [4][3]
+__device__ __forceinline__ void project4(const ThrMap& m, const double* __restrict__ lag24, double* __restrict__ Z) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fma(m.a4[r][i], lag24[3 * i + k], s);
+            Z[3 * r + k] = s;
+        }
+}
+
+__device__ __forceinline__ void load_weights(const float* __restrict__ g, float* __restrict__ sw) {
+    for (int e = threadIdx.x * 4; e < NW; e += PB * 4)
+        *reinterpret_cast<float4*>(sw + e) = *reinterpret_cast<const float4*>(g + e);
+}
+
+__device__ __forceinline__ void x12_to_9(const double* __restrict__ x12, float* __restrict__ x9) {
+    double s, c;
+    sincos(x12[5], &s, &c);
+    x9[0] = (float)x12[0]; x9[1] = (float)x12[1]; x9[2] = (float)x12[2];
+    x9[3] = (float)c; x9[4] = (float)s;
+    x9[5] = (float)x12[6]; x9[6] = (float)x12[7]; x9[7] = (float)x12[8]; x9[8] = (float)x12[11];
+}
+__device__ __forceinline__ void x9_to_12(const float* __restrict__ x9, double* __restrict__ x12) {
+    x12[0] = x9[0]; x12[1] = x9[1]; x12[2] = x9[2];
+    x12[3] = 0.0; x12[4] = 0.0; x12[5] = atan2((double)x9[4], (double)x9[3]);
+    x12[6] = x9[5]; x12[7] = x9[6]; x12[8] = x9[7];
+    x12[9] = 0.0; x12[10] = 0.0; x12[11] = x9[8];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t SMEM_BYTES = (size_t)(NW + HID * PB) * sizeof(float);
+
+__global__ void __launch_bounds__(PB) pinc_forward_kernel(PincParams p, const float* __restrict__ Zin,
+                                                          float* __restrict__ out, long long n) {
+    extern __shared__ __align__(16) float smf[];
+    float* sw = smf;
+    float* hcol = smf + NW + threadIdx.x;
+    load_weights(p.w, sw);
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * PB + threadIdx.x;
+    if (i >= n) return;
+    float z[NIN], xn[9];
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
+    pinc_forward(sw, p.beta, hcol, z, xn);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
+}
+
+struct PincRollArgs {
+    PincParams p;
+    ThrMap m;
+    const double* x0;      // [n][12]
+    const double* U;       // element (k, i, j) at U[k*u_stride_t + i*u_stride_n + j]
+    long long u_stride_t, u_stride_n;
+    const double* lag_in;  // [n][24] or nullptr
+    double* lag_out;       // [n][12] projected (X, Y, Z, Mz rows) or nullptr
+    double* traj;          // [steps/stride][n][12] or nullptr
+    float* x9T;            // [n][9] or nullptr
+    long long n;
+    int steps, stride;
+};
+
+__global__ void __launch_bounds__(PB) pinc_rollout_kernel(const __grid_constant__ PincRollArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    float* sw = smf;
+    float* hcol = smf + NW + threadIdx.x;
+    load_weights(a.p.w, sw);
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * PB + threadIdx.x;
+    if (i >= a.n) return;
+    double x12[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) x12[j] = a.x0[i * 12 + j];
+    float z[NIN], xn[9];
+    x12_to_9(x12, z);
+    z[13] = (float)a.m.dt;
+    double Z[12];
+    if (a.lag_in) {
+        double l24[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) l24[j] = a.lag_in[i * 24 + j];
+        project4(a.m, l24, Z);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
+    }
+    const double* up = a.U + i * a.u_stride_n;
+    for (int k = 0; k < a.steps; ++k) {
+        double u8[8], u4[4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u8[j] = __ldg(up + (long long)k * a.u_stride_t + j);
+        thruster_map4(a.m, u8, Z, u4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[9 + j] = (float)u4[j];
+        pinc_forward(sw, a.p.beta, hcol, z, xn);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) z[j] = xn[j];
+        if (a.traj && (k + 1) % a.stride == 0) {
+            x9_to_12(xn, x12);
+            double* dst = a.traj + (((long long)(k + 1) / a.stride - 1) * a.n + i) * 12;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) dst[j] = x12[j];
+        }
+    }
+    if (a.x9T) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) a.x9T[i * 9 + j] = z[j];
+    }
+    if (a.lag_out) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) a.lag_out[i * 12 + j] = Z[j];
+    }
+}
+
+struct PincSeArgs {
+    PincParams p;
+    ThrMap m;
+    const double* X;     // [rows][12]
+    const double* U;     // [rows][8]
+    double* partial;     // [gridDim.x][BROV_MAX_H]
+    long long rows, nwin;
+    int nH;
+    int H[BROV_MAX_H];
+    int carry_steps;     // 0 = every window starts from zero lag
+    long long win0, row0;
+    const double* carry_lag0;  // [8][3] lag state of the thruster-map object before window 0, or nullptr (zeros)
+};
+
+__global__ void __launch_bounds__(PB) pinc_se_kernel(const __grid_constant__ PincSeArgs a) {
+    extern __shared__ __align__(16) float smf[];
+    float* sw = smf;
+    float* hcol = smf + NW + threadIdx.x;
+    __shared__ double red[PB / 32][BROV_MAX_H];
+    load_weights(a.p.w, sw);
+    __syncthreads();
+    const long long gk = (long long)blockIdx.x * PB + threadIdx.x;
+    const bool live = gk < a.nwin;
+    const long long k = live ? gk : 0;
+    const long long kr = k + (a.win0 - a.row0);
+    double se[BROV_MAX_H];
+#pragma unroll
+    for (int h = 0; h < BROV_MAX_H; ++h) se[h] = 0.0;
+    if (live) {
+        double x12[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr * 12 + j);
+        float z[NIN], xn[9];
+        x12_to_9(x12, z);
+        z[13] = (float)a.m.dt;
+        double Z[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
+        if (a.carry_steps > 0) {
+            // the reference's single thruster-map object has seen windows 0..k-1, H steps each: replay the tail of that
+            // history that is distinguishable from zero in floating point
+            const long long H0 = a.H[0];
+            const long long total = (a.win0 + k) * H0;
+            const long long m = total < a.carry_steps ? total : a.carry_steps;
+            if (a.carry_lag0 && total <= a.carry_steps) {  // the object's initial lag state is still visible
+                double l24[24];
+#pragma unroll
+                for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
+                project4(a.m, l24, Z);
+            }
+            for (long long s = total - m; s < total; ++s) {
+                const long long w = s / H0;
+                const long long row = w + (s - w * H0) - a.row0;
+                double u8[8], u4[4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
+                thruster_map4(a.m, u8, Z, u4);
+            }
+        }
+        const int hmax = a.H[a.nH - 1];
+        const long long room = a.rows - 1 - kr;
+        const int nsteps = (int)(room < hmax ? (room < 0 ? 0 : room) : hmax);
+        for (int j = 0; j < nsteps; ++j) {
+            double u8[8], u4[4];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u8[q] = __ldg(a.U + (kr + j) * 8 + q);
+            thruster_map4(a.m, u8, Z, u4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[9 + q] = (float)u4[q];
+            pinc_forward(sw, a.p.beta, hcol, z, xn);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) z[q] = xn[q];
+#pragma unroll
+            for (int h = 0; h < BROV_MAX_H; ++h) {
+                if (h < a.nH && j + 1 == a.H[h]) {
+                    x9_to_12(xn, x12);
+                    const double* tgt = a.X + (kr + j + 1) * 12;
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) {
+                        const double e = x12[q] - __ldg(tgt + q);
+                        s += e * e;
+                    }
+                    se[h] = s;
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int h = 0; h < BROV_MAX_H; ++h) {
+        double v = se[h];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][h] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < BROV_MAX_H) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < PB / 32; ++w) v += red[w][threadIdx.x];
+        a.partial[(long long)blockIdx.x * BROV_MAX_H + threadIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) pinc_finish_kernel(const double* __restrict__ partial, int nblocks,
+                                                          double* __restrict__ out) {
+    __shared__ double sh[256];
+    for (int h = 0; h < BROV_MAX_H; ++h) {
+        double v = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += 256) v += partial[(long long)b * BROV_MAX_H + h];
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[h] = sh[0];
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------------------
+struct brov_pinc {
+    int device;
+    float* w;        // packed blob on the device
+    float beta[4];
+    ThrMap m;
+    bool have_map;
+    double* partial;
+    size_t cap_partial;
+    bool attr_set;
+};
+
+static int pinc_attrs(brov_pinc* h) {
+    if (h->attr_set) return BROV_OK;
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    h->attr_set = true;
+    return BROV_OK;
+}
+
+extern "C" int brov_pinc_create(int device, const brov_pinc_weights* wts, brov_pinc_t** out) {
+    if (!out) return brov::fail_msg(BROV_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!wts || wts->struct_size != sizeof(brov_pinc_weights)) return brov::fail_msg(BROV_EINVAL, "brov_pinc_weights size mismatch (ABI %d)", BROV_ABI_VERSION);
+    if (wts->n_hidden_layers != 4 || wts->hidden != HID) return brov::fail_msg(BROV_EUNSUPPORTED, "compiled for the reference's 4 x 64 network (PINc_HIDDEN), got %d x %d", wts->n_hidden_layers, wts->hidden);
+    for (int l = 0; l < 5; ++l)
+        if (!wts->W[l] || !wts->b[l] || (l < 4 && (!wts->ln_w[l] || !wts->ln_b[l]))) return brov::fail_msg(BROV_EINVAL, "weights of layer %d are NULL", l);
+    int ndev = 0;
+    BROV_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return brov::fail_msg(BROV_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    BROV_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return brov::fail_msg(BROV_EUNSUPPORTED, "libbrov is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    BROV_CUDA_TRY(cudaSetDevice(device));
+    // pack: linear layers transposed to input-major so that one input's fan-out is a contiguous row
+    float* blob = new (std::nothrow) float[NW];
+    brov_pinc* h = new (std::nothrow) brov_pinc();
+    if (!blob || !h) { delete[] blob; delete h; return brov::fail_msg(BROV_ENOMEM, "out of host memory"); }
+    memset(blob, 0, NW * sizeof(float));
+    for (int i = 0; i < NIN; ++i) for (int j = 0; j < HID; ++j) blob[OFF_W0 + i * HID + j] = wts->W[0][j * NIN + i];
+    for (int j = 0; j < HID; ++j) {
+        blob[OFF_B0 + j] = wts->b[0][j];
+        blob[OFF_B0 + HID + j] = wts->ln_w[0][j];
+        blob[OFF_B0 + 2 * HID + j] = wts->ln_b[0][j];
+    }
+    for (int l = 0; l < 3; ++l) {
+        float* L = blob + OFF_L1 + l * LSTRIDE;
+        for (int i = 0; i < HID; ++i) for (int j = 0; j < HID; ++j) L[i * HID + j] = wts->W[l + 1][j * HID + i];
+        for (int j = 0; j < HID; ++j) {
+            L[HID * HID + j] = wts->b[l + 1][j];
+            L[HID * HID + HID + j] = wts->ln_w[l + 1][j];
+            L[HID * HID + 2 * HID + j] = wts->ln_b[l + 1][j];
+        }
+    }
+    for (int i = 0; i < HID; ++i) for (int j = 0; j < 9; ++j) blob[OFF_W4 + i * 12 + j] = wts->W[4][j * HID + i];
+    for (int j = 0; j < 9; ++j) blob[OFF_B4 + j] = wts->b[4][j];
+    memset(h, 0, sizeof(*h));
+    h->device = device;
+    for (int l = 0; l < 4; ++l) h->beta[l] = wts->beta[l];
+    cudaError_t e = cudaMalloc(&h->w, NW * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->w, blob, NW * sizeof(float), cudaMemcpyHostToDevice);
+    delete[] blob;
+    if (e != cudaSuccess) {
+        cudaFree(h->w);
+        delete h;
+        return brov::fail_msg(BROV_ECUDA, "brov_pinc_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return BROV_OK;
+}
+
+extern "C" void brov_pinc_destroy(brov_pinc_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->w);
+    cudaFree(h->partial);
+    delete h;
+}
+
+extern "C" int brov_pinc_set_thruster_map(brov_pinc_t* h, double dt, const double* Ad, const double* Bd,
+                                          const double* alloc) {
+    if (!h || !Ad || !Bd || !alloc) return brov::fail_msg(BROV_EINVAL, "NULL argument");
+    if (!(dt > 0.0)) return brov::fail_msg(BROV_EINVAL, "dt must be > 0");
+    memcpy(h->m.Ad, Ad, sizeof(h->m.Ad));
+    memcpy(h->m.Bd, Bd, sizeof(h->m.Bd));
+    h->m.Cc[0] = 0.0; h->m.Cc[1] = 5.992; h->m.Cc[2] = 3.317;   // fossen/BlueROV2.py:480
+    const int rows[4] = {0, 1, 2, 5};
+    for (int r = 0; r < 4; ++r)
+        for (int i = 0; i < 8; ++i) {
+            const bool nz = (r < 2 || r == 3) ? (i < 4) : (i >= 4);
+            const double v = alloc[rows[r] * 8 + i];
+            if (!nz && v != 0.0) return brov::fail_msg(BROV_EUNSUPPORTED, "allocation[%d][%d] must be zero (BlueROV2 heavy layout)", rows[r], i);
+            h->m.a4[r][i] = v;
+        }
+    h->m.dt = dt;
+    h->have_map = true;
+    return BROV_OK;
+}
+
+extern "C" int brov_pinc_forward(brov_pinc_t* h, const float* z_dev, float* out_dev, long long n, void* stream) {
+    if (!h || (n > 0 && (!z_dev || !out_dev))) return brov::fail_msg(BROV_EINVAL, "NULL argument");
+    if (n <= 0) return BROV_OK;
+    BROV_CUDA_TRY(cudaSetDevice(h->device));
+    int rc = pinc_attrs(h);
+    if (rc) return rc;
+    PincParams p;
+    p.w = h->w;
+    memcpy(p.beta, h->beta, sizeof(p.beta));
+    pinc_forward_kernel<<<(unsigned)((n + PB - 1) / PB), PB, SMEM_BYTES, (cudaStream_t)stream>>>(p, z_dev, out_dev, n);
+    BROV_CUDA_TRY(cudaGetLastError());
+    return BROV_OK;
+}
+
+extern "C" int brov_pinc_rollout(brov_pinc_t* h, const brov_pinc_rollout_desc* d, void* stream) {
+    if (!h) return brov::fail_msg(BROV_EINVAL, "NULL handle");
+    if (!d || d->struct_size != sizeof(brov_pinc_rollout_desc)) return brov::fail_msg(BROV_EINVAL, "brov_pinc_rollout_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
+    if (!h->have_map) return brov::fail_msg(BROV_EINVAL, "call brov_pinc_set_thruster_map first");
+    if (d->n < 0 || d->steps < 0 || d->steps > 0x7fffffffLL) return brov::fail_msg(BROV_EINVAL, "n / steps out of range");
+    if (d->n == 0) return BROV_OK;
+    if (!d->x0_dev || (d->steps > 0 && !d->u_dev)) return brov::fail_msg(BROV_EINVAL, "NULL array");
+    if (d->traj_dev && d->stride < 1) return brov::fail_msg(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
+    BROV_CUDA_TRY(cudaSetDevice(h->device));
+    int rc = pinc_attrs(h);
+    if (rc) return rc;
+    PincRollArgs a;
+    a.p.w = h->w;
+    memcpy(a.p.beta, h->beta, sizeof(a.p.beta));
+    a.m = h->m;
+    a.x0 = (const double*)d->x0_dev; a.U = (const double*)d->u_dev;
+    a.u_stride_t = d->u_stride_t; a.u_stride_n = d->u_stride_n;
+    a.lag_in = (const double*)d->lag_in_dev; a.lag_out = (double*)d->lag_out_dev;
+    a.traj = (double*)d->traj_dev; a.x9T = (float*)d->x9T_dev;
+    a.n = d->n; a.steps = (int)d->steps; a.stride = d->traj_dev ? (int)d->stride : 1;
+    pinc_rollout_kernel<<<(unsigned)((d->n + PB - 1) / PB), PB, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    BROV_CUDA_TRY(cudaGetLastError());
+    return BROV_OK;
+}
+
+extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d, void* stream) {
+    if (!h) return brov::fail_msg(BROV_EINVAL, "NULL handle");
+    if (!d || d->struct_size != sizeof(brov_pinc_se_desc)) return brov::fail_msg(BROV_EINVAL, "brov_pinc_se_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
+    if (!h->have_map) return brov::fail_msg(BROV_EINVAL, "call brov_pinc_set_thruster_map first");
+    if (d->n_horizons < 1 || d->n_horizons > BROV_MAX_H) return brov::fail_msg(BROV_EINVAL, "n_horizons must be 1..%d", BROV_MAX_H);
+    for (int q = 0; q < d->n_horizons; ++q)
+        if (d->horizons[q] < 1 || (q && d->horizons[q] <= d->horizons[q - 1])) return brov::fail_msg(BROV_EINVAL, "horizons must be >= 1 and strictly ascending");
+    if (d->carry_steps < 0 || (d->carry_steps > 0 && d->n_horizons != 1)) return brov::fail_msg(BROV_EINVAL, "a carried lag scores one horizon per call");
+    if (d->window0 < 0 || d->row0 < 0 || d->row0 > d->window0) return brov::fail_msg(BROV_EINVAL, "window0 / row0 out of range");
+    if (d->rows < 0 || d->n_windows < 0 || d->n_windows > d->rows) return brov::fail_msg(BROV_EINVAL, "rows / n_windows out of range");
+    if (!d->se_out_dev || (d->n_windows > 0 && (!d->X_dev || !d->U_dev))) return brov::fail_msg(BROV_EINVAL, "NULL array");
+    cudaStream_t st = (cudaStream_t)stream;
+    BROV_CUDA_TRY(cudaSetDevice(h->device));
+    if (d->n_windows == 0) {
+        BROV_CUDA_TRY(cudaMemsetAsync(d->se_out_dev, 0, BROV_MAX_H * sizeof(double), st));
+        return BROV_OK;
+    }
+    int rc = pinc_attrs(h);
+    if (rc) return rc;
+    const size_t nblocks = (size_t)((d->n_windows + PB - 1) / PB);
+    if (nblocks * BROV_MAX_H > h->cap_partial) {
+        cudaFree(h->partial);
+        h->partial = nullptr; h->cap_partial = 0;
+        BROV_CUDA_TRY(cudaMalloc(&h->partial, nblocks * BROV_MAX_H * sizeof(double)));
+        h->cap_partial = nblocks * BROV_MAX_H;
+    }
+    PincSeArgs a;
+    a.p.w = h->w;
+    memcpy(a.p.beta, h->beta, sizeof(a.p.beta));
+    a.m = h->m;
+    a.X = (const double*)d->X_dev; a.U = (const double*)d->U_dev; a.partial = h->partial;
+    a.rows = d->rows; a.nwin = d->n_windows; a.nH = d->n_horizons;
+    for (int q = 0; q < BROV_MAX_H; ++q) a.H[q] = q < d->n_horizons ? d->horizons[q] : 0x7fffffff;
+    a.carry_steps = d->carry_steps; a.win0 = d->window0; a.row0 = d->row0;
+    a.carry_lag0 = (const double*)d->carry_lag0_dev;
+    pinc_se_kernel<<<(unsigned)nblocks, PB, SMEM_BYTES, st>>>(a);
+    pinc_finish_kernel<<<1, 256, 0, st>>>(h->partial, (int)nblocks, d->se_out_dev);
+    BROV_CUDA_TRY(cudaGetLastError());
+    return BROV_OK;
+}

@@ -239,6 +239,71 @@ int brov_koopman_multistep_se(brov_koopman_t* h, const double* X_dev, const doub
 int brov_koopman_simulate(brov_koopman_t* h, const double* X0_dev, const double* U_dev, long long T, long long nb,
                           int u_shared, double* out_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * PINc comparison model — inference of the reference's residual network x_{k+1} = x_k + f([x_k, u_k, dt]) on the
+ * 9-state [x y z cos(psi) sin(psi) u v w r] with inputs [X Y Z Mz] from the thruster map (training/
+ * train_tank_brov2_rk4.py:553-840).  Network arithmetic is float32 (as torch runs it), the thruster map float64.
+ * Weights: the tensors of PINcNet.state_dict() (14 -> 64 -> 64 -> 64 -> 64 -> 9; Linear / AdaptiveSoftplus / LayerNorm
+ * per hidden layer), HOST float arrays in torch's layouts: W[l] is [out][in] row-major. */
+typedef struct brov_pinc brov_pinc_t;
+typedef struct brov_pinc_weights {
+    uint32_t struct_size;
+    int32_t n_hidden_layers;    /* 4 */
+    int32_t hidden;             /* 64 */
+    int32_t reserved;
+    const float* W[5];          /* net.0 / net.3 / net.6 / net.9 / net.12 .weight */
+    const float* b[5];          /* ... .bias */
+    float beta[4];              /* net.1 / net.4 / net.7 / net.10 .beta */
+    const float* ln_w[4];       /* net.2 / net.5 / net.8 / net.11 .weight */
+    const float* ln_b[4];       /* ... .bias */
+} brov_pinc_weights;
+int brov_pinc_create(int device, const brov_pinc_weights* w, brov_pinc_t** out);
+void brov_pinc_destroy(brov_pinc_t* h);
+/* Thruster map constants for the sampling time the rollouts run at: (Ad, Bd) from brov_lag_discretize(dt), alloc
+ * [6][8] from brov_default_allocation (thrusters_to_body_wrenches, :553-562). */
+int brov_pinc_set_thruster_map(brov_pinc_t* h, double dt, const double* Ad, const double* Bd, const double* alloc);
+/* PINcNet.forward (:627-673): z [n][14] = [x9, u4, dt] float -> x9_next [n][9] float. */
+int brov_pinc_forward(brov_pinc_t* h, const float* z_dev, float* out_dev, long long n, void* stream);
+/* simulate_pinc (:789-812) for n windows at once.  x0 [n][12] double (12-state rows), inputs as in brov_rollout
+ * (8 thruster voltages, double), lag_in [n][8][3] double or NULL = zeros; lag_out [n][4][3] double or NULL: the
+ * allocation-projected lag of the X, Y, Z, Mz rows; traj [steps/stride][n][12] double or NULL: 12-state projection
+ * (state9_to_12: phi = theta = p = q = 0, psi = atan2) after steps stride, 2 stride, ...; x9T [n][9] float or NULL. */
+typedef struct brov_pinc_rollout_desc {
+    uint32_t struct_size;
+    int32_t reserved;
+    long long n;
+    long long steps;
+    const void* x0_dev;
+    const void* u_dev;
+    long long u_stride_t, u_stride_n;
+    const void* lag_in_dev;
+    void* lag_out_dev;
+    void* traj_dev;
+    long long stride;
+    void* x9T_dev;
+} brov_pinc_rollout_desc;
+int brov_pinc_rollout(brov_pinc_t* h, const brov_pinc_rollout_desc* d, void* stream);
+/* multistep_rmse_endpoint_pinc (:815-840): as brov_multistep_se on X [rows][12], U [rows][8] (double).  carry_steps
+ * = 0: every window starts from zero lag; > 0 (one horizon): the reference's literal behaviour — one thruster-map
+ * object scores all windows in order — reproduced by replaying the last carry_steps lag steps of that history
+ * (brov_se_carry_steps(thruster engine, dt, BROV_EULER)).  se_out_dev: double[BROV_MAX_H], dev. */
+typedef struct brov_pinc_se_desc {
+    uint32_t struct_size;
+    int32_t n_horizons;
+    int32_t horizons[BROV_MAX_H];
+    long long rows;
+    long long n_windows;
+    const void* X_dev;
+    const void* U_dev;
+    double* se_out_dev;
+    int32_t carry_steps;
+    int32_t reserved;
+    long long window0;
+    long long row0;
+    const void* carry_lag0_dev;  /* [8][3] double: lag state of the thruster-map object before window 0, or NULL = zeros */
+} brov_pinc_se_desc;
+int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d, void* stream);
+
 /* Host-buffer rollout: the same operation as brov_rollout with every array in HOST memory (pinned memory gives
  * asynchronous copies).  The engine streams the inputs to the device in time chunks on a copy stream, double
  * buffered against the rollout kernels, and copies snapshots and final state back; it returns after everything has

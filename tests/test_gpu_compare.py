@@ -140,3 +140,76 @@ def test_koopman_fit_matches_reference(cg):
     M = (np.linalg.pinv(Gm.T @ Gm + 0.1 * np.eye(40)) @ (Gm.T @ Zp)).T
     assert np.allclose(K.A_, M[:, :32], atol=1e-9) and np.allclose(K.B_, M[:, 32:], atol=1e-9)
     assert K.evaluate(X, U) < 0.5
+
+
+# --------------------------------------------------------------------------------------------------------- PINc
+@pytest.fixture(scope="module")
+def PM(cg):
+    from bluerov2_dynamics_b200 import pinc
+    sd = {k[len("pinc_sd_"):]: v for k, v in cg.items() if k.startswith("pinc_sd_")}
+    return pinc, pinc.PincModel(sd)
+
+
+def test_pinc_forward_against_reference(PM, cg):
+    pinc, model = PM
+    out = cpu(model(cg["pinc_dataset_zin"][:64]))
+    assert normwise(out, cg["pinc_forward"]) < 2e-6     # float32 network, torch CPU vs CUDA rounding
+    with pytest.raises(ValueError):
+        model(np.zeros((3, 13), np.float32))
+
+
+def test_pinc_rollout_and_rmse_against_reference(PM, golden, cg):
+    pinc, model = PM
+    from bluerov2_dynamics_b200.fossen.BlueROV2 import BlueROV2
+    X12, U8, dt = golden["rmse_X12"], golden["rmse_U8"], float(cg["cmp_dt"])
+    HS = [int(h) for h in cg["cmp_H"]]
+    rov = BlueROV2(dt=dt)
+    traj = pinc.simulate_pinc(X12[0], U8[:120], dt, model, rov, None)
+    assert traj.shape == cg["pinc_traj"].shape
+    assert normwise(traj, cg["pinc_traj"]) < TOL32
+    # the rollout left rov's lag where 120 reference thruster-map calls leave it
+    from oracle import fossen_np as O
+    m = O.Model("thruster8", dt)
+    lag = m.zero_lag(1)
+    for u in U8[:120]:
+        _, lag = CN.thruster_map4(u[None], lag, m.Ad, m.Bd, m.alloc)
+    assert normwise(np.stack([l._x for l in rov.thruster_lags]), lag[0]) < 1e-12
+    got = pinc.multistep_rmse_endpoint_pinc(X12, U8, HS, dt, model, None, None, lag_mode="reset")
+    assert np.allclose(got, cg["pinc_rmse_reset"], rtol=TOL32)
+    got = [pinc.multistep_rmse_endpoint_pinc(X12, U8, h, dt, model, BlueROV2(dt=dt), None) for h in HS]
+    assert np.allclose(got, cg["pinc_rmse_carry"], rtol=TOL32)
+    assert np.isnan(pinc.multistep_rmse_endpoint_pinc(X12[:5], U8[:5], 10, dt, model))
+
+
+def test_pinc_helpers(PM, golden, cg):
+    pinc, _ = PM
+    X12 = golden["rmse_X12"]
+    assert normwise(pinc.batch12_to_9(X12)[:-1], cg["pinc_dataset_zin"][:, :9]) < 1e-15
+    assert np.allclose(pinc.dataset12_to_9(X12[3]), pinc.batch12_to_9(X12[3:4])[0])
+    x9 = pinc.batch12_to_9(X12)
+    back = pinc.batch9_to_12(x9)
+    assert np.allclose(back[:, [0, 1, 2, 6, 7, 8, 11]], X12[:, [0, 1, 2, 6, 7, 8, 11]])
+    assert np.allclose(np.cos(back[:, 5]), np.cos(X12[:, 5])) and np.all(back[:, [3, 4, 9, 10]] == 0)
+    assert np.allclose(pinc.state9_to_12(x9[5]), back[5])
+    from bluerov2_dynamics_b200.fossen.BlueROV2 import BlueROV2
+    rov = BlueROV2(dt=0.02)
+    u4 = np.stack([pinc.thrusters_to_body_wrenches(u, 0.02, rov) for u in golden["rmse_U8"][:20]])
+    assert normwise(u4, cg["pinc_U4_carry"][:20]) < 1e-12
+
+
+def test_pinc_ensemble_against_oracle(PM, cg):
+    """4096 windows x 60 steps with per-window inputs and non-zero initial lag vs the numpy float32 oracle."""
+    pinc, model = PM
+    rng = np.random.default_rng(17)
+    n, T, dt = 4096, 60, 0.02
+    x0 = np.zeros((n, 12))
+    x0[:, :3] = rng.uniform(-2, 2, (n, 3))
+    x0[:, 5] = rng.uniform(-3, 3, n)
+    x0[:, 6:9] = rng.uniform(-0.3, 0.3, (n, 3))
+    x0[:, 11] = rng.uniform(-0.3, 0.3, n)
+    U = rng.uniform(-0.6, 0.6, (T, n, 8))
+    lag0 = rng.normal(0, 0.05, (n, 8, 3))
+    snaps, x9, _ = CN.pinc_rollout(x0, U, dt, CN.pinc_weights(cg), lag0=lag0, stride=20)
+    traj, x9g, _ = model.rollout(x0, U, dt, lag0=lag0, stride=20)
+    assert normwise(cpu(traj), snaps) < TOL32
+    assert normwise(cpu(x9g), x9) < TOL32

@@ -24,7 +24,9 @@
 
 namespace {
 
-constexpr int KB = 128;        // threads per block of the window kernels
+constexpr int KB = 128;        // threads per block of the lift kernel
+constexpr int SEB = 512;       // threads per block of the scoring kernel: ONE persistent block per SM (16 warps) so that
+                               // the model is staged into shared memory once per SM, not once per 128 windows
 constexpr int NMAX = 16;       // state dimension bound (registers)
 constexpr int RMAX = 8;        // input dimension bound
 
@@ -126,7 +128,7 @@ struct KoopSeArgs {
     const double* c2;     // [k]
     const double* WH;     // [n][d]   = W_H
     const double* G;      // [H][n][r] (G_0 .. G_{H-1})
-    double* partial;      // [gridDim.x]
+    double* partial;      // [tiles of SEB windows]
     double gamma;
     long long nwin;
     int n, r, k, H;
@@ -134,81 +136,92 @@ struct KoopSeArgs {
 };
 
 template <int N, int R>
-__global__ void __launch_bounds__(KB) koop_se_kernel(const KoopSeArgs a) {
+__global__ void __launch_bounds__(SEB, 1) koop_se_kernel(const KoopSeArgs a) {
     extern __shared__ double sm[];
     const int k = a.k, d = N + a.k, H = a.H;
     double* sC = sm;                         // [k][N]
     double* sc2 = sC + (size_t)k * N;        // [k]
     double* sW = sc2 + k;                    // [d][N]  (transposed: the N outputs of one lifted coordinate contiguous)
     double* sG = sW + (size_t)d * N;         // [H][N][R]
-    for (int e = threadIdx.x; e < k * N; e += KB) sC[e] = a.C[e];
-    for (int e = threadIdx.x; e < k; e += KB) sc2[e] = a.c2[e];
-    for (int e = threadIdx.x; e < d * N; e += KB) {
+    for (int e = threadIdx.x; e < k * N; e += SEB) sC[e] = a.C[e];
+    for (int e = threadIdx.x; e < k; e += SEB) sc2[e] = a.c2[e];
+    for (int e = threadIdx.x; e < d * N; e += SEB) {
         const int q = e / N, i = e - q * N;
         sW[e] = a.WH[(size_t)i * d + q];
     }
     if (a.g_in_smem)
-        for (int e = threadIdx.x; e < H * N * R; e += KB) sG[e] = a.G[e];
+        for (int e = threadIdx.x; e < H * N * R; e += SEB) sG[e] = a.G[e];
     __syncthreads();
     const double* G = a.g_in_smem ? sG : a.G;
+    __shared__ double red[SEB / 32];
 
-    const long long w = (long long)blockIdx.x * KB + threadIdx.x;
-    double se = 0.0;
-    if (w < a.nwin) {
-        double x[N], acc[N], x2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            x[i] = __ldg(a.X + w * N + i);
-            x2 = fma(x[i], x[i], x2);
-            acc[i] = 0.0;
-        }
-        // linear part of the lift
-#pragma unroll
-        for (int q = 0; q < N; ++q) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = fma(sW[q * N + i], x[q], acc[i]);
-        }
-        // radial basis functions
-        const double mg = -a.gamma;
-#pragma unroll 2
-        for (int j = 0; j < k; ++j) {
-            double dot = 0.0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) dot = fma(x[i], sC[j * N + i], dot);
-            const double e = exp(mg * (x2 + sc2[j] - 2.0 * dot));
-            const double* wc = sW + (size_t)(N + j) * N;
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc[i] = fma(wc[i], e, acc[i]);
-        }
-        // input FIR: sum_t G_{H-1-t} u_{k+t}
-        for (int t = 0; t < H; ++t) {
-            double u[R];
-#pragma unroll
-            for (int c = 0; c < R; ++c) u[c] = __ldg(a.U + (w + t) * R + c);
-            const double* g = G + (size_t)(H - 1 - t) * N * R;
+    const long long ntiles = (a.nwin + SEB - 1) / SEB;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long w = tile * SEB + threadIdx.x;
+        double se = 0.0;
+        if (w < a.nwin) {
+            double x[N], acc[N], x2 = 0.0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
+                x[i] = __ldg(a.X + w * N + i);
+                x2 = fma(x[i], x[i], x2);
+                acc[i] = 0.0;
+            }
+            // linear part of the lift
 #pragma unroll
-                for (int c = 0; c < R; ++c) acc[i] = fma(g[i * R + c], u[c], acc[i]);
+            for (int q = 0; q < N; ++q) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = fma(sW[q * N + i], x[q], acc[i]);
+            }
+            // radial basis functions
+            const double mg = -a.gamma;
+#pragma unroll 2
+            for (int j = 0; j < k; ++j) {
+                double dot = 0.0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) dot = fma(x[i], sC[j * N + i], dot);
+                const double e = exp(mg * (x2 + sc2[j] - 2.0 * dot));
+                const double* wc = sW + (size_t)(N + j) * N;
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[i] = fma(wc[i], e, acc[i]);
+            }
+            // input FIR: sum_t G_{H-1-t} u_{k+t}; the next row of inputs is in flight while this one is consumed
+            double un[R];
+#pragma unroll
+            for (int c = 0; c < R; ++c) un[c] = __ldg(a.U + w * R + c);
+            for (int t = 0; t < H; ++t) {
+                double u[R];
+#pragma unroll
+                for (int c = 0; c < R; ++c) u[c] = un[c];
+                if (t + 1 < H) {
+#pragma unroll
+                    for (int c = 0; c < R; ++c) un[c] = __ldg(a.U + (w + t + 1) * R + c);
+                }
+                const double* g = G + (size_t)(H - 1 - t) * N * R;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+#pragma unroll
+                    for (int c = 0; c < R; ++c) acc[i] = fma(g[i * R + c], u[c], acc[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double e = __ldg(a.X + (w + H) * N + i) - acc[i];
+                se = fma(e, e, se);
             }
         }
+        // block reduction, fixed order; one partial per tile keeps the final sum independent of the grid size
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double e = __ldg(a.X + (w + H) * N + i) - acc[i];
-            se = fma(e, e, se);
+        for (int off = 16; off > 0; off >>= 1) se += __shfl_down_sync(0xffffffffu, se, off);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < SEB / 32; ++q) s += red[q];
+            a.partial[tile] = s;
         }
-    }
-    // block reduction, fixed order
-    __shared__ double red[KB / 32];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) se += __shfl_down_sync(0xffffffffu, se, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < KB / 32; ++q) s += red[q];
-        a.partial[blockIdx.x] = s;
+        __syncthreads();
     }
 }
 
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(128) koop_sim_kernel(const double* __restrict_
 // handle
 // ---------------------------------------------------------------------------------------------------------------
 struct brov_koopman {
-    int device, n, r, k, d;
+    int device, n, r, k, d, num_sms;
     double gamma;
     double *C, *c2, *A, *B;     // device copies
     double* W;                  // [cap_t + 1][n][d]: W_0 .. W_{have_t}
@@ -321,6 +334,7 @@ extern "C" int brov_koopman_create(int device, int n, int r, int k, double gamma
     if (!h) return brov::fail_msg(BROV_ENOMEM, "out of host memory");
     memset(h, 0, sizeof(*h));
     h->device = device; h->n = n; h->r = r; h->k = k; h->d = n + k; h->gamma = gamma;
+    h->num_sms = prop.multiProcessorCount;
     const int d = h->d;
     cudaError_t e = cudaSuccess;
     if (e == cudaSuccess) e = cudaMalloc(&h->C, (size_t)(k > 0 ? k : 1) * n * sizeof(double));
@@ -370,8 +384,9 @@ static int koop_se_launch(brov_koopman* h, const KoopSeArgs& a0, size_t smem_bas
     a.g_in_smem = (smem_base + g_bytes <= 200 * 1024) ? 1 : 0;
     const size_t smem = smem_base + (a.g_in_smem ? g_bytes : 0);
     if (smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_se_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((a.nwin + KB - 1) / KB);
-    koop_se_kernel<N, R><<<grid, KB, smem, st>>>(a);
+    const long long ntiles = (a.nwin + SEB - 1) / SEB;
+    const unsigned grid = (unsigned)(ntiles < h->num_sms ? ntiles : h->num_sms);
+    koop_se_kernel<N, R><<<grid, SEB, smem, st>>>(a);
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;
 }
@@ -389,7 +404,7 @@ extern "C" int brov_koopman_multistep_se(brov_koopman_t* h, const double* X_dev,
     }
     int rc = koop_prepare(h, H, st);
     if (rc) return rc;
-    const size_t nblocks = (size_t)((n_windows + KB - 1) / KB);
+    const size_t nblocks = (size_t)((n_windows + SEB - 1) / SEB);   // one partial per tile of SEB windows
     if (nblocks > h->cap_partial) {
         cudaFree(h->partial);
         h->partial = nullptr; h->cap_partial = 0;

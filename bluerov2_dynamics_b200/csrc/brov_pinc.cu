@@ -25,7 +25,8 @@ namespace {
 
 constexpr int HID = 64;
 constexpr int NIN = 14;
-constexpr int PB = 128;   // threads per block
+constexpr int PB = 384;   // threads per block: 12 warps share one 58 KB copy of the weights; with the 96 KB of activation
+                          // columns that is one block per SM, and 168 registers x 384 threads fill the register file
 
 // packed weight blob (floats), see brov_pinc_create
 constexpr int OFF_W0 = 0;                         // [14][64]  (input-major: the 64 weights of one input contiguous)
@@ -47,94 +48,110 @@ struct PincParams {
     float beta[4];
 };
 
-__device__ __forceinline__ float softplus_f(float x) {
-    // torch.nn.functional.softplus(beta = 1, threshold = 20)
-    return x > 20.0f ? x : log1pf(expf(x));
+// Packed FP32 arithmetic of sm_100: one FFMA2 instruction performs two fused multiply-adds on a 64-bit register pair,
+// halving the issue slots of the dense layers (the FP32 pipe rate is unchanged; the freed slots go to the shared-memory
+// loads that feed it).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ void fma2(u64& d, u64 a, u64 b) {   // d += a * b, lane-wise on (lo, hi)
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 
-// activation + LayerNorm of the 64 pre-activations in `a`, result to the thread's shared-memory column
-__device__ __forceinline__ void act_norm_store(float* a, float beta, const float* __restrict__ lnw,
+// torch.nn.functional.softplus(beta = 1, threshold = 20) = x > 20 ? x : log1p(exp(x)), evaluated as
+// max(x, 0) + log(1 + exp(-|x|)) with the two MUFU approximations: absolute error <= 1.2e-7 (the rounding of 1 + e),
+// i.e. float32 resolution of the O(1) activations that LayerNorm is about to standardise.
+__device__ __forceinline__ float softplus_f(float x) {
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -1.4426950408889634f));   // exp(-|x|)
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));                           // argument in [1, 2]
+    return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.0f));
+}
+
+// activation + LayerNorm of the 64 pre-activations (32 packed pairs), result to the thread's shared-memory column
+__device__ __forceinline__ void act_norm_store(const u64* a2, float beta, const float* __restrict__ lnw,
                                                const float* __restrict__ lnb, float* __restrict__ hcol) {
     const float ib = 1.0f / (beta + 1e-12f);
+    float a[HID];
     float mean = 0.0f;
 #pragma unroll
-    for (int j = 0; j < HID; ++j) {
-        a[j] = softplus_f(beta * a[j]) * ib;
-        mean += a[j];
+    for (int j = 0; j < HID / 2; ++j) {
+        float lo, hi;
+        unpack2(a2[j], lo, hi);
+        a[2 * j] = softplus_f(beta * lo) * ib;
+        a[2 * j + 1] = softplus_f(beta * hi) * ib;
+        mean += a[2 * j] + a[2 * j + 1];
     }
     mean *= (1.0f / HID);
     float var = 0.0f;
 #pragma unroll
     for (int j = 0; j < HID; ++j) {
-        const float d = a[j] - mean;
-        var = fmaf(d, d, var);
+        a[j] -= mean;
+        var = fmaf(a[j], a[j], var);
     }
     const float rstd = rsqrtf(var * (1.0f / HID) + 1e-5f);
 #pragma unroll
     for (int q = 0; q < HID / 4; ++q) {
         const float4 g = *reinterpret_cast<const float4*>(lnw + 4 * q);
         const float4 b = *reinterpret_cast<const float4*>(lnb + 4 * q);
-        hcol[(4 * q + 0) * PB] = fmaf((a[4 * q + 0] - mean) * rstd, g.x, b.x);
-        hcol[(4 * q + 1) * PB] = fmaf((a[4 * q + 1] - mean) * rstd, g.y, b.y);
-        hcol[(4 * q + 2) * PB] = fmaf((a[4 * q + 2] - mean) * rstd, g.z, b.z);
-        hcol[(4 * q + 3) * PB] = fmaf((a[4 * q + 3] - mean) * rstd, g.w, b.w);
+        hcol[(4 * q + 0) * PB] = fmaf(a[4 * q + 0] * rstd, g.x, b.x);
+        hcol[(4 * q + 1) * PB] = fmaf(a[4 * q + 1] * rstd, g.y, b.y);
+        hcol[(4 * q + 2) * PB] = fmaf(a[4 * q + 2] * rstd, g.z, b.z);
+        hcol[(4 * q + 3) * PB] = fmaf(a[4 * q + 3] * rstd, g.w, b.w);
     }
 }
 
-__device__ __forceinline__ void bias_init(float* a, const float* __restrict__ b) {
+template <int NPAIR>
+__device__ __forceinline__ void bias_init(u64* a2, const float* __restrict__ b) {
 #pragma unroll
-    for (int q = 0; q < HID / 4; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(b + 4 * q);
-        a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    for (int q = 0; q < NPAIR / 2; ++q) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(b + 4 * q);
+        a2[2 * q] = v.x;
+        a2[2 * q + 1] = v.y;
     }
 }
 
-__device__ __forceinline__ void axpy64(float* a, const float* __restrict__ wrow, float x) {
+// a2 += wrow * x for NPAIR packed pairs (wrow: 2 NPAIR contiguous floats in shared memory, 128-bit broadcast loads)
+template <int NPAIR>
+__device__ __forceinline__ void axpy(u64* a2, const float* __restrict__ wrow, float x) {
+    const u64 xx = pack2(x, x);
 #pragma unroll
-    for (int q = 0; q < HID / 4; ++q) {
-        const float4 w = *reinterpret_cast<const float4*>(wrow + 4 * q);
-        a[4 * q + 0] = fmaf(w.x, x, a[4 * q + 0]);
-        a[4 * q + 1] = fmaf(w.y, x, a[4 * q + 1]);
-        a[4 * q + 2] = fmaf(w.z, x, a[4 * q + 2]);
-        a[4 * q + 3] = fmaf(w.w, x, a[4 * q + 3]);
+    for (int q = 0; q < NPAIR / 2; ++q) {
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wrow + 4 * q);
+        fma2(a2[2 * q], w.x, xx);
+        fma2(a2[2 * q + 1], w.y, xx);
     }
 }
 
 // PINcNet.forward: z[14] -> x9_next[9].  sw: weights in shared memory, hcol: this thread's activation column.
 __device__ __forceinline__ void pinc_forward(const float* __restrict__ sw, const float* beta, float* __restrict__ hcol,
                                              const float* __restrict__ z, float* __restrict__ xn) {
-    float a[HID];
-    bias_init(a, sw + OFF_B0);
+    u64 a2[HID / 2];
+    bias_init<HID / 2>(a2, sw + OFF_B0);
 #pragma unroll
-    for (int i = 0; i < NIN; ++i) axpy64(a, sw + OFF_W0 + i * HID, z[i]);
-    act_norm_store(a, beta[0], sw + OFF_B0 + HID, sw + OFF_B0 + 2 * HID, hcol);
+    for (int i = 0; i < NIN; ++i) axpy<HID / 2>(a2, sw + OFF_W0 + i * HID, z[i]);
+    act_norm_store(a2, beta[0], sw + OFF_B0 + HID, sw + OFF_B0 + 2 * HID, hcol);
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
         const float* L = sw + OFF_L1 + l * LSTRIDE;
-        bias_init(a, L + HID * HID);
+        bias_init<HID / 2>(a2, L + HID * HID);
 #pragma unroll 4
-        for (int i = 0; i < HID; ++i) axpy64(a, L + i * HID, hcol[i * PB]);
-        act_norm_store(a, beta[l + 1], L + HID * HID + HID, L + HID * HID + 2 * HID, hcol);
+        for (int i = 0; i < HID; ++i) axpy<HID / 2>(a2, L + i * HID, hcol[i * PB]);
+        act_norm_store(a2, beta[l + 1], L + HID * HID + HID, L + HID * HID + 2 * HID, hcol);
     }
+    u64 d2[6];
+    bias_init<6>(d2, sw + OFF_B4);
+#pragma unroll 4
+    for (int i = 0; i < HID; ++i) axpy<6>(d2, sw + OFF_W4 + i * 12, hcol[i * PB]);
     float dx[12];
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(sw + OFF_B4 + 4 * q);
-        dx[4 * q] = v.x; dx[4 * q + 1] = v.y; dx[4 * q + 2] = v.z; dx[4 * q + 3] = v.w;
-    }
-#pragma unroll 4
-    for (int i = 0; i < HID; ++i) {
-        const float h = hcol[i * PB];
-        const float* wr = sw + OFF_W4 + i * 12;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const float4 w = *reinterpret_cast<const float4*>(wr + 4 * q);
-            dx[4 * q + 0] = fmaf(w.x, h, dx[4 * q + 0]);
-            dx[4 * q + 1] = fmaf(w.y, h, dx[4 * q + 1]);
-            dx[4 * q + 2] = fmaf(w.z, h, dx[4 * q + 2]);
-            dx[4 * q + 3] = fmaf(w.w, h, dx[4 * q + 3]);
-        }
-    }
+    for (int q = 0; q < 6; ++q) unpack2(d2[q], dx[2 * q], dx[2 * q + 1]);
     // residual update; body-frame (dx, dy) rotated by the CURRENT yaw; (cos, sin) re-normalised (:639-673)
     const float c = z[3], s = z[4];
     float base[9];
@@ -220,7 +237,7 @@ __device__ __forceinline__ void x9_to_12(const float* __restrict__ x9, double* _
 // ---------------------------------------------------------------------------------------------------------------
 constexpr size_t SMEM_BYTES = (size_t)(NW + HID * PB) * sizeof(float);
 
-__global__ void __launch_bounds__(PB) pinc_forward_kernel(PincParams p, const float* __restrict__ Zin,
+__global__ void __launch_bounds__(PB, 1) pinc_forward_kernel(PincParams p, const float* __restrict__ Zin,
                                                           float* __restrict__ out, long long n) {
     extern __shared__ __align__(16) float smf[];
     float* sw = smf;
@@ -251,7 +268,7 @@ struct PincRollArgs {
     int steps, stride;
 };
 
-__global__ void __launch_bounds__(PB) pinc_rollout_kernel(const __grid_constant__ PincRollArgs a) {
+__global__ void __launch_bounds__(PB, 1) pinc_rollout_kernel(const __grid_constant__ PincRollArgs a) {
     extern __shared__ __align__(16) float smf[];
     float* sw = smf;
     float* hcol = smf + NW + threadIdx.x;
@@ -317,7 +334,7 @@ struct PincSeArgs {
     const double* carry_lag0;  // [8][3] lag state of the thruster-map object before window 0, or nullptr (zeros)
 };
 
-__global__ void __launch_bounds__(PB) pinc_se_kernel(const __grid_constant__ PincSeArgs a) {
+__global__ void __launch_bounds__(PB, 1) pinc_se_kernel(const __grid_constant__ PincSeArgs a) {
     extern __shared__ __align__(16) float smf[];
     float* sw = smf;
     float* hcol = smf + NW + threadIdx.x;

@@ -213,3 +213,23 @@ def test_pinc_ensemble_against_oracle(PM, cg):
     traj, x9g, _ = model.rollout(x0, U, dt, lag0=lag0, stride=20)
     assert normwise(cpu(traj), snaps) < TOL32
     assert normwise(cpu(x9g), x9) < TOL32
+
+
+# ------------------------------------------------------------------------------------- data formats around the path
+def test_generate_sim_dataset_matches_reference(golden):
+    """training/train_sim_brov2_koopmanEDMDc.py:153-197 with seed 42: same inputs (bit for bit), same Euler rollout."""
+    from bluerov2_dynamics_b200.datasets import generate_sim_dataset
+    true, noisy, U = generate_sim_dataset(1500, dt=0.05, seed=42)
+    assert np.array_equal(U, golden["simgen_inputs"])
+    assert normwise(true[::10], golden["simgen_states_true_s10"]) < TOL64
+    assert normwise(noisy[::10], golden["simgen_states_noisy_s10"]) < TOL64
+
+
+def test_csv_series_through_the_evaluators(tmp_path, golden):
+    from bluerov2_dynamics_b200.datasets import load_dataset, save_dataset
+    from bluerov2_dynamics_b200.evaluators import multistep_rmse_endpoint_physics
+    p = tmp_path / "series.csv"
+    save_dataset(p, golden["rmse_X12"], golden["rmse_U8"], 0.02)
+    X, U, dt = load_dataset(p, verbose=False)
+    got = multistep_rmse_endpoint_physics(X, U, [1, 10, 100], dt, integrator="rk4", lag_mode="carry")
+    assert np.allclose(got, golden["rmse_thr_rk4_carry"], rtol=1e-9)

@@ -244,6 +244,19 @@ static int make_consts(brov_engine* e, double dt, int nsub, Consts<T>* c) {
     for (int i = 0; i < KP_COUNT; ++i) c->kp[i] = (T)e->kp[i];
     for (int r = 0; r < 6; ++r) for (int i = 0; i < 8; ++i) c->alloc[r][i] = (T)e->alloc[r][i];
     c->dt = (T)dt;
+    {
+        const double poly[5] = {-140.3, 389.9, -404.1, 176.0, 8.9};   // fossen/BlueROV2.py:251-257, highest power first
+        const double sc[16] = {0.6366197723675814, 1.5707963267948966, 6.123233995736766e-17, -1.4973849048591698e-33,
+                               -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                               2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+                               4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                               -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+        const double rot[8] = {-1.6666666666666667e-1, 8.3333333333333333e-3, -1.9841269841269841e-4, -0.5,
+                               4.1666666666666667e-2, -1.3888888888888889e-3, 2.4801587301587302e-5, 0.0};
+        for (int i = 0; i < 5; ++i) c->poly[i] = (T)poly[i];
+        for (int i = 0; i < 16; ++i) c->sc[i] = (T)sc[i];
+        for (int i = 0; i < 8; ++i) c->rot[i] = (T)rot[i];
+    }
     c->has_current = (e->kp[KP_CUR] != 0.0 || e->kp[KP_CUR + 1] != 0.0 || e->kp[KP_CUR + 2] != 0.0 || e->pv != nullptr) ? 1 : 0;
     c->use_lag1 = e->use_lag1;
     if (e->model == BROV_THRUSTER8_LAG3) {
@@ -503,6 +516,8 @@ static int check_rollout_common(brov_engine* e, int integrator, long long n, lon
     if (integrator != BROV_RK4 && integrator != BROV_EULER) return fail(BROV_EINVAL, "unknown integrator %d", integrator);
     if (n < 0 || n > 0x7fffffffLL) return fail(BROV_EINVAL, "n = %lld out of range", n);
     if (steps < 0 || steps > 0x7fffffffLL) return fail(BROV_EINVAL, "steps = %lld out of range", steps);
+    // the fp64 kernels re-base their constant block by (step + stage) >> 30, which must stay zero (brov_device.cuh)
+    if (steps > (1LL << 29)) return fail(BROV_EINVAL, "steps = %lld: at most 2^29 steps per call; continue from xT / lag_out with step0", steps);
     if (!(dt > 0.0) || !std::isfinite(dt)) return fail(BROV_EINVAL, "dt must be a positive finite number");
     if (e->pv && e->pv_n != n) return fail(BROV_EINVAL, "vehicle table has %lld rows, call has n = %lld", e->pv_n, n);
     return BROV_OK;
@@ -608,7 +623,7 @@ extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* 
     if (d->window0 < 0 || d->row0 < 0 || d->row0 > d->window0) return fail(BROV_EINVAL, "window0 / row0 out of range");
     if (!d->lag_carry && (d->window0 != d->row0)) return fail(BROV_EINVAL, "rows before the first window are only meaningful with lag_carry");
     for (int h = 0; h < d->n_horizons; ++h)
-        if (d->horizons[h] < 1 || (h && d->horizons[h] <= d->horizons[h - 1])) return fail(BROV_EINVAL, "horizons must be >= 1 and strictly ascending");
+        if (d->horizons[h] < 1 || d->horizons[h] > (1 << 29) || (h && d->horizons[h] <= d->horizons[h - 1])) return fail(BROV_EINVAL, "horizons must be in [1, 2^29] and strictly ascending");
     if (d->rows < 0 || d->rows > 0x7fffffffLL || d->n_windows < 0 || d->n_windows > d->rows) return fail(BROV_EINVAL, "rows / n_windows out of range");
     if (!(d->dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
     if (!d->se_out_dev) return fail(BROV_EINVAL, "se_out is NULL");

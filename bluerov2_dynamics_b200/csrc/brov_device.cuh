@@ -18,6 +18,14 @@
 #include <stdint.h>
 #include <type_traits>
 
+// Measured on B200 (profiles/tune_variants.py, 65,536 vehicles x 100 RK4 steps, fp64): constants as kernel-argument
+// members, hoisted + R2UR/UMOV shuffling 0.491 ms; constants in shared memory, hoisted 0.481 ms (default); re-based
+// kernel-argument constants (LDC.64 c[0][R+off] at every use, 450 fewer instructions per step) 0.542 ms; re-based
+// shared-memory constants (LDS.64 at every use) 0.527 ms.  The instruction savings of re-basing lose to the load
+// latency they put in front of the FP64 pipe at 2 warps per scheduler, so it is off by default.
+#ifndef BROV_F64_REBASE
+#define BROV_F64_REBASE 0
+#endif
 #ifndef BROV_STAGE_UNROLL
 #define BROV_STAGE_UNROLL 3
 #endif
@@ -75,9 +83,29 @@ template <typename T> struct Consts {
     T lagA[3][3];
     T lagB[3];
     T dt;
+    // literal tables of the fp64 build (filled by make_consts): T200 polynomial, sincos kernel, stage-rotation Taylor
+    // coefficients.  As kernel-argument members they are fetched with one LDCU.64 each; as C++ literals every use costs
+    // two UMOVs, as a __constant__ array they are hoisted into registers and shuffled back through R2UR.
+    T poly[5];     // -140.3, 389.9, -404.1, 176.0, 8.9
+    T sc[16];      // see kSinCos64
+    T rot[8];      // sin: -1/6, 1/120, -1/5040 ; cos: -1/2, 1/24, -1/720, 1/40320 ; pad
     int has_current;
     int use_lag1;
 };
+
+// fp64 only, experimental (BROV_F64_REBASE).  sm_100 FP instructions take constants from UNIFORM REGISTERS, not from the constant bank directly; an fp64
+// step touches ~130 distinct 64-bit constants = 260 uniform registers against ~80 available.  Left alone, the compiler
+// hoists every constant load out of the step loop and then spends ~450 instructions per step moving them between
+// regular and uniform registers (R2UR / MOV.SPILL / UMOV).  Re-basing the constant block by a loop-variant offset that
+// is always zero (`z` = step index >> 30) makes the loads non-hoistable: each use becomes ONE `LDCU.64 UR, c[0][UR+off]`
+// next to its consumer.  fp32 constants are half the size and fit; that build keeps the plain reference.
+template <typename T>
+__device__ __forceinline__ const Consts<T>& rebase(const Consts<T>& c, int z) {
+    if constexpr (sizeof(T) == 8 && BROV_F64_REBASE)
+        return *reinterpret_cast<const Consts<T>*>(reinterpret_cast<const char*>(&c) + (long long)z * 8);
+    else
+        return c;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // scalar helpers
@@ -111,7 +139,7 @@ __device__ __forceinline__ double rcp_(double a) {
 // sin & cos.  fp32: 3-term Cody-Waite reduction by pi/2 (FMA keeps the products exact) + minimax polynomials on
 // [-pi/4, pi/4] (Cephes sinf/cosf coefficients); |error| <= ~1.5 ulp.  No slow path, no local memory; domain
 // |a| < 2^30 rad (a float that large has an ulp of 64 rad anyway).
-__device__ __forceinline__ void sincos_(float a, float* s, float* c) {
+__device__ __forceinline__ void sincos_(float a, float* s, float* c, const float* = nullptr) {
     float j = rintf(a * 0.6366197466850281f);
     float r = fmaf(-j, 1.5707963705062866f, a);
     r = fmaf(-j, -4.371138828673793e-08f, r);
@@ -136,8 +164,7 @@ static __constant__ double kSinCos64[16] = {
     -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
 // fp64: same scheme with the fdlibm __kernel_sin/__kernel_cos coefficients.  The FMA makes each reduction step a
 // single rounding, so full-precision parts of pi/2 suffice.  Domain |a| < 2^30 rad (quadrant held in an int).
-__device__ __forceinline__ void sincos_(double a, double* s, double* c) {
-    const double* K = kSinCos64;  // constant bank: 64-bit literals would otherwise be rebuilt with UMOV pairs per use
+__device__ __forceinline__ void sincos_(double a, double* s, double* c, const double* K = kSinCos64) {
     double j = rint(a * K[0]);
     double r = fma(-j, K[1], a);
     r = fma(-j, K[2], r);
@@ -182,6 +209,19 @@ template <typename T> __device__ __forceinline__ T thrust_poly(T V) {
     p = p * z + T(8.9);
     return p * V;
 }
+// same with the coefficients read from the constant block (fp64 rollouts)
+template <typename T> __device__ __forceinline__ T thrust_poly(const Consts<T>& c, T V) {
+    if constexpr (sizeof(T) == 8) {
+        T z = V * V;
+        T p = c.poly[0] * z + c.poly[1];
+        p = p * z + c.poly[2];
+        p = p * z + c.poly[3];
+        p = p * z + c.poly[4];
+        return p * V;
+    } else {
+        return thrust_poly<T>(V);
+    }
+}
 
 // nu_dot = Minv (tau - C(nu) nu - D(nu_r) nu_r - g); g from (sin th, cos th sin phi, cos th cos phi).
 template <typename T, class P>
@@ -219,6 +259,16 @@ template <typename T> __device__ __forceinline__ void trig_full(const T* __restr
     sincos_(ang[1], &t.sth, &t.cth);
     sincos_(ang[2], &t.spsi, &t.cpsi);
 }
+template <typename T>
+__device__ __forceinline__ void trig_full(const Consts<T>& c, const T* __restrict__ ang, Trig<T>& t) {
+    if constexpr (sizeof(T) == 8) {
+        sincos_(ang[0], &t.sphi, &t.cphi, c.sc);
+        sincos_(ang[1], &t.sth, &t.cth, c.sc);
+        sincos_(ang[2], &t.spsi, &t.cpsi, c.sc);
+    } else {
+        trig_full<T>(ang, t);
+    }
+}
 
 // fp32 RK4 stages 2..4: the stage angles are base + d with a small increment d = c*dt*k, so their sines/cosines
 // follow from the step's base values by the angle-addition formulas with a short Taylor series for sin d, cos d
@@ -232,7 +282,7 @@ __device__ __forceinline__ void rotate_sc(float s, float c, float d, float* so, 
     *so = fmaf(s, cd, c * sd);
     *co = fmaf(c, cd, -(s * sd));
 }
-__device__ __forceinline__ void trig_stage(const Trig<float>& b, const float* __restrict__ d,
+__device__ __forceinline__ void trig_stage(const Consts<float>&, const Trig<float>& b, const float* __restrict__ d,
                                            const float* __restrict__ ang, Trig<float>& t) {
     if (fmaxf(fmaxf(fabsf(d[0]), fabsf(d[1])), fabsf(d[2])) > 0.125f) {
         trig_full<float>(ang, t);
@@ -244,21 +294,22 @@ __device__ __forceinline__ void trig_stage(const Trig<float>& b, const float* __
 }
 // fp64: same idea with two more Taylor terms and a tighter bound (|d| <= 1/32: truncation < 1e-19 relative); the
 // result differs from a full evaluation by ~2 ulp, 6 orders of magnitude inside the 1e-10 parity budget.
-__device__ __forceinline__ void rotate_sc(double s, double c, double d, double* so, double* co) {
+__device__ __forceinline__ void rotate_sc(const double* __restrict__ K, double s, double c, double d, double* so,
+                                          double* co) {
     double z = d * d;
-    double sd = fma(d * z, fma(z, fma(z, -1.9841269841269841e-4, 8.3333333333333333e-3), -1.6666666666666667e-1), d);
-    double cd = fma(z, fma(z, fma(z, fma(z, 2.4801587301587302e-5, -1.3888888888888889e-3), 4.1666666666666667e-2), -0.5), 1.0);
+    double sd = fma(d * z, fma(z, fma(z, K[2], K[1]), K[0]), d);
+    double cd = fma(z, fma(z, fma(z, fma(z, K[6], K[5]), K[4]), K[3]), 1.0);
     *so = fma(s, cd, c * sd);
     *co = fma(c, cd, -(s * sd));
 }
-__device__ __forceinline__ void trig_stage(const Trig<double>& b, const double* __restrict__ d,
+__device__ __forceinline__ void trig_stage(const Consts<double>& c, const Trig<double>& b, const double* __restrict__ d,
                                            const double* __restrict__ ang, Trig<double>& t) {
     if (fmax(fmax(fabs(d[0]), fabs(d[1])), fabs(d[2])) > 0.03125) {
-        trig_full<double>(ang, t);
+        trig_full<double>(c, ang, t);
     } else {
-        rotate_sc(b.sphi, b.cphi, d[0], &t.sphi, &t.cphi);
-        rotate_sc(b.sth, b.cth, d[1], &t.sth, &t.cth);
-        rotate_sc(b.spsi, b.cpsi, d[2], &t.spsi, &t.cpsi);
+        rotate_sc(c.rot, b.sphi, b.cphi, d[0], &t.sphi, &t.cphi);
+        rotate_sc(c.rot, b.sth, b.cth, d[1], &t.sth, &t.cth);
+        rotate_sc(c.rot, b.spsi, b.cpsi, d[2], &t.spsi, &t.cpsi);
     }
 }
 
@@ -500,19 +551,34 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
     }
 }
 
+template <typename T, class P>
+__device__ __forceinline__ P params_at(const P& p, const Consts<T>& cz) {
+    if constexpr (std::is_same<P, ParamsConst<T>>::value) {
+        P q;
+        q.kp = cz.kp;
+        return q;
+    } else {
+        return p;
+    }
+}
+
 // AS: element stride of the RK4 accumulator: 1 = registers; otherwise `acc_sm` points at this thread's column of a
 // shared-memory array [NX][AS] (fp64 build: frees 24 registers so that 14 warps fit an SM without spilling).
+// zk: the caller's step counter (any uniform value < 2^30): the fp64 build re-bases the constant block by
+// (zk + stage) >> 30 = 0 so that constant loads stay next to their uses (see rebase()).
 template <typename T, int MODEL, int INTEG, bool LAG1, int LS, bool LAGW, int AS, class P, class LP, class AP>
-__device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x, LP lag,
-                                               const T* __restrict__ u, AP acc_sm) {
+__device__ __forceinline__ void integrate_step(const Consts<T>& c_, const P& p_, T* __restrict__ x, LP lag,
+                                               const T* __restrict__ u, AP acc_sm, int zk = 0) {
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NL = LAG1 ? 6 : 1;  // continuous auxiliary states integrated with x
+    const Consts<T>& c = rebase<T>(c_, zk >> 30);
+    const P p = params_at<T, P>(p_, c);
     const T dt = c.dt;
     T Fu[ModelDim<MODEL>::NU];
     if constexpr (MODEL == MODEL_THRUSTER8) {
         T F[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(u[i]);
+        for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(c, u[i]);
         if constexpr (LAGW) {
             allocate_wrench<T>(c, F, Fu);
         } else {
@@ -530,7 +596,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
     T k[NX], kl[NL];
     constexpr bool EULER_ANGLES = !ModelDim<MODEL>::QUAT;
     Trig<T> tr0;
-    if constexpr (EULER_ANGLES) trig_full<T>(x + 3, tr0);
+    if constexpr (EULER_ANGLES) trig_full<T>(c, x + 3, tr0);
     if constexpr (INTEG == INTEG_EULER) {
         model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, tr0, lag, Fu, k, kl);
 #pragma unroll
@@ -552,6 +618,8 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         // unrolled step does not fit the 32 KB instruction cache), 3 unrolls it completely
 #pragma unroll kStageUnroll
         for (int s = 1; s <= 3; ++s) {
+            const Consts<T>& cs = rebase<T>(c_, (zk + s) >> 30);
+            const P ps = params_at<T, P>(p_, cs);
             const T w = (s == 1) ? T(1) : T(2);   // weight of the stage just evaluated
             const T h = (s == 3) ? dt : hdt;      // offset of the next stage
 #pragma unroll
@@ -569,10 +637,10 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
             if constexpr (EULER_ANGLES) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) dang[i] = h * k[3 + i];
-                trig_stage(tr0, dang, xs + 3, trs);
+                trig_stage(cs, tr0, dang, xs + 3, trs);
             }
-            if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(c, p, s, xs, trs, ls, Fu, k, kl);
-            else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, s, xs, trs, lag, Fu, k, kl);
+            if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(cs, ps, s, xs, trs, ls, Fu, k, kl);
+            else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(cs, ps, s, xs, trs, lag, Fu, k, kl);
         }
         const T dt6 = dt * T(1.0 / 6.0);
 #pragma unroll
@@ -582,7 +650,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
             for (int i = 0; i < 6; ++i) lag[i] += dt6 * (accl[i] + kl[i]);
         }
     }
-    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LS, LAGW, LP>(c, lag, Fu);
+    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LS, LAGW, LP>(rebase<T>(c_, (zk + 4) >> 30), lag, Fu);
     if constexpr (ModelDim<MODEL>::QUAT) quat_renorm<T>(x + 3);
 }
 

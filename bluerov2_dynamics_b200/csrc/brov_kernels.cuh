@@ -37,6 +37,9 @@ constexpr int RED9_BLOCK = 256;
 #ifndef BROV_F64_PREFETCH
 #define BROV_F64_PREFETCH 1
 #endif
+#ifndef BROV_F64_CONST_SMEM
+#define BROV_F64_CONST_SMEM 1
+#endif
 #ifndef BROV_F32_MAXREG
 #define BROV_F32_MAXREG 128
 #endif
@@ -221,7 +224,10 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
         __shared__ int s_item;
         if (tid == 0) s_item = atomicAdd(a.ticket, 1);
         __syncthreads();
-        const int item = s_item;
+        // the ticket is the same for every thread of the block; passing it through a warp reduction lets the compiler see
+        // that (REDUX writes a uniform register), so slice bounds, the step loop and the re-based constant loads of the
+        // fp64 build all run on the uniform datapath
+        const int item = __reduce_max_sync(0xffffffffu, s_item);
         slice = item / a.nvblocks;
         vb = item - slice * a.nvblocks;
         const int per = (a.steps + a.quanta - 1) / a.quanta;
@@ -240,6 +246,18 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const bool live = gi < a.n;
     const long long i = live ? gi : (long long)a.n - 1;  // dead lanes shadow the last vehicle, never store
 
+    // fp64: the constant block is staged into shared memory and read from there (BROV_F64_CONST_SMEM): sm_100 feeds
+    // FP instructions from uniform registers, and the ~130 64-bit constants of a step do not fit them (see rebase())
+    constexpr bool CSM = sizeof(T) == 8 && BROV_F64_CONST_SMEM;
+    __shared__ __align__(16) unsigned char cs_raw[CSM ? sizeof(Consts<T>) : 16];
+    if constexpr (CSM) {
+        const T* src = reinterpret_cast<const T*>(&a.c);
+        T* dst = reinterpret_cast<T*>(cs_raw);
+        for (int j = tid; j < (int)(sizeof(Consts<T>) / sizeof(T)); j += BLOCK) dst[j] = src[j];
+        __syncthreads();
+    }
+    const Consts<T>& cc = CSM ? *reinterpret_cast<const Consts<T>*>(cs_raw) : a.c;
+
     // shared memory: [per-vehicle coefficient table][lag state (fp64)][snapshot tiles]
     typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type p;
     if constexpr (PV) {
@@ -249,7 +267,7 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
         p.pitch = BLOCK;
         smem += KP_COUNT * BLOCK;
     } else {
-        p.kp = a.c.kp;
+        p.kp = cc.kp;
     }
     // shared-memory residents are accessed through volatile pointers: without it the compiler promotes them back
     // into registers for the whole step, which is exactly what the placement is meant to avoid
@@ -299,7 +317,10 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const int n_valid = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem)) * NX;
 
     constexpr bool PREFETCH = Prefetch<T>::V;  // next step's inputs ride in registers across the step
-    for (int k = 0; k < nsteps; ++k) {
+    // uniform counter feeding rebase(): derived from kernel arguments only, so that it lives in a uniform register and
+    // the re-based constant loads become LDCU.64 c[0][UR + off] (a per-thread register index would make them LDC)
+    int zc = a.stride & 1;
+    for (int k = 0; k < nsteps; ++k, zc += 8) {
         T un[NU];
         if constexpr (PREFETCH) {
             const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
@@ -309,7 +330,7 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
             if (stream) load_u<T, NU, true>(cur, uvec, u); else load_u<T, NU, false>(cur, uvec, u);
         }
 
-        integrate_step<T, MODEL, INTEG, LAG1, LS, LAGW, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm);
+        integrate_step<T, MODEL, INTEG, LAG1, LS, LAGW, AS, decltype(p), LP, AP>(cc, p, x, lag, u, acc_sm, zc);
 
         if (--countdown == 0) {
             countdown = a.stride;
@@ -487,10 +508,11 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     // window k may run j steps while row k + j exists
     long long room = (long long)a.rows - 1 - kr;
     const int nsteps = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
-    for (int j = 0; j < nsteps; ++j) {
+    int zc = a.nH & 1;   // uniform counter for rebase(), see rollout_kernel
+    for (int j = 0; j < nsteps; ++j, zc += 8) {
         T u[NU];
         load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
-        integrate_step<T, MODEL, INTEG, false, LS, true, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm);
+        integrate_step<T, MODEL, INTEG, false, LS, true, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm, zc);
 #pragma unroll
         for (int h = 0; h < MAX_H; ++h) {
             if (h < a.nH && j + 1 == a.H[h]) {

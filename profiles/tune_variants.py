@@ -4,8 +4,10 @@ import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "U1_stage_loop": ["BROV_STAGE_UNROLL=1"],
-    "U3_stage_unrolled": ["BROV_STAGE_UNROLL=3"],
+    "param_consts": ["BROV_F64_CONST_SMEM=0"],
+    "rebase_param_consts_LDC": ["BROV_F64_REBASE=1", "BROV_F64_CONST_SMEM=0"],
+    "rebase_smem_consts_LDS": ["BROV_F64_REBASE=1"],
+    "smem_consts_b64_r168": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=168", "BROV_F64_REBASE=1"],
 }
 VDIR = os.path.join(ROOT, "bluerov2_dynamics_b200", "variants")
 

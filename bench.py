@@ -33,6 +33,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "rk4_vehicle_steps_per_s"
 UNIT = "vehicle-steps/s"

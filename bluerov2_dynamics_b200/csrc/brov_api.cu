@@ -288,6 +288,31 @@ static int make_consts(brov_engine* e, double dt, int nsub, Consts<T>* c) {
             c->lagB[a] = (T)(double)sb;
         }
     }
+    // operand pairs of the packed-FP32 step (PK_* layout of brov_device_f32x2.cuh)
+    {
+        T* pk = c->pk;
+        auto splat = [&](int pair, T v) { pk[2 * pair] = v; pk[2 * pair + 1] = v; };
+        for (int i = 0; i < 5; ++i) splat(PK_POLY + i, c->poly[i]);
+        for (int j = 0; j < 4; ++j) {
+            for (int b = 0; b < 3; ++b) splat(PK_LAGG + 4 * j + b, c->lagG[j][b]);
+            splat(PK_LAGG + 4 * j + 3, c->lagH[j]);
+        }
+        for (int k = 0; k < 3; ++k) {
+            for (int b = 0; b < 3; ++b) splat(PK_LAGA + 4 * k + b, c->lagA[k][b]);
+            splat(PK_LAGA + 4 * k + 3, c->lagB[k]);
+        }
+        for (int i = 0; i < 6; ++i) {
+            pk[2 * PK_DL + i] = c->kp[KP_DL + i];
+            pk[2 * PK_DQ + i] = c->kp[KP_DQ + i];
+            pk[2 * PK_MINV + i] = c->kp[KP_MINV + i];
+        }
+        const double rot[6] = {8.3333333e-3, -1.6666667e-1, -1.3888889e-3, 4.1666667e-2, -0.5, 1.0};
+        for (int i = 0; i < 6; ++i) splat(PK_ROT + i, (T)rot[i]);
+        splat(PK_RK + 0, (T)0.5 * c->dt);
+        splat(PK_RK + 1, c->dt);
+        splat(PK_RK + 2, c->dt * (T)(1.0 / 6.0));
+        splat(PK_RK + 3, (T)2);
+    }
     return BROV_OK;
 }
 

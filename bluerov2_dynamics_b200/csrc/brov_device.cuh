@@ -89,6 +89,8 @@ template <typename T> struct Consts {
     T poly[5];     // -140.3, 389.9, -404.1, 176.0, 8.9
     T sc[16];      // see kSinCos64
     T rot[8];      // sin: -1/6, 1/120, -1/5040 ; cos: -1/2, 1/24, -1/720, 1/40320 ; pad
+    // operand pairs of the packed-FP32 step (brov_device_f32x2.cuh, PK_* layout); 8-byte aligned by construction
+    T pk[104];
     int has_current;
     int use_lag1;
 };
@@ -551,6 +553,13 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
     }
 }
 
+}  // namespace brov
+#ifndef BROV_F32_PACKED
+#define BROV_F32_PACKED 1
+#endif
+#include "brov_device_f32x2.cuh"
+namespace brov {
+
 template <typename T, class P>
 __device__ __forceinline__ P params_at(const P& p, const Consts<T>& cz) {
     if constexpr (std::is_same<P, ParamsConst<T>>::value) {
@@ -571,6 +580,12 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c_, const P& p_,
                                                const T* __restrict__ u, AP acc_sm, int zk = 0) {
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NL = LAG1 ? 6 : 1;  // continuous auxiliary states integrated with x
+    if constexpr (BROV_F32_PACKED && std::is_same<T, float>::value && MODEL == MODEL_THRUSTER8 && INTEG == INTEG_RK4 &&
+                  !LAG1 && LAGW && LS == 1 && AS == 1 && std::is_same<P, ParamsConst<float>>::value &&
+                  std::is_same<LP, float*>::value) {
+        integrate_step_packed(c_, x, lag, u);
+        return;
+    }
     const Consts<T>& c = rebase<T>(c_, zk >> 30);
     const P p = params_at<T, P>(p_, c);
     const T dt = c.dt;

@@ -4,10 +4,11 @@ import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "param_consts": ["BROV_F64_CONST_SMEM=0"],
-    "rebase_param_consts_LDC": ["BROV_F64_REBASE=1", "BROV_F64_CONST_SMEM=0"],
-    "rebase_smem_consts_LDS": ["BROV_F64_REBASE=1"],
-    "smem_consts_b64_r168": ["BROV_F64_BLOCK=64", "BROV_F64_MAXREG=168", "BROV_F64_REBASE=1"],
+    "f32_packed_ffma2": ["BROV_F32_PACKED=1"],
+    "f64_acc_smem_r168": ["BROV_F64_ACC_SMEM=1", "BROV_F64_MAXREG=168"],
+    "f64_acc_lag_smem_r168": ["BROV_F64_ACC_SMEM=1", "BROV_F64_LAG_SMEM=1", "BROV_F64_MAXREG=168"],
+    "f64_acc_smem_b64_r192": ["BROV_F64_ACC_SMEM=1", "BROV_F64_BLOCK=64", "BROV_F64_MAXREG=192"],
+    "f64_param_consts": ["BROV_F64_CONST_SMEM=0"],
 }
 VDIR = os.path.join(ROOT, "bluerov2_dynamics_b200", "variants")
 

@@ -63,7 +63,7 @@ class KoopmanEDMDc:
 
     def _release(self):
         cached = self.__dict__.pop("_h", None)
-        if cached is not None:
+        if cached is not None and L is not None and getattr(L, "lib", None) is not None:
             L.lib.brov_koopman_destroy(cached[1])
 
     def __del__(self):

@@ -17,7 +17,14 @@ static cudaError_t rollout_go(const RolloutArgs<T>& a, cudaStream_t st) {
     if (a.pv) {
         smem += (size_t)KP_COUNT * BLOCK * sizeof(T);
         auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, true, LAGW>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // static + dynamic shared memory beyond 48 KB needs the opt-in (the fp64 coefficient table alone is 36 KB)
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        if (smem + fa.sharedSizeBytes > 48 * 1024) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         kern<<<grid, BLOCK, smem, st>>>(a);
     } else {
         rollout_kernel<T, MODEL, INTEG, LAG1, false, LAGW><<<grid, BLOCK, smem, st>>>(a);

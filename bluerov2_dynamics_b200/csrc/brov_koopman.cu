@@ -25,8 +25,9 @@
 namespace {
 
 constexpr int KB = 128;        // threads per block of the lift kernel
-constexpr int SEB = 512;       // threads per block of the scoring kernel: ONE persistent block per SM (16 warps) so that
-                               // the model is staged into shared memory once per SM, not once per 128 windows
+constexpr int SEB = 512;       // windows per tile of the scoring kernel
+constexpr int SET = 256;       // its threads per block (two windows each): ONE persistent block per SM, so the model is
+                               // staged into shared memory once per SM, not once per tile
 constexpr int NMAX = 16;       // state dimension bound (registers)
 constexpr int RMAX = 8;        // input dimension bound
 
@@ -136,80 +137,104 @@ struct KoopSeArgs {
 };
 
 template <int N, int R>
-__global__ void __launch_bounds__(SEB, 1) koop_se_kernel(const KoopSeArgs a) {
+__global__ void __launch_bounds__(SET, 1) koop_se_kernel(const KoopSeArgs a) {
     extern __shared__ double sm[];
     const int k = a.k, d = N + a.k, H = a.H;
     double* sC = sm;                         // [k][N]
     double* sc2 = sC + (size_t)k * N;        // [k]
     double* sW = sc2 + k;                    // [d][N]  (transposed: the N outputs of one lifted coordinate contiguous)
     double* sG = sW + (size_t)d * N;         // [H][N][R]
-    for (int e = threadIdx.x; e < k * N; e += SEB) sC[e] = a.C[e];
-    for (int e = threadIdx.x; e < k; e += SEB) sc2[e] = a.c2[e];
-    for (int e = threadIdx.x; e < d * N; e += SEB) {
+    for (int e = threadIdx.x; e < k * N; e += SET) sC[e] = a.C[e];
+    for (int e = threadIdx.x; e < k; e += SET) sc2[e] = a.c2[e];
+    for (int e = threadIdx.x; e < d * N; e += SET) {
         const int q = e / N, i = e - q * N;
         sW[e] = a.WH[(size_t)i * d + q];
     }
     if (a.g_in_smem)
-        for (int e = threadIdx.x; e < H * N * R; e += SEB) sG[e] = a.G[e];
+        for (int e = threadIdx.x; e < H * N * R; e += SET) sG[e] = a.G[e];
     __syncthreads();
     const double* G = a.g_in_smem ? sG : a.G;
-    __shared__ double red[SEB / 32];
+    __shared__ double red[SET / 32];
 
+    // Each thread scores TWO windows of the tile (w and w + SET): every centre, decoder column and FIR tap fetched from
+    // shared memory feeds two multiply-adds instead of one.  A thread whose second window falls off the end shadows the
+    // last window and discards the result.
     const long long ntiles = (a.nwin + SEB - 1) / SEB;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long w = tile * SEB + threadIdx.x;
-        double se = 0.0;
-        if (w < a.nwin) {
-            double x[N], acc[N], x2 = 0.0;
+        const long long w0 = tile * SEB + threadIdx.x;
+        const long long w1 = w0 + SET;
+        const bool ok0 = w0 < a.nwin, ok1 = w1 < a.nwin;
+        const long long v0 = ok0 ? w0 : a.nwin - 1, v1 = ok1 ? w1 : a.nwin - 1;
+        double x0[N], x1[N], acc0[N], acc1[N], s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            x0[i] = __ldg(a.X + v0 * N + i);
+            x1[i] = __ldg(a.X + v1 * N + i);
+            s0 = fma(x0[i], x0[i], s0);
+            s1 = fma(x1[i], x1[i], s1);
+            acc0[i] = 0.0;
+            acc1[i] = 0.0;
+        }
+        // linear part of the lift
+#pragma unroll
+        for (int q = 0; q < N; ++q) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                x[i] = __ldg(a.X + w * N + i);
-                x2 = fma(x[i], x[i], x2);
-                acc[i] = 0.0;
-            }
-            // linear part of the lift
-#pragma unroll
-            for (int q = 0; q < N; ++q) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) acc[i] = fma(sW[q * N + i], x[q], acc[i]);
-            }
-            // radial basis functions
-            const double mg = -a.gamma;
-#pragma unroll 2
-            for (int j = 0; j < k; ++j) {
-                double dot = 0.0;
-#pragma unroll
-                for (int i = 0; i < N; ++i) dot = fma(x[i], sC[j * N + i], dot);
-                const double e = exp(mg * (x2 + sc2[j] - 2.0 * dot));
-                const double* wc = sW + (size_t)(N + j) * N;
-#pragma unroll
-                for (int i = 0; i < N; ++i) acc[i] = fma(wc[i], e, acc[i]);
-            }
-            // input FIR: sum_t G_{H-1-t} u_{k+t}; the next row of inputs is in flight while this one is consumed
-            double un[R];
-#pragma unroll
-            for (int c = 0; c < R; ++c) un[c] = __ldg(a.U + w * R + c);
-            for (int t = 0; t < H; ++t) {
-                double u[R];
-#pragma unroll
-                for (int c = 0; c < R; ++c) u[c] = un[c];
-                if (t + 1 < H) {
-#pragma unroll
-                    for (int c = 0; c < R; ++c) un[c] = __ldg(a.U + (w + t + 1) * R + c);
-                }
-                const double* g = G + (size_t)(H - 1 - t) * N * R;
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-#pragma unroll
-                    for (int c = 0; c < R; ++c) acc[i] = fma(g[i * R + c], u[c], acc[i]);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double e = __ldg(a.X + (w + H) * N + i) - acc[i];
-                se = fma(e, e, se);
+                const double wv = sW[q * N + i];
+                acc0[i] = fma(wv, x0[q], acc0[i]);
+                acc1[i] = fma(wv, x1[q], acc1[i]);
             }
         }
+        // radial basis functions
+        const double mg = -a.gamma;
+#pragma unroll 2
+        for (int j = 0; j < k; ++j) {
+            double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double cv = sC[j * N + i];
+                d0 = fma(x0[i], cv, d0);
+                d1 = fma(x1[i], cv, d1);
+            }
+            const double cj = sc2[j];
+            const double e0 = exp(mg * (s0 + cj - 2.0 * d0));
+            const double e1 = exp(mg * (s1 + cj - 2.0 * d1));
+            const double* wc = sW + (size_t)(N + j) * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double wv = wc[i];
+                acc0[i] = fma(wv, e0, acc0[i]);
+                acc1[i] = fma(wv, e1, acc1[i]);
+            }
+        }
+        // input FIR: sum_t G_{H-1-t} u_{k+t}
+        for (int t = 0; t < H; ++t) {
+            double u0[R], u1[R];
+#pragma unroll
+            for (int c = 0; c < R; ++c) {
+                u0[c] = __ldg(a.U + (v0 + t) * R + c);
+                u1[c] = __ldg(a.U + (v1 + t) * R + c);
+            }
+            const double* g = G + (size_t)(H - 1 - t) * N * R;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+#pragma unroll
+                for (int c = 0; c < R; ++c) {
+                    const double gv = g[i * R + c];
+                    acc0[i] = fma(gv, u0[c], acc0[i]);
+                    acc1[i] = fma(gv, u1[c], acc1[i]);
+                }
+            }
+        }
+        double se0 = 0.0, se1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double e0 = __ldg(a.X + (v0 + H) * N + i) - acc0[i];
+            const double e1 = __ldg(a.X + (v1 + H) * N + i) - acc1[i];
+            se0 = fma(e0, e0, se0);
+            se1 = fma(e1, e1, se1);
+        }
+        double se = (ok0 ? se0 : 0.0) + (ok1 ? se1 : 0.0);
         // block reduction, fixed order; one partial per tile keeps the final sum independent of the grid size
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) se += __shfl_down_sync(0xffffffffu, se, off);
@@ -218,7 +243,7 @@ __global__ void __launch_bounds__(SEB, 1) koop_se_kernel(const KoopSeArgs a) {
         if (threadIdx.x == 0) {
             double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < SEB / 32; ++q) s += red[q];
+            for (int q = 0; q < SET / 32; ++q) s += red[q];
             a.partial[tile] = s;
         }
         __syncthreads();
@@ -386,7 +411,7 @@ static int koop_se_launch(brov_koopman* h, const KoopSeArgs& a0, size_t smem_bas
     if (smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_se_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (a.nwin + SEB - 1) / SEB;
     const unsigned grid = (unsigned)(ntiles < h->num_sms ? ntiles : h->num_sms);
-    koop_se_kernel<N, R><<<grid, SEB, smem, st>>>(a);
+    koop_se_kernel<N, R><<<grid, SET, smem, st>>>(a);
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;
 }

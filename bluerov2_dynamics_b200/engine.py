@@ -93,7 +93,7 @@ class Engine:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and L is not None and getattr(L, "lib", None) is not None:   # module globals may be gone at shutdown
             L.lib.brov_destroy(h)
             self._h = None
 

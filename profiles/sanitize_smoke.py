@@ -1,0 +1,78 @@
+"""Small-size pass over every kernel of libbrov.so, meant to run under compute-sanitizer on a B200:
+
+    compute-sanitizer --tool memcheck  python profiles/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python profiles/sanitize_smoke.py
+
+Sizes are ragged on purpose (partial warps / blocks, odd snapshot counts, unaligned quaternion rows)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bluerov2_dynamics_b200 as B  # noqa: E402
+from bluerov2_dynamics_b200 import pinc as P  # noqa: E402
+from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc  # noqa: E402
+
+rng = np.random.default_rng(0)
+dt = 0.02
+for dtype in ("f64", "f32"):
+    for model, nx, nu in (("thruster8", 12, 8), ("wrench12", 12, 6), ("quat13", 13, 6), ("di12_u8", 12, 8),
+                          ("di12_u6", 12, 6), ("diq13_u6", 13, 6)):
+        e = B.Engine(model, dtype)
+        if e.is_di:
+            e.set_di_gains(rng.normal(0, 0.1, (nu, 3)), rng.normal(0, 0.1, (nu, 3)))
+        n, T = 333, 23
+        x0 = rng.uniform(-0.5, 0.5, (n, nx))
+        if nx == 13:
+            x0[:, 3:7] /= np.linalg.norm(x0[:, 3:7], axis=1, keepdims=True)
+        U = rng.uniform(-0.5, 0.5, (T, n, nu))
+        for integ in ("rk4", "euler"):
+            r = e.rollout(x0, U, dt=dt, integrator=integ, stride=5)
+            r2 = e.rollout(x0, U[:, 0], dt=dt, integrator=integ, stride=0, u_layout="shared")
+            e.rollout(x0, U, dt=dt, integrator=integ, stride=3, time_slices=3)
+            assert torch.isfinite(r.xT).all() and torch.isfinite(r2.xT).all()
+        e.rhs(x0, U[0])
+        X = r.traj[:, 0, :].contiguous()
+        e.multistep_rmse(np.tile(X.cpu().numpy(), (8, 1)), np.tile(U[:X.shape[0], 0], (8, 1)), [1, 3, 7], dt=dt)
+        if model == "thruster8":
+            e.thruster_wrench(U[0], lag=torch.zeros((n, 24), device="cuda", dtype=e.tdtype), dt=dt)
+            e.multistep_rmse(np.tile(X.cpu().numpy(), (60, 1)), np.tile(U[:X.shape[0], 0], (60, 1)), 5, dt=dt,
+                             lag_mode="carry")
+            xh, uh = x0.astype(e.ndtype), U.astype(e.ndtype)
+            e.rollout_host(np.ascontiguousarray(xh), np.ascontiguousarray(uh), dt=dt, stride=4, chunk_steps=8)
+        if model in ("wrench12", "quat13"):
+            ph = np.tile(B.default_physical(), (n, 1)) * rng.uniform(0.9, 1.1, (n, 1))
+            e.set_vehicle_physical(ph)
+            e.rollout(x0, U, dt=dt, stride=2)
+            e.set_vehicle_physical(None)
+            e.set_wrench_lag1(True, 0.1)
+            e.rollout(x0, U, dt=dt, stride=0)
+    x9 = torch.randn((1001, 9), device="cuda", dtype=torch.float32 if dtype == "f32" else torch.float64)
+    B.reduced9_rhs(x9, torch.randn((1001, 4), device="cuda", dtype=x9.dtype))
+
+# Koopman
+n, r, k, T = 12, 8, 37, 300
+K = KoopmanEDMDc(state_dim=n, input_dim=r, n_rbfs=k, gamma=0.5)
+K.centers_ = rng.uniform(-1, 1, (k, n))
+K.A_ = 0.9 * np.linalg.qr(rng.standard_normal((n + k, n + k)))[0]
+K.B_ = 0.1 * rng.standard_normal((n + k, r))
+Xk, Uk = np.cumsum(0.05 * rng.standard_normal((T, n)), axis=0), rng.uniform(-1, 1, (T, r))
+for H in (1, 7, 150):
+    assert np.isfinite(K.multistep_rmse(Xk, Uk, H))
+K.simulate(Xk[0], Uk[:77])
+K.simulate_batch(Xk[:5], Uk[:33])
+K._lift(Xk[:19])
+
+# PINc (reference checkpoint from the golden file)
+cg = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_cmp.npz"))
+g = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+M = P.PincModel({kk[len("pinc_sd_"):]: cg[kk] for kk in cg.files if kk.startswith("pinc_sd_")})
+M(cg["pinc_dataset_zin"][:77])
+M.rollout(np.tile(g["rmse_X12"][:3], (150, 1))[:401], np.tile(g["rmse_U8"][:17, None, :], (1, 401, 1)), dt, stride=4)
+P.multistep_rmse_endpoint_pinc(g["rmse_X12"], g["rmse_U8"], [1, 10, 100], dt, M, lag_mode="reset")
+P.multistep_rmse_endpoint_pinc(g["rmse_X12"], g["rmse_U8"], 10, dt, M)
+torch.cuda.synchronize()
+print("sanitize_smoke OK")

@@ -75,6 +75,8 @@ __device__ __forceinline__ float softplus_f(float x) {
 }
 
 // activation + LayerNorm of the 64 pre-activations (32 packed pairs), result to the thread's shared-memory column
+// (element stride PBLK)
+template <int PBLK>
 __device__ __forceinline__ void act_norm_store(const u64* a2, float beta, const float* __restrict__ lnw,
                                                const float* __restrict__ lnb, float* __restrict__ hcol) {
     const float ib = 1.0f / (beta + 1e-12f);
@@ -100,71 +102,103 @@ __device__ __forceinline__ void act_norm_store(const u64* a2, float beta, const 
     for (int q = 0; q < HID / 4; ++q) {
         const float4 g = *reinterpret_cast<const float4*>(lnw + 4 * q);
         const float4 b = *reinterpret_cast<const float4*>(lnb + 4 * q);
-        hcol[(4 * q + 0) * PB] = fmaf(a[4 * q + 0] * rstd, g.x, b.x);
-        hcol[(4 * q + 1) * PB] = fmaf(a[4 * q + 1] * rstd, g.y, b.y);
-        hcol[(4 * q + 2) * PB] = fmaf(a[4 * q + 2] * rstd, g.z, b.z);
-        hcol[(4 * q + 3) * PB] = fmaf(a[4 * q + 3] * rstd, g.w, b.w);
+        hcol[(4 * q + 0) * PBLK] = fmaf(a[4 * q + 0] * rstd, g.x, b.x);
+        hcol[(4 * q + 1) * PBLK] = fmaf(a[4 * q + 1] * rstd, g.y, b.y);
+        hcol[(4 * q + 2) * PBLK] = fmaf(a[4 * q + 2] * rstd, g.z, b.z);
+        hcol[(4 * q + 3) * PBLK] = fmaf(a[4 * q + 3] * rstd, g.w, b.w);
     }
 }
 
-template <int NPAIR>
-__device__ __forceinline__ void bias_init(u64* a2, const float* __restrict__ b) {
+template <int NPAIR, int NWIN>
+__device__ __forceinline__ void bias_init(u64 (&a2)[NWIN][NPAIR], const float* __restrict__ b) {
 #pragma unroll
     for (int q = 0; q < NPAIR / 2; ++q) {
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(b + 4 * q);
-        a2[2 * q] = v.x;
-        a2[2 * q + 1] = v.y;
+#pragma unroll
+        for (int w = 0; w < NWIN; ++w) {
+            a2[w][2 * q] = v.x;
+            a2[w][2 * q + 1] = v.y;
+        }
     }
 }
 
-// a2 += wrow * x for NPAIR packed pairs (wrow: 2 NPAIR contiguous floats in shared memory, 128-bit broadcast loads)
-template <int NPAIR>
-__device__ __forceinline__ void axpy(u64* a2, const float* __restrict__ wrow, float x) {
-    const u64 xx = pack2(x, x);
+// a2[w] += wrow * x[w] for NPAIR packed pairs and NWIN windows: every 128-bit broadcast load of four weights from
+// shared memory feeds 2 NWIN packed FMAs (the shared-memory pipe is the bottleneck at one window per thread:
+// 90 % of its peak in profiles/r01h_compare_raw.csv)
+template <int NPAIR, int NWIN>
+__device__ __forceinline__ void axpy(u64 (&a2)[NWIN][NPAIR], const float* __restrict__ wrow, const float (&x)[NWIN]) {
+    u64 xx[NWIN];
+#pragma unroll
+    for (int w = 0; w < NWIN; ++w) xx[w] = pack2(x[w], x[w]);
 #pragma unroll
     for (int q = 0; q < NPAIR / 2; ++q) {
-        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(wrow + 4 * q);
-        fma2(a2[2 * q], w.x, xx);
-        fma2(a2[2 * q + 1], w.y, xx);
+        const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(wrow + 4 * q);
+#pragma unroll
+        for (int w = 0; w < NWIN; ++w) {
+            fma2(a2[w][2 * q], wv.x, xx[w]);
+            fma2(a2[w][2 * q + 1], wv.y, xx[w]);
+        }
     }
 }
 
-// PINcNet.forward: z[14] -> x9_next[9].  sw: weights in shared memory, hcol: this thread's activation column.
-__device__ __forceinline__ void pinc_forward(const float* __restrict__ sw, const float* beta, float* __restrict__ hcol,
-                                             const float* __restrict__ z, float* __restrict__ xn) {
-    u64 a2[HID / 2];
-    bias_init<HID / 2>(a2, sw + OFF_B0);
+// PINcNet.forward for NWIN windows of one thread: z[w][14] -> xn[w][9].  sw: weights in shared memory; hbase: this
+// thread's activation columns, element (window w, unit j) at hbase[(w * HID + j) * PBLK].
+template <int NWIN, int PBLK>
+__device__ __forceinline__ void pinc_forward(const float* __restrict__ sw, const float* beta, float* __restrict__ hbase,
+                                             const float (&z)[NWIN][NIN], float (&xn)[NWIN][9]) {
+    u64 a2[NWIN][HID / 2];
+    float xin[NWIN];
+    bias_init<HID / 2, NWIN>(a2, sw + OFF_B0);
 #pragma unroll
-    for (int i = 0; i < NIN; ++i) axpy<HID / 2>(a2, sw + OFF_W0 + i * HID, z[i]);
-    act_norm_store(a2, beta[0], sw + OFF_B0 + HID, sw + OFF_B0 + 2 * HID, hcol);
+    for (int i = 0; i < NIN; ++i) {
+#pragma unroll
+        for (int w = 0; w < NWIN; ++w) xin[w] = z[w][i];
+        axpy<HID / 2, NWIN>(a2, sw + OFF_W0 + i * HID, xin);
+    }
+#pragma unroll
+    for (int w = 0; w < NWIN; ++w)
+        act_norm_store<PBLK>(a2[w], beta[0], sw + OFF_B0 + HID, sw + OFF_B0 + 2 * HID, hbase + w * HID * PBLK);
 #pragma unroll 1
     for (int l = 0; l < 3; ++l) {
         const float* L = sw + OFF_L1 + l * LSTRIDE;
-        bias_init<HID / 2>(a2, L + HID * HID);
+        bias_init<HID / 2, NWIN>(a2, L + HID * HID);
 #pragma unroll 4
-        for (int i = 0; i < HID; ++i) axpy<HID / 2>(a2, L + i * HID, hcol[i * PB]);
-        act_norm_store(a2, beta[l + 1], L + HID * HID + HID, L + HID * HID + 2 * HID, hcol);
+        for (int i = 0; i < HID; ++i) {
+#pragma unroll
+            for (int w = 0; w < NWIN; ++w) xin[w] = hbase[(w * HID + i) * PBLK];
+            axpy<HID / 2, NWIN>(a2, L + i * HID, xin);
+        }
+#pragma unroll
+        for (int w = 0; w < NWIN; ++w)
+            act_norm_store<PBLK>(a2[w], beta[l + 1], L + HID * HID + HID, L + HID * HID + 2 * HID, hbase + w * HID * PBLK);
     }
-    u64 d2[6];
-    bias_init<6>(d2, sw + OFF_B4);
+    u64 d2[NWIN][6];
+    bias_init<6, NWIN>(d2, sw + OFF_B4);
 #pragma unroll 4
-    for (int i = 0; i < HID; ++i) axpy<6>(d2, sw + OFF_W4 + i * 12, hcol[i * PB]);
-    float dx[12];
+    for (int i = 0; i < HID; ++i) {
 #pragma unroll
-    for (int q = 0; q < 6; ++q) unpack2(d2[q], dx[2 * q], dx[2 * q + 1]);
-    // residual update; body-frame (dx, dy) rotated by the CURRENT yaw; (cos, sin) re-normalised (:639-673)
-    const float c = z[3], s = z[4];
-    float base[9];
+        for (int w = 0; w < NWIN; ++w) xin[w] = hbase[(w * HID + i) * PBLK];
+        axpy<6, NWIN>(d2, sw + OFF_W4 + i * 12, xin);
+    }
 #pragma unroll
-    for (int j = 0; j < 9; ++j) base[j] = z[j] + dx[j];
-    xn[0] = (c * dx[0] - s * dx[1]) + z[0];
-    xn[1] = (s * dx[0] + c * dx[1]) + z[1];
-    xn[2] = base[2];
-    const float nrm = fmaxf(sqrtf(base[3] * base[3] + base[4] * base[4]), 1e-6f);
-    xn[3] = base[3] / nrm;
-    xn[4] = base[4] / nrm;
+    for (int w = 0; w < NWIN; ++w) {
+        float dx[12];
 #pragma unroll
-    for (int j = 5; j < 9; ++j) xn[j] = base[j];
+        for (int q = 0; q < 6; ++q) unpack2(d2[w][q], dx[2 * q], dx[2 * q + 1]);
+        // residual update; body-frame (dx, dy) rotated by the CURRENT yaw; (cos, sin) re-normalised (:639-673)
+        const float c = z[w][3], s = z[w][4];
+        float base[9];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) base[j] = z[w][j] + dx[j];
+        xn[w][0] = (c * dx[0] - s * dx[1]) + z[w][0];
+        xn[w][1] = (s * dx[0] + c * dx[1]) + z[w][1];
+        xn[w][2] = base[2];
+        const float nrm = fmaxf(sqrtf(base[3] * base[3] + base[4] * base[4]), 1e-6f);
+        xn[w][3] = base[3] / nrm;
+        xn[w][4] = base[4] / nrm;
+#pragma unroll
+        for (int j = 5; j < 9; ++j) xn[w][j] = base[j];
+    }
 }
 
 __device__ __forceinline__ double poly_t200(double V) {
@@ -213,10 +247,6 @@ __device__ __forceinline__ void project4(const ThrMap& m, const double* __restri
         }
 }
 
-__device__ __forceinline__ void load_weights(const float* __restrict__ g, float* __restrict__ sw) {
-    for (int e = threadIdx.x * 4; e < NW; e += PB * 4)
-        *reinterpret_cast<float4*>(sw + e) = *reinterpret_cast<const float4*>(g + e);
-}
 
 __device__ __forceinline__ void x12_to_9(const double* __restrict__ x12, float* __restrict__ x9) {
     double s, c;
@@ -235,23 +265,31 @@ __device__ __forceinline__ void x9_to_12(const float* __restrict__ x9, double* _
 // ---------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
-constexpr size_t SMEM_BYTES = (size_t)(NW + HID * PB) * sizeof(float);
+constexpr int PB2 = 256;   // threads per block of the rollout / scoring kernels, TWO windows per thread
+constexpr int NWIN = 2;
+constexpr size_t SMEM_BYTES = (size_t)(NW + HID * PB) * sizeof(float);                 // forward kernel
+constexpr size_t SMEM_BYTES2 = (size_t)(NW + NWIN * HID * PB2) * sizeof(float);        // 190 KB: one block per SM
+
+__device__ __forceinline__ void load_weights_n(const float* __restrict__ g, float* __restrict__ sw, int nthreads) {
+    for (int e = threadIdx.x * 4; e < NW; e += nthreads * 4)
+        *reinterpret_cast<float4*>(sw + e) = *reinterpret_cast<const float4*>(g + e);
+}
 
 __global__ void __launch_bounds__(PB, 1) pinc_forward_kernel(PincParams p, const float* __restrict__ Zin,
                                                           float* __restrict__ out, long long n) {
     extern __shared__ __align__(16) float smf[];
     float* sw = smf;
     float* hcol = smf + NW + threadIdx.x;
-    load_weights(p.w, sw);
+    load_weights_n(p.w, sw, PB);
     __syncthreads();
     const long long i = (long long)blockIdx.x * PB + threadIdx.x;
     if (i >= n) return;
-    float z[NIN], xn[9];
+    float z[1][NIN], xn[1][9];
 #pragma unroll
-    for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
-    pinc_forward(sw, p.beta, hcol, z, xn);
+    for (int j = 0; j < NIN; ++j) z[0][j] = Zin[i * NIN + j];
+    pinc_forward<1, PB>(sw, p.beta, hcol, z, xn);
 #pragma unroll
-    for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
+    for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[0][j];
 }
 
 struct PincRollArgs {
@@ -268,55 +306,75 @@ struct PincRollArgs {
     int steps, stride;
 };
 
-__global__ void __launch_bounds__(PB, 1) pinc_rollout_kernel(const __grid_constant__ PincRollArgs a) {
+// Thread t of block b rolls windows i0 = b * 2 PB2 + t and i1 = i0 + PB2.  A thread whose second (or both) window
+// falls off the end shadows the last window and stores nothing for it.
+__global__ void __launch_bounds__(PB2, 1) pinc_rollout_kernel(const __grid_constant__ PincRollArgs a) {
     extern __shared__ __align__(16) float smf[];
     float* sw = smf;
-    float* hcol = smf + NW + threadIdx.x;
-    load_weights(a.p.w, sw);
+    float* hbase = smf + NW + threadIdx.x;
+    load_weights_n(a.p.w, sw, PB2);
     __syncthreads();
-    const long long i = (long long)blockIdx.x * PB + threadIdx.x;
-    if (i >= a.n) return;
-    double x12[12];
+    long long idx[NWIN];
+    bool ok[NWIN];
+    float z[NWIN][NIN], xn[NWIN][9];
+    double Z[NWIN][12];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) x12[j] = a.x0[i * 12 + j];
-    float z[NIN], xn[9];
-    x12_to_9(x12, z);
-    z[13] = (float)a.m.dt;
-    double Z[12];
-    if (a.lag_in) {
-        double l24[24];
+    for (int w = 0; w < NWIN; ++w) {
+        const long long i = (long long)blockIdx.x * (NWIN * PB2) + w * PB2 + threadIdx.x;
+        ok[w] = i < a.n;
+        idx[w] = ok[w] ? i : a.n - 1;
+        double x12[12];
 #pragma unroll
-        for (int j = 0; j < 24; ++j) l24[j] = a.lag_in[i * 24 + j];
-        project4(a.m, l24, Z);
-    } else {
+        for (int j = 0; j < 12; ++j) x12[j] = a.x0[idx[w] * 12 + j];
+        x12_to_9(x12, z[w]);
+        z[w][13] = (float)a.m.dt;
+        if (a.lag_in) {
+            double l24[24];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
-    }
-    const double* up = a.U + i * a.u_stride_n;
-    for (int k = 0; k < a.steps; ++k) {
-        double u8[8], u4[4];
+            for (int j = 0; j < 24; ++j) l24[j] = a.lag_in[idx[w] * 24 + j];
+            project4(a.m, l24, Z[w]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) u8[j] = __ldg(up + (long long)k * a.u_stride_t + j);
-        thruster_map4(a.m, u8, Z, u4);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) z[9 + j] = (float)u4[j];
-        pinc_forward(sw, a.p.beta, hcol, z, xn);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) z[j] = xn[j];
-        if (a.traj && (k + 1) % a.stride == 0) {
-            x9_to_12(xn, x12);
-            double* dst = a.traj + (((long long)(k + 1) / a.stride - 1) * a.n + i) * 12;
-#pragma unroll
-            for (int j = 0; j < 12; ++j) dst[j] = x12[j];
+            for (int j = 0; j < 12; ++j) Z[w][j] = 0.0;
         }
     }
-    if (a.x9T) {
+    for (int k = 0; k < a.steps; ++k) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) a.x9T[i * 9 + j] = z[j];
+        for (int w = 0; w < NWIN; ++w) {
+            double u8[8], u4[4];
+            const double* up = a.U + idx[w] * a.u_stride_n + (long long)k * a.u_stride_t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u8[j] = __ldg(up + j);
+            thruster_map4(a.m, u8, Z[w], u4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[w][9 + j] = (float)u4[j];
+        }
+        pinc_forward<NWIN, PB2>(sw, a.p.beta, hbase, z, xn);
+        const bool snap = a.traj && (k + 1) % a.stride == 0;
+#pragma unroll
+        for (int w = 0; w < NWIN; ++w) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) z[w][j] = xn[w][j];
+            if (snap && ok[w]) {
+                double x12[12];
+                x9_to_12(xn[w], x12);
+                double* dst = a.traj + (((long long)(k + 1) / a.stride - 1) * a.n + idx[w]) * 12;
+#pragma unroll
+                for (int j = 0; j < 12; ++j) dst[j] = x12[j];
+            }
+        }
     }
-    if (a.lag_out) {
 #pragma unroll
-        for (int j = 0; j < 12; ++j) a.lag_out[i * 12 + j] = Z[j];
+    for (int w = 0; w < NWIN; ++w) {
+        if (!ok[w]) continue;
+        if (a.x9T) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) a.x9T[idx[w] * 9 + j] = z[w][j];
+        }
+        if (a.lag_out) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) a.lag_out[idx[w] * 12 + j] = Z[w][j];
+        }
     }
 }
 
@@ -334,31 +392,37 @@ struct PincSeArgs {
     const double* carry_lag0;  // [8][3] lag state of the thruster-map object before window 0, or nullptr (zeros)
 };
 
-__global__ void __launch_bounds__(PB, 1) pinc_se_kernel(const __grid_constant__ PincSeArgs a) {
+__global__ void __launch_bounds__(PB2, 1) pinc_se_kernel(const __grid_constant__ PincSeArgs a) {
     extern __shared__ __align__(16) float smf[];
     float* sw = smf;
-    float* hcol = smf + NW + threadIdx.x;
-    __shared__ double red[PB / 32][BROV_MAX_H];
-    load_weights(a.p.w, sw);
+    float* hbase = smf + NW + threadIdx.x;
+    __shared__ double red[PB2 / 32][BROV_MAX_H];
+    load_weights_n(a.p.w, sw, PB2);
     __syncthreads();
-    const long long gk = (long long)blockIdx.x * PB + threadIdx.x;
-    const bool live = gk < a.nwin;
-    const long long k = live ? gk : 0;
-    const long long kr = k + (a.win0 - a.row0);
     double se[BROV_MAX_H];
 #pragma unroll
     for (int h = 0; h < BROV_MAX_H; ++h) se[h] = 0.0;
-    if (live) {
+    const int hmax = a.H[a.nH - 1];
+    long long kr[NWIN];
+    int nst[NWIN];
+    float z[NWIN][NIN], xn[NWIN][9];
+    double Z[NWIN][12];
+#pragma unroll
+    for (int w = 0; w < NWIN; ++w) {
+        const long long gk = (long long)blockIdx.x * (NWIN * PB2) + w * PB2 + threadIdx.x;
+        const bool live = gk < a.nwin;
+        const long long k = live ? gk : a.nwin - 1;     // dead slots shadow the last window and score nothing
+        kr[w] = k + (a.win0 - a.row0);
+        const long long room = a.rows - 1 - kr[w];
+        nst[w] = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
         double x12[12];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr * 12 + j);
-        float z[NIN], xn[9];
-        x12_to_9(x12, z);
-        z[13] = (float)a.m.dt;
-        double Z[12];
+        for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr[w] * 12 + j);
+        x12_to_9(x12, z[w]);
+        z[w][13] = (float)a.m.dt;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
-        if (a.carry_steps > 0) {
+        for (int j = 0; j < 12; ++j) Z[w][j] = 0.0;
+        if (a.carry_steps > 0 && live) {
             // the reference's single thruster-map object has seen windows 0..k-1, H steps each: replay the tail of that
             // history that is distinguishable from zero in floating point
             const long long H0 = a.H[0];
@@ -368,42 +432,49 @@ __global__ void __launch_bounds__(PB, 1) pinc_se_kernel(const __grid_constant__ 
                 double l24[24];
 #pragma unroll
                 for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
-                project4(a.m, l24, Z);
+                project4(a.m, l24, Z[w]);
             }
             for (long long s = total - m; s < total; ++s) {
-                const long long w = s / H0;
-                const long long row = w + (s - w * H0) - a.row0;
+                const long long ww = s / H0;
+                const long long row = ww + (s - ww * H0) - a.row0;
                 double u8[8], u4[4];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
-                thruster_map4(a.m, u8, Z, u4);
+                thruster_map4(a.m, u8, Z[w], u4);
             }
         }
-        const int hmax = a.H[a.nH - 1];
-        const long long room = a.rows - 1 - kr;
-        const int nsteps = (int)(room < hmax ? (room < 0 ? 0 : room) : hmax);
-        for (int j = 0; j < nsteps; ++j) {
+    }
+    const int nmax = nst[0] > nst[1] ? nst[0] : nst[1];
+    for (int j = 0; j < nmax; ++j) {
+#pragma unroll
+        for (int w = 0; w < NWIN; ++w) {
+            // a window that has run out of rows keeps stepping on its last valid input row; its results are ignored
+            const long long row = kr[w] + (j < nst[w] ? j : (nst[w] > 0 ? nst[w] - 1 : 0));
             double u8[8], u4[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) u8[q] = __ldg(a.U + (kr + j) * 8 + q);
-            thruster_map4(a.m, u8, Z, u4);
+            for (int q = 0; q < 8; ++q) u8[q] = __ldg(a.U + row * 8 + q);
+            thruster_map4(a.m, u8, Z[w], u4);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) z[9 + q] = (float)u4[q];
-            pinc_forward(sw, a.p.beta, hcol, z, xn);
+            for (int q = 0; q < 4; ++q) z[w][9 + q] = (float)u4[q];
+        }
+        pinc_forward<NWIN, PB2>(sw, a.p.beta, hbase, z, xn);
 #pragma unroll
-            for (int q = 0; q < 9; ++q) z[q] = xn[q];
+        for (int w = 0; w < NWIN; ++w) {
+#pragma unroll
+            for (int q = 0; q < 9; ++q) z[w][q] = xn[w][q];
 #pragma unroll
             for (int h = 0; h < BROV_MAX_H; ++h) {
-                if (h < a.nH && j + 1 == a.H[h]) {
-                    x9_to_12(xn, x12);
-                    const double* tgt = a.X + (kr + j + 1) * 12;
+                if (h < a.nH && j + 1 == a.H[h] && j < nst[w]) {
+                    double x12[12];
+                    x9_to_12(xn[w], x12);
+                    const double* tgt = a.X + (kr[w] + j + 1) * 12;
                     double s = 0.0;
 #pragma unroll
                     for (int q = 0; q < 12; ++q) {
                         const double e = x12[q] - __ldg(tgt + q);
                         s += e * e;
                     }
-                    se[h] = s;
+                    se[h] += s;
                 }
             }
         }
@@ -420,7 +491,7 @@ __global__ void __launch_bounds__(PB, 1) pinc_se_kernel(const __grid_constant__ 
     if (threadIdx.x < BROV_MAX_H) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < PB / 32; ++w) v += red[w][threadIdx.x];
+        for (int w = 0; w < PB2 / 32; ++w) v += red[w][threadIdx.x];
         a.partial[(long long)blockIdx.x * BROV_MAX_H + threadIdx.x] = v;
     }
 }
@@ -461,8 +532,8 @@ struct brov_pinc {
 static int pinc_attrs(brov_pinc* h) {
     if (h->attr_set) return BROV_OK;
     BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES2));
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES2));
     h->attr_set = true;
     return BROV_OK;
 }
@@ -580,7 +651,7 @@ extern "C" int brov_pinc_rollout(brov_pinc_t* h, const brov_pinc_rollout_desc* d
     a.lag_in = (const double*)d->lag_in_dev; a.lag_out = (double*)d->lag_out_dev;
     a.traj = (double*)d->traj_dev; a.x9T = (float*)d->x9T_dev;
     a.n = d->n; a.steps = (int)d->steps; a.stride = d->traj_dev ? (int)d->stride : 1;
-    pinc_rollout_kernel<<<(unsigned)((d->n + PB - 1) / PB), PB, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+    pinc_rollout_kernel<<<(unsigned)((d->n + NWIN * PB2 - 1) / (NWIN * PB2)), PB2, SMEM_BYTES2, (cudaStream_t)stream>>>(a);
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;
 }
@@ -604,7 +675,7 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     }
     int rc = pinc_attrs(h);
     if (rc) return rc;
-    const size_t nblocks = (size_t)((d->n_windows + PB - 1) / PB);
+    const size_t nblocks = (size_t)((d->n_windows + NWIN * PB2 - 1) / (NWIN * PB2));
     if (nblocks * BROV_MAX_H > h->cap_partial) {
         cudaFree(h->partial);
         h->partial = nullptr; h->cap_partial = 0;
@@ -620,7 +691,7 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     for (int q = 0; q < BROV_MAX_H; ++q) a.H[q] = q < d->n_horizons ? d->horizons[q] : 0x7fffffff;
     a.carry_steps = d->carry_steps; a.win0 = d->window0; a.row0 = d->row0;
     a.carry_lag0 = (const double*)d->carry_lag0_dev;
-    pinc_se_kernel<<<(unsigned)nblocks, PB, SMEM_BYTES, st>>>(a);
+    pinc_se_kernel<<<(unsigned)nblocks, PB2, SMEM_BYTES2, st>>>(a);
     pinc_finish_kernel<<<1, 256, 0, st>>>(h->partial, (int)nblocks, d->se_out_dev);
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;

@@ -36,6 +36,9 @@ def test_every_declared_symbol_is_exported(L):
     assert C.sizeof(L.RolloutDesc) == 4 + 4 + 8 * 14 + 4 + 4 + 4 + 4
     assert C.sizeof(L.SeDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 * 4 + 4 + 8 * 4 + 4 + 4 + 8 + 8
     assert C.sizeof(L.RolloutHostDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 + 8 * 5 + 4 + 4
+    assert C.sizeof(L.PincWeights) == 4 * 4 + 5 * 8 + 5 * 8 + 4 * 4 + 4 * 8 + 4 * 8
+    assert C.sizeof(L.PincRolloutDesc) == 4 + 4 + 8 * 11
+    assert C.sizeof(L.PincSeDesc) == 4 + 4 + 4 * 4 + 8 * 5 + 4 + 4 + 8 * 3
 
 
 def test_constants_match_reference(L, golden):
@@ -68,6 +71,15 @@ def test_errors_are_reported_without_a_gpu(L):
     h = C.c_void_p()
     rc = L.lib.brov_create(7, L.F64, 0, C.byref(h))  # unknown model: rejected before any CUDA call
     assert rc == -1 and not h.value
+    # comparison models: argument errors are reported before any CUDA call, too
+    z = np.zeros(4)
+    assert L.lib.brov_koopman_create(0, 99, 8, 4, 1.0, L.dptr(z), L.dptr(z), L.dptr(z), C.byref(h)) == -1
+    assert b"unsupported dimensions" in L.lib.brov_last_error() and not h.value
+    w = L.PincWeights()
+    w.struct_size = 1
+    assert L.lib.brov_pinc_create(0, C.byref(w), C.byref(h)) == -1 and b"size mismatch" in L.lib.brov_last_error()
+    w.struct_size, w.n_hidden_layers, w.hidden = C.sizeof(L.PincWeights), 3, 64
+    assert L.lib.brov_pinc_create(0, C.byref(w), C.byref(h)) == -4 and not h.value
 
 
 def test_product_has_no_cpu_fallback_and_never_imports_the_oracle():

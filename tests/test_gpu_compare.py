@@ -233,3 +233,55 @@ def test_csv_series_through_the_evaluators(tmp_path, golden):
     X, U, dt = load_dataset(p, verbose=False)
     got = multistep_rmse_endpoint_physics(X, U, [1, 10, 100], dt, integrator="rk4", lag_mode="carry")
     assert np.allclose(got, golden["rmse_thr_rk4_carry"], rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_koopman_long_horizon_taps_from_global_memory():
+    """d = 512 with H = 170: the FIR taps (170 x 12 x 8 doubles) no longer fit shared memory beside the model and are
+    read from global memory; ragged window count (not a multiple of the 512-window tile)."""
+    from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc
+    rng = np.random.default_rng(3)
+    n, r, k, T = 12, 8, 500, 170 + 777
+    C = rng.uniform(-1, 1, (k, n))
+    X = np.cumsum(0.02 * rng.standard_normal((T, n)), axis=0)
+    U = rng.uniform(-1, 1, (T, r))
+    A = 0.97 * np.linalg.qr(rng.standard_normal((n + k, n + k)))[0]
+    Bm = 0.05 * rng.standard_normal((n + k, r))
+    K = KoopmanEDMDc(state_dim=n, input_dim=r, n_rbfs=k, gamma=0.9)
+    K.centers_, K.A_, K.B_ = C, A, Bm
+    assert np.isclose(K.multistep_rmse(X, U, 170), CN.koop_multistep_se(X, U, 170, C, 0.9, A, Bm)[2], rtol=TOL64)
+    # a second, shorter horizon after the long one reuses the cached decoder rows
+    assert np.isclose(K.multistep_rmse(X, U, 3), CN.koop_multistep_se(X, U, 3, C, 0.9, A, Bm)[2], rtol=TOL64)
+
+
+def test_pinc_ragged_windows_and_tail(PM, golden, cg):
+    """Window counts that are not a multiple of the 512-window tile, a single window, and horizons longer than what is
+    left of the series for the last windows (those horizons simply do not count them)."""
+    pinc, model = PM
+    dt = float(cg["cmp_dt"])
+    L = CN.pinc_weights(cg)
+    X12, U8 = golden["rmse_X12"], golden["rmse_U8"]
+    Xr, Ur = np.tile(X12, (5, 1))[:613], np.tile(U8, (5, 1))[:613]
+    for hs in ([1], [2, 5, 40]):
+        ref = CN.pinc_multistep_se(Xr, Ur, hs, dt, L, "reset")
+        se, cnt = model.multistep_se(Xr, Ur, hs, dt, "reset")
+        se = se.cpu().numpy()
+        assert cnt == [ref[h][1] for h in hs]
+        assert np.allclose(se[:len(hs)], [ref[h][0] for h in hs], rtol=2e-4)
+    traj, x9, _ = model.rollout(X12[7:8], U8[:9], dt)
+    snaps, x9r, _ = CN.pinc_rollout(X12[7:8], U8[:9], dt, L)
+    assert normwise(cpu(traj), snaps) < TOL32 and normwise(cpu(x9), x9r) < TOL32
+    with pytest.raises(ValueError):
+        model.multistep_se(Xr, Ur, [5, 2], dt)
+
+
+def test_di_shard_invariance(B):
+    """Rows of a sub-ensemble equal the same rows of the whole ensemble, bit for bit (no cross-vehicle coupling)."""
+    rng = np.random.default_rng(2)
+    n, T = 1500, 40
+    x0, U = rng.uniform(-1, 1, (n, 12)), rng.uniform(-1, 1, (T, n, 8))
+    e = B.Engine("di12_u8", "f64")
+    e.set_di_gains(rng.normal(0, 0.3, (8, 3)), rng.normal(0, 0.3, (8, 3)))
+    whole = cpu(e.rollout(x0, U, dt=0.02).xT)
+    part = cpu(e.rollout(x0[700:1333], np.ascontiguousarray(U[:, 700:1333]), dt=0.02).xT)
+    assert np.array_equal(whole[700:1333], part)

@@ -32,35 +32,46 @@ constexpr int NMAX = 16;       // state dimension bound (registers)
 constexpr int RMAX = 8;        // input dimension bound
 
 // ---------------------------------------------------------------------------------------------------------------
-// W_{t+1} = W_t A  (n x d times d x d).  Block: 32 output columns x 8 slices of the inner dimension.
+// W_{t+1} = W_t A  (n x d times d x d), one launch per power: a sequential chain, so each launch has to be short.
+// Block: 16 output columns x 16 slices of the inner dimension; W_t is staged in shared memory, the A loads of a
+// thread are independent and unrolled so that several are in flight; fixed-order reduction over the slices.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) koop_power_kernel(const double* __restrict__ W, const double* __restrict__ A,
-                                                         double* __restrict__ Wn, int n, int d) {
-    __shared__ double part[8][NMAX][33];
-    const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cx;
+constexpr int PW_COLS = 16, PW_SLICES = 16;
+__global__ void __launch_bounds__(PW_COLS * PW_SLICES) koop_power_kernel(const double* __restrict__ W,
+                                                                          const double* __restrict__ A,
+                                                                          double* __restrict__ Wn, int n, int d) {
+    extern __shared__ double pw_sm[];
+    double* sWt = pw_sm;                                   // [d][NMAX]: W_t transposed, zero-padded rows n..NMAX
+    double* part = pw_sm + (size_t)d * NMAX;               // [PW_SLICES][NMAX][PW_COLS + 1]
+    const int cx = threadIdx.x % PW_COLS, sl = threadIdx.x / PW_COLS;
+    const int c = blockIdx.x * PW_COLS + cx;
+    for (int e = threadIdx.x; e < d * NMAX; e += PW_COLS * PW_SLICES) {
+        const int q = e / NMAX, i = e - q * NMAX;
+        sWt[e] = i < n ? W[(size_t)i * d + q] : 0.0;
+    }
+    __syncthreads();
     double acc[NMAX];
 #pragma unroll
     for (int i = 0; i < NMAX; ++i) acc[i] = 0.0;
     if (c < d) {
-        for (int q = sl; q < d; q += 8) {
-            const double a = A[(size_t)q * d + c];
+#pragma unroll 4
+        for (int q = sl; q < d; q += PW_SLICES) {
+            const double a = __ldg(A + (size_t)q * d + c);
+            const double* w = sWt + (size_t)q * NMAX;
 #pragma unroll
-            for (int i = 0; i < NMAX; ++i)
-                if (i < n) acc[i] = fma(W[(size_t)i * d + q], a, acc[i]);
+            for (int i = 0; i < NMAX; ++i) acc[i] = fma(w[i], a, acc[i]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) part[sl][i][cx] = acc[i];
+    for (int i = 0; i < NMAX; ++i) part[(sl * NMAX + i) * (PW_COLS + 1) + cx] = acc[i];
     __syncthreads();
-    // fixed-order sum over the 8 slices
-    for (int e = threadIdx.x; e < n * 32; e += 256) {
-        const int i = e >> 5, x = e & 31;
-        const int cc = blockIdx.x * 32 + x;
+    for (int e = threadIdx.x; e < n * PW_COLS; e += PW_COLS * PW_SLICES) {
+        const int i = e / PW_COLS, x = e - i * PW_COLS;
+        const int cc = blockIdx.x * PW_COLS + x;
         if (cc >= d) continue;
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s += part[k][i][x];
+        for (int k = 0; k < PW_SLICES; ++k) s += part[(k * NMAX + i) * (PW_COLS + 1) + x];
         Wn[(size_t)i * d + cc] = s;
     }
 }
@@ -334,8 +345,11 @@ static int koop_prepare(brov_koopman* h, int T, cudaStream_t st) {
     }
     if (T <= h->have_t) return BROV_OK;
     const int j0 = h->have_t;
+    const size_t pw_smem = ((size_t)d * NMAX + (size_t)PW_SLICES * NMAX * (PW_COLS + 1)) * sizeof(double);
+    if (pw_smem > 200 * 1024) return brov::fail_msg(BROV_EUNSUPPORTED, "model with d = %d does not fit shared memory", d);
+    if (pw_smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_power_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem));
     for (int t = j0; t < T; ++t)
-        koop_power_kernel<<<(d + 31) / 32, 256, 0, st>>>(h->W + (size_t)t * n * d, h->A, h->W + (size_t)(t + 1) * n * d, n, d);
+        koop_power_kernel<<<(d + PW_COLS - 1) / PW_COLS, PW_COLS * PW_SLICES, pw_smem, st>>>(h->W + (size_t)t * n * d, h->A, h->W + (size_t)(t + 1) * n * d, n, d);
     koop_gain_kernel<<<T - j0, 128, 0, st>>>(h->W, h->B, h->G, n, r, d, j0);
     BROV_CUDA_TRY(cudaGetLastError());
     h->have_t = T;

@@ -594,3 +594,54 @@ def test_monte_carlo_with_trajectory_fp64_shared_memory_opt_in(B, golden):
     e.set_vehicle_physical(ph)
     r = e.rollout(x0, U, dt=DT, stride=4)
     assert normwise(cpu(r.xT), xT) < TOL64 and normwise(cpu(r.traj), snaps) < TOL64
+
+
+# ------------------------------------------------------------------------------------ full size, EVERY vehicle checked
+def _c_oracle():
+    import os
+    import subprocess
+    from conftest import ROOT
+    from oracle import c_oracle
+    if not c_oracle.available():
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s"], check=True)
+    return c_oracle
+
+
+def test_full_size_cfg2_every_vehicle_against_c_oracle(B):
+    """BASELINE config 2 at full width: all 65,536 fp64 vehicles x 1000 RK4 steps (10 chunks of 100 steps carrying
+    state and per-thruster lag) against the plain-C oracle, which runs the reference's sequential lag steps on every
+    host core.  1e-10 normwise on the final state AND on the hidden lag state of every vehicle."""
+    CO = _c_oracle()
+    n, chunks, T = 65536, 10, 100
+    g = torch.Generator(device="cuda").manual_seed(11)
+    e = B.Engine("thruster8", "f64")
+    x = torch.zeros((n, 12), device="cuda", dtype=torch.float64)
+    x[:, :3] = torch.rand((n, 3), device="cuda", dtype=torch.float64, generator=g) * 4 - 2
+    x[:, 3:5] = torch.rand((n, 2), device="cuda", dtype=torch.float64, generator=g) * 0.2 - 0.1
+    x[:, 5] = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 6 - 3
+    lag = torch.zeros((n, 24), device="cuda", dtype=torch.float64)
+    xo, lo = cpu(x), np.zeros((n, 8, 3))
+    worst = 0.0
+    for c in range(chunks):
+        U = (torch.rand((T, n, 8), device="cuda", dtype=torch.float64, generator=g) * 0.8 - 0.4).contiguous()
+        r = e.rollout(x, U, dt=DT, lag0=lag, step0=c * T)
+        x, lag = r.xT, r.lag
+        _, xo, lo = CO.rollout("thruster8", "rk4", DT, xo, cpu(U), lag0=lo)
+        worst = max(worst, normwise(cpu(x), xo), normwise(cpu(lag).reshape(n, 8, 3), lo))
+    assert worst < TOL64, worst
+
+
+def test_full_size_cfg3_every_vehicle_against_c_oracle(B):
+    """BASELINE config 3 at full width: all 1,048,576 fp32 vehicles x 100 RK4 steps with stride-10 snapshots against
+    the float64 C oracle fed the same (float32-representable) inputs; 1e-4 normwise on every snapshot."""
+    CO = _c_oracle()
+    n, T = 1 << 20, 100
+    g = torch.Generator(device="cuda").manual_seed(12)
+    e = B.Engine("thruster8", "f32")
+    x0 = torch.zeros((n, 12), device="cuda", dtype=torch.float32)
+    x0[:, :3] = torch.rand((n, 3), device="cuda", generator=g) * 4 - 2
+    x0[:, 5] = torch.rand(n, device="cuda", generator=g) * 6 - 3
+    U = (torch.rand((T, n, 8), device="cuda", generator=g) * 0.8 - 0.4).contiguous()
+    r = e.rollout(x0, U, dt=DT, stride=10)
+    snaps, xT, _ = CO.rollout("thruster8", "rk4", DT, cpu(x0), cpu(U), stride=10)
+    assert normwise(cpu(r.traj), snaps) < TOL32 and normwise(cpu(r.xT), xT) < TOL32

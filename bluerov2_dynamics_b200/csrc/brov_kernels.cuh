@@ -20,8 +20,13 @@ namespace brov {
 constexpr int MAX_H = 4;          // horizons per se launch
 constexpr int RHS_BLOCK = 128;
 constexpr int RED9_BLOCK = 256;
-// Threads per block of the per-vehicle kernels.  fp32: 128.  fp64: 64 — with <= 144 registers seven such blocks fit
-// an SM (14 warps) and BASELINE's 65,536-vehicle ensemble is exactly ONE wave of 1024 blocks on 148 x 7 slots.
+// Compile-time tuning knobs of the per-vehicle kernels; the defaults are the fastest configuration measured on B200
+// (profiles/tune_variants.py builds the alternatives, profiles/r01e / r01g *.json hold their timings):
+//   fp32: 128-thread blocks, 128-register cap (16 warps per SM), everything in registers;
+//   fp64: 128-thread blocks, no register cap (~248 registers, 8 warps per SM), lag state and RK4 accumulator in
+//         registers, next-step inputs prefetched, constant block in shared memory.  The smaller-footprint layouts
+//         (64-thread blocks, 144-192 register caps, lag / accumulator in shared memory) buy more warps but lose to
+//         spills and shared-memory round trips (0.59-0.71 ms against 0.48 ms per 65,536 x 100 steps).
 #ifndef BROV_F64_BLOCK
 #define BROV_F64_BLOCK 128
 #endif
@@ -46,9 +51,9 @@ constexpr int RED9_BLOCK = 256;
 template <typename T> struct BlockOf { static constexpr int N = sizeof(T) == 8 ? BROV_F64_BLOCK : 128; };
 template <typename T> struct MaxReg { static constexpr int N = sizeof(T) == 8 ? BROV_F64_MAXREG : BROV_F32_MAXREG; };
 template <typename T> struct Prefetch { static constexpr bool V = sizeof(T) == 8 ? (BROV_F64_PREFETCH != 0) : true; };
-// fp64 keeps the thruster-lag state in shared memory ([component][thread]); fp32 keeps it in registers.
+// optional fp64 layouts: thruster-lag state in shared memory ([component][thread]) ...
 template <typename T> struct LagInSmem { static constexpr bool V = sizeof(T) == 8 && BROV_F64_LAG_SMEM; };
-// fp64 also keeps the RK4 accumulator in shared memory and does not hold next-step inputs in registers.
+// ... and the RK4 accumulator in shared memory
 template <typename T> struct AccInSmem { static constexpr bool V = sizeof(T) == 8 && BROV_F64_ACC_SMEM; };
 
 template <typename T> struct RolloutArgs {

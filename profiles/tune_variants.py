@@ -4,11 +4,9 @@ import json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "f32_packed_ffma2": ["BROV_F32_PACKED=1"],
-    "f64_acc_smem_r168": ["BROV_F64_ACC_SMEM=1", "BROV_F64_MAXREG=168"],
-    "f64_acc_lag_smem_r168": ["BROV_F64_ACC_SMEM=1", "BROV_F64_LAG_SMEM=1", "BROV_F64_MAXREG=168"],
-    "f64_acc_smem_b64_r192": ["BROV_F64_ACC_SMEM=1", "BROV_F64_BLOCK=64", "BROV_F64_MAXREG=192"],
-    "f64_param_consts": ["BROV_F64_CONST_SMEM=0"],
+    "f32_r96": ["BROV_F32_MAXREG=96"],
+    "f32_r160": ["BROV_F32_MAXREG=160"],
+    "f32_r255": ["BROV_F32_MAXREG=255"],
 }
 VDIR = os.path.join(ROOT, "bluerov2_dynamics_b200", "variants")
 

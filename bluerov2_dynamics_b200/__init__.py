@@ -9,7 +9,7 @@ multi-step endpoint RMSE) behind the reference's own `fossen/` model API:
     from bluerov2_dynamics_b200.fossen.bluerov_torch import bluerov_compute, ssa
     from bluerov2_dynamics_b200.evaluators import simulate_physics, multistep_rmse_endpoint_physics
 
-or `bluerov2_dynamics_b200.install_as_fossen()` to serve `import fossen...` from this package.  Batched entry points
+or `bluerov2_dynamics_b200.install_as_fossen()` to serve `import fossen...` / `import Koopman...` from this package.  Batched entry points
 live on `Engine`.  All compute runs in libbrov.so (hand-written CUDA behind the C ABI of include/brov.h); there is no
 CPU fallback — importing this package without the built library raises.
 """
@@ -40,3 +40,6 @@ def install_as_fossen() -> None:
     sys.modules["fossen"] = pkg
     for sub in ("BlueROV2", "BlueROV2_thrust", "BlueROV2_wrench", "bluerov_torch", "parameters"):
         sys.modules["fossen." + sub] = importlib.import_module(f"{__name__}.fossen.{sub}")
+    # the training scripts also do `from Koopman.koopmanEDMDc import KoopmanEDMDc`
+    sys.modules["Koopman"] = importlib.import_module(__name__ + ".Koopman")
+    sys.modules["Koopman.koopmanEDMDc"] = importlib.import_module(__name__ + ".Koopman.koopmanEDMDc")

@@ -645,3 +645,37 @@ def test_full_size_cfg3_every_vehicle_against_c_oracle(B):
     r = e.rollout(x0, U, dt=DT, stride=10)
     snaps, xT, _ = CO.rollout("thruster8", "rk4", DT, cpu(x0), cpu(U), stride=10)
     assert normwise(cpu(r.traj), snaps) < TOL32 and normwise(cpu(r.xT), xT) < TOL32
+
+
+def test_install_as_fossen_serves_unmodified_reference_imports(golden):
+    """The import lines and the loop of the reference's fossen/test_euler.py, run against the engine in a fresh
+    interpreter: `import fossen...` / `import Koopman...` resolve to the mirrors, and ten stateful Euler steps through
+    `rov.dynamics` land on the reference's trajectory."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = """
+import json, sys
+import numpy as np
+sys.path.insert(0, %r)
+import bluerov2_dynamics_b200 as brov
+brov.install_as_fossen()
+from fossen.BlueROV2 import BlueROV2                      # fossen/test_euler.py:2 (flat import there)
+from fossen.BlueROV2_thrust import BlueROV2 as Wrench12
+from fossen.BlueROV2_wrench import BlueROV2 as Quat13, euler_to_quat
+from fossen.bluerov_torch import bluerov_compute, ssa
+from Koopman.koopmanEDMDc import KoopmanEDMDc
+import fossen.parameters as P
+assert BlueROV2.__module__.startswith("bluerov2_dynamics_b200") and P.m == 11.4
+rov = BlueROV2(dt=0.01)
+x = np.zeros(12); x[2] = 5.0
+u = np.array([0.1, 0.1, 0.1, 0.0, 0.5, 0.5, 0.5, 0.5])
+for _ in range(10):
+    x = x + 0.01 * rov.dynamics(x, u, 0.01)
+print(json.dumps(x.tolist()))
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    x = np.array(json.loads(out.stdout.strip().splitlines()[-1]))
+    assert normwise(x, golden["cfg1_euler_dt001_traj_s10"][1]) < TOL64

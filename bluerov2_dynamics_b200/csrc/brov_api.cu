@@ -79,6 +79,11 @@ struct brov_engine {
     int num_sms;
     int* d_sched;        // [1 + nvblocks] ticket counter + per-vehicle-block progress flags (temporal tiling)
     size_t cap_sched;    // in ints
+    // staging of the host-buffer single-call entry points (brov_rhs_host, brov_thruster_wrench_host)
+    void* call_pinned;   // pinned host buffer
+    void* call_dev;      // device mirror
+    size_t cap_call;     // bytes of each
+    cudaStream_t call_stream;
 };
 
 static const double LAG_AC[9] = {-89.0, -72.33, -26.54, 128.0, 0.0, 0.0, 0.0, 32.0, 0.0};  // fossen/BlueROV2.py:476-478
@@ -333,6 +338,7 @@ extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out
     e->use_lag1 = 0; e->pv = nullptr; e->pv_n = 0;
     e->lag_cache.dt = -1.0;
     e->num_sms = prop.multiProcessorCount; e->d_sched = nullptr; e->cap_sched = 0;
+    e->call_pinned = nullptr; e->call_dev = nullptr; e->cap_call = 0; e->call_stream = nullptr;
     double ph[BROV_NPHYS];
     brov_default_physical(1000.0, ph);
     brov_derive_params(ph, e->kp);
@@ -362,6 +368,9 @@ extern "C" void brov_destroy(brov_engine_t* e) {
     if (!e) return;
     hs_release(e);
     if (e->d_sched) cudaFree(e->d_sched);
+    if (e->call_pinned) cudaFreeHost(e->call_pinned);
+    if (e->call_dev) cudaFree(e->call_dev);
+    if (e->call_stream) cudaStreamDestroy(e->call_stream);
     delete e;
 }
 
@@ -478,6 +487,89 @@ extern "C" int brov_thruster_wrench(brov_engine_t* e, long long n, const void* u
     CUDA_TRY(cudaSetDevice(e->device));
     return e->dtype == BROV_F32 ? thruster_impl<float>(e, n, u, lag, dt, tau, (cudaStream_t)stream)
                                 : thruster_impl<double>(e, n, u, lag, dt, tau, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-buffer single calls: what `rov.dynamics(x, u, dt)` / `rov.compute_thruster_forces(u, dt)` of the model mirrors
+// cost per call is launch latency, so everything travels in ONE pinned staging buffer: [in | out] -> one copy each way
+// ---------------------------------------------------------------------------------------------------------------
+static int call_staging(brov_engine* e, size_t bytes) {
+    if (!e->call_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->call_stream, cudaStreamNonBlocking));
+    if (bytes <= e->cap_call) return BROV_OK;
+    size_t cap = e->cap_call ? e->cap_call : 4096;
+    while (cap < bytes) cap *= 2;
+    if (e->call_pinned) cudaFreeHost(e->call_pinned);
+    if (e->call_dev) cudaFree(e->call_dev);
+    e->call_pinned = nullptr; e->call_dev = nullptr; e->cap_call = 0;
+    CUDA_TRY(cudaHostAlloc(&e->call_pinned, cap, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc(&e->call_dev, cap));
+    e->cap_call = cap;
+    return BROV_OK;
+}
+
+extern "C" int brov_rhs_host(brov_engine_t* e, long long n, const void* x_host, const void* u_host, void* lag_inout_host,
+                             double dt, void* xdot_host) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (n < 0 || n > (1 << 24)) return fail(BROV_EINVAL, "n = %lld out of range for a host-buffer call", n);
+    if (n == 0) return BROV_OK;
+    if (!x_host || !u_host || !xdot_host) return fail(BROV_EINVAL, "x, u and xdot must not be NULL");
+    if (e->model == BROV_THRUSTER8_LAG3 && !(dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0 (it fixes the lag discretisation)");
+    if (e->pv && e->pv_n != n) return fail(BROV_EINVAL, "vehicle table has %lld rows, call has n = %lld", e->pv_n, n);
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t sz = scalar_size(e->dtype);
+    const int NX = model_nx(e->model), NU = model_nu(e->model);
+    const int NL = (e->model == BROV_THRUSTER8_LAG3 && lag_inout_host) ? 24 : 0;
+    const int NXD = NX + (e->use_lag1 ? 6 : 0);
+    const size_t bx = (size_t)n * NX * sz, bu = (size_t)n * NU * sz, bl = (size_t)n * NL * sz, bo = (size_t)n * NXD * sz;
+    // layout: [lag | x | u | xdot]; host->device copies [lag | x | u], device->host copies back [lag] and [xdot]
+    int rc = call_staging(e, bl + bx + bu + bo);
+    if (rc) return rc;
+    char* hp = (char*)e->call_pinned;
+    char* dp = (char*)e->call_dev;
+    if (NL) memcpy(hp, lag_inout_host, bl);
+    memcpy(hp + bl, x_host, bx);
+    memcpy(hp + bl + bx, u_host, bu);
+    cudaStream_t st = e->call_stream;
+    CUDA_TRY(cudaMemcpyAsync(dp, hp, bl + bx + bu, cudaMemcpyHostToDevice, st));
+    rc = e->dtype == BROV_F32 ? rhs_impl<float>(e, n, dp + bl, dp + bl + bx, NL ? dp : nullptr, dt, dp + bl + bx + bu, st)
+                              : rhs_impl<double>(e, n, dp + bl, dp + bl + bx, NL ? dp : nullptr, dt, dp + bl + bx + bu, st);
+    if (rc) return rc;
+    if (NL) CUDA_TRY(cudaMemcpyAsync(hp, dp, bl, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hp + bl + bx + bu, dp + bl + bx + bu, bo, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (NL) memcpy(lag_inout_host, hp, bl);
+    memcpy(xdot_host, hp + bl + bx + bu, bo);
+    return BROV_OK;
+}
+
+extern "C" int brov_thruster_wrench_host(brov_engine_t* e, long long n, const void* u_host, void* lag_inout_host, double dt,
+                                         void* tau_host) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (e->model != BROV_THRUSTER8_LAG3) return fail(BROV_EUNSUPPORTED, "brov_thruster_wrench_host needs a BROV_THRUSTER8_LAG3 engine");
+    if (n < 0 || n > (1 << 24)) return fail(BROV_EINVAL, "n = %lld out of range for a host-buffer call", n);
+    if (n == 0) return BROV_OK;
+    if (!u_host || !tau_host) return fail(BROV_EINVAL, "u and tau must not be NULL");
+    if (!(dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const size_t sz = scalar_size(e->dtype);
+    const size_t bl = lag_inout_host ? (size_t)n * 24 * sz : 0, bu = (size_t)n * 8 * sz, bo = (size_t)n * 6 * sz;
+    int rc = call_staging(e, bl + bu + bo);
+    if (rc) return rc;
+    char* hp = (char*)e->call_pinned;
+    char* dp = (char*)e->call_dev;
+    if (bl) memcpy(hp, lag_inout_host, bl);
+    memcpy(hp + bl, u_host, bu);
+    cudaStream_t st = e->call_stream;
+    CUDA_TRY(cudaMemcpyAsync(dp, hp, bl + bu, cudaMemcpyHostToDevice, st));
+    rc = e->dtype == BROV_F32 ? thruster_impl<float>(e, n, dp + bl, bl ? dp : nullptr, dt, dp + bl + bu, st)
+                              : thruster_impl<double>(e, n, dp + bl, bl ? dp : nullptr, dt, dp + bl + bu, st);
+    if (rc) return rc;
+    if (bl) CUDA_TRY(cudaMemcpyAsync(hp, dp, bl, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hp + bl + bu, dp + bl + bu, bo, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (bl) memcpy(lag_inout_host, hp, bl);
+    memcpy(tau_host, hp + bl + bu, bo);
+    return BROV_OK;
 }
 
 template <typename T>

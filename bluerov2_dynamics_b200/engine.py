@@ -190,6 +190,31 @@ class Engine:
                                                float(dt), out.data_ptr(), self._stream()))
         return out
 
+    def rhs_host(self, x: np.ndarray, u: np.ndarray, lag: Optional[np.ndarray] = None, dt: float = 0.02) -> np.ndarray:
+        """`rhs` with numpy arrays in host memory (engine dtype): one pinned staging copy each way inside the library,
+        no torch tensors — the low-latency path behind the model mirrors' per-call `dynamics()`.  `lag` [N,24]
+        (thruster model) is advanced in place."""
+        x = np.ascontiguousarray(x, dtype=self.ndtype).reshape(-1, self.nx)
+        u = np.ascontiguousarray(u, dtype=self.ndtype).reshape(-1, self.nu)
+        if u.shape[0] != x.shape[0]:
+            raise ValueError("x and u must have the same number of rows")
+        if lag is not None and (lag.dtype != self.ndtype or not lag.flags.c_contiguous or lag.size != x.shape[0] * 24):
+            raise ValueError(f"lag must be a C-contiguous {np.dtype(self.ndtype)} array with 24 values per row")
+        out = np.empty((x.shape[0], self.nx + (6 if self._lag1 else 0)), dtype=self.ndtype)
+        L.check(L.lib.brov_rhs_host(self._h, x.shape[0], x.ctypes.data, u.ctypes.data,
+                                    lag.ctypes.data if lag is not None else None, float(dt), out.ctypes.data))
+        return out
+
+    def thruster_wrench_host(self, u: np.ndarray, lag: Optional[np.ndarray] = None, dt: float = 0.02) -> np.ndarray:
+        """`thruster_wrench` with numpy arrays in host memory; `lag` [N,24] is advanced in place."""
+        u = np.ascontiguousarray(u, dtype=self.ndtype).reshape(-1, 8)
+        if lag is not None and (lag.dtype != self.ndtype or not lag.flags.c_contiguous or lag.size != u.shape[0] * 24):
+            raise ValueError(f"lag must be a C-contiguous {np.dtype(self.ndtype)} array with 24 values per row")
+        out = np.empty((u.shape[0], 6), dtype=self.ndtype)
+        L.check(L.lib.brov_thruster_wrench_host(self._h, u.shape[0], u.ctypes.data,
+                                                lag.ctypes.data if lag is not None else None, float(dt), out.ctypes.data))
+        return out
+
     def rollout(self, x0, U, dt: float = 0.02, integrator: str = "rk4", lag0=None, stride: int = 0,
                 u_layout: str = "auto", step0: int = 0, xT_out: Optional[torch.Tensor] = None,
                 lag_out: Optional[torch.Tensor] = None, traj_out: Optional[torch.Tensor] = None,

@@ -85,19 +85,24 @@ class BlueROV2(FossenModelBase):
             l._prepare(dt)
             l._x = vals[i].copy()
 
+    def _lag_host(self):
+        return np.concatenate([np.asarray(l._x, float).reshape(3) for l in self.thruster_lags]).reshape(1, 24)
+
+    def _store_lag_host(self, lag, dt):
+        for i, l in enumerate(self.thruster_lags):
+            l._prepare(dt)
+            l._x = lag[0, 3 * i:3 * i + 3].copy()
+
     def compute_thruster_forces(self, u_thrust, dt):
-        eng = self.engine("f64")
-        lag = self._lag_tensor(eng)
-        u = np.asarray(u_thrust, dtype=float).reshape(1, 8)
-        tau = eng.thruster_wrench(u, lag=lag, dt=dt)[0].cpu().numpy()
-        self._store_lag(lag, dt)
+        lag = self._lag_host()
+        tau = self.engine("f64").thruster_wrench_host(np.asarray(u_thrust, dtype=float).reshape(1, 8), lag=lag, dt=dt)[0]
+        self._store_lag_host(lag, dt)
         return tau
 
     def dynamics(self, x, u_thrust, dt):
-        eng = self.engine("f64")
-        lag = self._lag_tensor(eng)
+        lag = self._lag_host()
         xd = self._dynamics_one(np.asarray(x, dtype=float)[:12], np.asarray(u_thrust, dtype=float)[:8], 12, 8, dt, lag=lag)
-        self._store_lag(lag, dt)
+        self._store_lag_host(lag, dt)
         return xd
 
     def _n_tether_states(self):

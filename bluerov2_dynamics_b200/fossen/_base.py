@@ -77,8 +77,6 @@ class FossenModelBase:
         return eng
 
     def _dynamics_one(self, x, u, nx, nu, dt, lag=None):
-        eng = self.engine("f64")
-        xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64).reshape(1, nx))
-        ut = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float64).reshape(1, nu))
-        out = eng.rhs(xt, ut, lag=lag, dt=dt)
-        return out[0].cpu().numpy()
+        """One dynamics() call through the host-buffer entry point (brov_rhs_host); `lag` is a numpy [1,24] array that
+        is advanced in place."""
+        return self.engine("f64").rhs_host(x, u, lag=lag, dt=dt)[0]

@@ -122,6 +122,14 @@ int brov_rhs(brov_engine_t* e, long long n, const void* x_dev, const void* u_dev
 int brov_thruster_wrench(brov_engine_t* e, long long n, const void* u_dev, void* lag_inout_dev, double dt,
                          void* tau_dev, void* stream);
 
+/* The same two calls with every array in HOST memory (engine scalar type): what a model object's `dynamics()` /
+ * `compute_thruster_forces()` costs per call is launch latency, so inputs and outputs travel in one pinned staging
+ * buffer each way and the call returns after the results have landed.  lag_inout_host as above ([n][8][3] or NULL). */
+int brov_rhs_host(brov_engine_t* e, long long n, const void* x_host, const void* u_host, void* lag_inout_host,
+                  double dt, void* xdot_host);
+int brov_thruster_wrench_host(brov_engine_t* e, long long n, const void* u_host, void* lag_inout_host, double dt,
+                              void* tau_host);
+
 /* Open-loop rollout — `simulate_physics(x0, U_seq, dt, rov)` for n vehicles at once
  * (RK4: training/train_tank_brov2_rk4.py:375-396; Euler: training/train_tank_brov2_full_comparison.py:453-466,
  * quaternion re-normalisation per step: training/train_tank_brov2_wrench_quat.py:262-263).

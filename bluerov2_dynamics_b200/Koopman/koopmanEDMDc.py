@@ -44,7 +44,11 @@ class KoopmanEDMDc:
             A, B = np.zeros((d, d)), np.zeros((d, self.input_dim))
         else:
             A, B = self.A_, self.B_
-        key = (id(self.centers_), id(A) if self.A_ is not None else 0, id(B) if self.B_ is not None else 0,
+        # identity + a cheap content fingerprint: assigning new arrays OR editing them in place re-uploads the model
+        def fp(a):
+            a = np.asarray(a)
+            return (id(a), a.shape, float(a.sum()), float(np.abs(a).sum()))
+        key = (fp(self.centers_), fp(A) if self.A_ is not None else 0, fp(B) if self.B_ is not None else 0,
                float(self.gamma), torch.cuda.current_device())
         cached = self.__dict__.get("_h")
         if cached is not None and cached[0] == key:

@@ -285,3 +285,14 @@ def test_di_shard_invariance(B):
     whole = cpu(e.rollout(x0, U, dt=0.02).xT)
     part = cpu(e.rollout(x0[700:1333], np.ascontiguousarray(U[:, 700:1333]), dt=0.02).xT)
     assert np.array_equal(whole[700:1333], part)
+
+
+def test_koopman_model_edited_in_place_is_reuploaded(cg):
+    from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc
+    K = KoopmanEDMDc(state_dim=12, input_dim=8, n_rbfs=116, gamma=float(cg["koop_gamma"]))
+    K.centers_, K.A_, K.B_ = cg["koop_centers"].copy(), cg["koop_A"].copy(), cg["koop_B"].copy()
+    X, U = cg["koop_X"], cg["koop_U"]
+    assert np.isclose(K.multistep_rmse(X, U, 10), cg["koop_rmse"][1], rtol=TOL64)
+    K.A_ *= 0.5            # same array object, new contents
+    ref = CN.koop_multistep_se(X, U, 10, K.centers_, K.gamma, K.A_, K.B_)[2]
+    assert np.isclose(K.multistep_rmse(X, U, 10), ref, rtol=TOL64) and not np.isclose(ref, cg["koop_rmse"][1])

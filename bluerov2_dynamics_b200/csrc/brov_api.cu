@@ -698,6 +698,25 @@ static int carry_depth(brov_engine* e, double dt, int nsub, long long* out) {
     return BROV_OK;
 }
 
+// One integrator step for n vehicles with one input row per vehicle: the body of the reference's simulate_physics loop
+// (training/train_tank_brov2_rk4.py:386-394 RK4, train_tank_brov2_full_comparison.py:462-465 Euler) as a call.
+extern "C" int brov_step(brov_engine_t* e, int integrator, long long n, const void* x_dev, const void* u_dev, double dt,
+                         void* x_out_dev, void* lag_inout_dev, void* stream) {
+    brov_rollout_desc d;
+    memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.integrator = integrator;
+    d.n = n; d.steps = 1; d.dt = dt;
+    d.x0_dev = x_dev; d.xT_dev = x_out_dev; d.u_dev = u_dev;
+    d.u_stride_t = 0;
+    d.u_stride_n = e ? model_nu(e->model) : 0;
+    d.lag_in_dev = lag_inout_dev; d.lag_out_dev = lag_inout_dev;
+    d.stride = 1;
+    d.lag_in_repr = d.lag_out_repr = BROV_LAG_THRUSTER;
+    d.time_slices = 1;
+    return brov_rollout(e, &d, stream);
+}
+
 extern "C" int brov_se_carry_steps(brov_engine_t* e, double dt, int integrator, long long* steps_out) {
     if (!e || !steps_out) return fail(BROV_EINVAL, "NULL argument");
     if (e->model != BROV_THRUSTER8_LAG3) { *steps_out = 0; return BROV_OK; }

@@ -296,8 +296,22 @@ class Engine:
         return torch.einsum("ci,nik->nck", A, self.tensor(lag24).reshape(-1, 8, 3)).reshape(-1, 18).contiguous()
 
     def step(self, x, u, lag=None, dt: float = 0.02, integrator: str = "rk4") -> RolloutResult:
-        """One integrator step for N vehicles (u [N,NU])."""
-        return self.rollout(x, (u, 1), dt=dt, integrator=integrator, lag0=lag, u_layout="const")
+        """One integrator step for N vehicles (u [N,NU]) through brov_step; `lag` [N,NLAG] is advanced in place."""
+        x = self.tensor(x)
+        u = self.tensor(u)
+        self._check_rows(x, self.nx, "x")
+        self._check_rows(u, self.nu, "u")
+        n = x.shape[0]
+        if u.shape[0] != n:
+            raise ValueError("x and u must have the same number of rows")
+        lag_t = None
+        if self.nlag and lag is not None:
+            lag_t = self.tensor(lag).reshape(n, self.nlag)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_step(self._h, INTEGRATORS[integrator], n, x.data_ptr(), u.data_ptr(), float(dt),
+                                    out.data_ptr(), lag_t.data_ptr() if lag_t is not None else None, self._stream()))
+        return RolloutResult(xT=out, lag=lag_t, traj=None)
 
     def carry_steps(self, dt: float = 0.02, integrator: str = "rk4") -> int:
         """Replay depth (integrator steps) of the carried-lag evaluator for this dt / integrator."""

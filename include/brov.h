@@ -175,6 +175,10 @@ typedef struct brov_rollout_desc {
     int32_t reserved0;
 } brov_rollout_desc;
 int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* stream);
+/* One integrator step with one input row per vehicle (u [n][NU]) — the body of the reference's simulate_physics loop
+ * as a call; lag_inout [n][NLAG] or NULL (zero lag, nothing written).  x_out may alias x. */
+int brov_step(brov_engine_t* e, int integrator, long long n, const void* x_dev, const void* u_dev, double dt,
+              void* x_out_dev, void* lag_inout_dev, void* stream);
 
 /* Multi-step endpoint squared error over sliding windows — `multistep_rmse_endpoint_physics(X, U, H, dt)`
  * (training/train_tank_brov2_rk4.py:399-417 and the Euler twins in train_tank_brov2_full_comparison.py:469-487,

@@ -679,3 +679,20 @@ print(json.dumps(x.tolist()))
     assert out.returncode == 0, out.stderr[-2000:]
     x = np.array(json.loads(out.stdout.strip().splitlines()[-1]))
     assert normwise(x, golden["cfg1_euler_dt001_traj_s10"][1]) < TOL64
+
+
+def test_step_entry_point_matches_rollout(B, golden):
+    """brov_step = one iteration of the reference's simulate_physics loop; chaining it reproduces the rollout."""
+    e = B.Engine("thruster8", "f64")
+    x0, U = golden["ens_x0"], np.transpose(golden["ens_U8"], (1, 0, 2))[:25]
+    ref = e.rollout(x0, U, dt=DT)
+    x = e.tensor(x0)
+    lag = torch.zeros((x0.shape[0], 24), device="cuda", dtype=torch.float64)
+    for k in range(U.shape[0]):
+        r = e.step(x, U[k], lag=lag, dt=DT)
+        x = r.xT
+    assert torch.equal(x, ref.xT) and torch.equal(lag, ref.lag)
+    q = B.Engine("quat13", "f32")
+    xq = golden["ens_x0_q13"]
+    one = q.step(xq, golden["ens_W6"][:, 0], dt=DT, integrator="euler")
+    assert torch.equal(one.xT, q.rollout(xq, golden["ens_W6"][:, :1].transpose(1, 0, 2), dt=DT, integrator="euler").xT)

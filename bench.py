@@ -596,7 +596,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=40)
-    ap.add_argument("--cpu-steps", type=int, default=400, help="RK4 steps per core of the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=1500,
+                    help="RK4 steps per core of the CPU baseline sample (1500 = about 25 core-seconds on 16 cores)")
     ap.add_argument("--reference-budget-s", type=float, default=120.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rmse", action="store_true")

@@ -144,6 +144,31 @@ class KoopmanEDMDc:
         se, ns = self._se(X, U, int(H))
         return float(np.sqrt(se / (ns * self.state_dim))) if ns else float("nan")
 
+    def multistep_rmse_multi(self, X, U, horizons: Sequence[int]):
+        """`multistep_rmse` for several horizons at once (engine extension): the lift of every window — the expensive
+        part, `n_rbfs` exponentials — is evaluated once and shared by all horizons.  Returns a list of RMSEs (NaN
+        where the series is not longer than the horizon)."""
+        hs = [int(h) for h in horizons]
+        order = sorted(set(hs))
+        if not order or order[0] < 1:
+            raise ValueError("horizons must be positive integers")
+        h = self._handle()
+        Xd, Ud = self._dev(X, self.state_dim), self._dev(U, self.input_dim)
+        rows = Xd.shape[0]
+        if Ud.shape[0] != rows:
+            raise ValueError("X and U must have the same number of rows")
+        out = {}
+        for i in range(0, len(order), L.MAX_H):
+            part = order[i:i + L.MAX_H]
+            se = torch.zeros(len(part), device=Xd.device, dtype=torch.float64)
+            arr = (C.c_int * len(part))(*part)
+            L.check(L.lib.brov_koopman_multistep_se_multi(h, Xd.data_ptr(), Ud.data_ptr(), rows, len(part), arr,
+                                                          se.data_ptr(), self._stream()))
+            for hh, v in zip(part, se.cpu().numpy()):
+                ns = rows - hh
+                out[hh] = float(np.sqrt(v / (ns * self.state_dim))) if ns > 0 else float("nan")
+        return [out[hh] for hh in hs]
+
     def simulate(self, x0, U_seq) -> np.ndarray:
         """Open-loop rollout from x0 under U_seq -> predicted states [T+1, n], row 0 = x0 (:202-216)."""
         h = self._handle()

@@ -102,6 +102,8 @@ _PROTOS = {
     "brov_koopman_destroy": (None, [C.c_void_p]),
     "brov_koopman_lift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "brov_koopman_multistep_se": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "brov_koopman_multistep_se_multi": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                                 C.POINTER(C.c_int), C.c_void_p, C.c_void_p]),
     "brov_koopman_simulate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "brov_pinc_create": (C.c_int, [C.c_int, C.POINTER(PincWeights), C.POINTER(C.c_void_p)]),
     "brov_pinc_destroy": (None, [C.c_void_p]),

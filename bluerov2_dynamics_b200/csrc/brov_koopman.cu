@@ -13,8 +13,10 @@
 //       x_hat_k = W_H phi(x_k) + sum_{t<H} G_{H-1-t} u_{k+t}
 // which is the same linear map evaluated in a different association order (agreement with the sequential form:
 // 1e-15 relative on the RMSE, tests/test_gpu_compare.py) at 2 n (d + r H) flop per window — a 1600-fold reduction
-// for d = 512, H = 100.  What remains per window is the RBF lift (k exponentials), an n x d mat-vec and an FIR
-// filter over the inputs: one thread per window, centers / W_H / G broadcast from shared memory, FP64-pipe bound.
+// for d = 512, H = 100.  What remains per window is the RBF lift (k exponentials) with an n x d mat-vec per horizon
+// (koop_liftw_kernel: one thread per window, centres and decoder rows broadcast from shared memory, evaluated ONCE for
+// all requested horizons) and an FIR filter over the inputs per horizon (koop_fir_se_kernel: four windows per thread,
+// taps and a transposed input tile in shared memory).  FP64-pipe bound.
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -25,9 +27,6 @@
 namespace {
 
 constexpr int KB = 128;        // threads per block of the lift kernel
-constexpr int SEB = 512;       // windows per tile of the scoring kernel
-constexpr int SET = 256;       // its threads per block (two windows each): ONE persistent block per SM, so the model is
-                               // staged into shared memory once per SM, not once per tile
 constexpr int NMAX = 16;       // state dimension bound (registers)
 constexpr int RMAX = 8;        // input dimension bound
 
@@ -130,134 +129,156 @@ __global__ void __launch_bounds__(KB) koop_lift_kernel(const double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// multistep squared error: one thread per window
-//   shared memory: centers [k][n], |c|^2 [k], W_H transposed to [d][n], G [H][n][r] (if it fits, else global)
+// Several horizons in one pass.  The lift phi(x_k) (500 exponentials) does not depend on the horizon, so it is evaluated
+// ONCE per window and pushed through the decoder rows of every requested horizon:
+//   koop_liftw_kernel   P[h][k][:] = W_{H_h} phi(x_k)                     one thread per window, persistent blocks
+//   koop_fir_se_kernel  x_hat = P[h][k] + sum_t G_{H-1-t} u_{k+t}, squared error vs X[k+H]   four windows per thread
 // ---------------------------------------------------------------------------------------------------------------
-struct KoopSeArgs {
-    const double* X;      // [rows][n]
-    const double* U;      // [rows][r]
-    const double* C;      // [k][n]
-    const double* c2;     // [k]
-    const double* WH;     // [n][d]   = W_H
-    const double* G;      // [H][n][r] (G_0 .. G_{H-1})
-    double* partial;      // [tiles of SEB windows]
-    double gamma;
-    long long nwin;
-    int n, r, k, H;
-    int g_in_smem;
-};
+constexpr int LWT = 384;       // threads per block of the lift kernel (one window each; 170 registers available)
 
-template <int N, int R>
-__global__ void __launch_bounds__(SET, 1) koop_se_kernel(const KoopSeArgs a) {
+template <int N, int NH>
+__global__ void __launch_bounds__(LWT, 1) koop_liftw_kernel(const double* __restrict__ X, const double* __restrict__ C,
+                                                           const double* __restrict__ c2, const double* __restrict__ W,
+                                                           const int* __restrict__ Hs, double gamma, long long nwin,
+                                                           int k, double* __restrict__ P) {
     extern __shared__ double sm[];
-    const int k = a.k, d = N + a.k, H = a.H;
-    double* sC = sm;                         // [k][N]
-    double* sc2 = sC + (size_t)k * N;        // [k]
-    double* sW = sc2 + k;                    // [d][N]  (transposed: the N outputs of one lifted coordinate contiguous)
-    double* sG = sW + (size_t)d * N;         // [H][N][R]
-    for (int e = threadIdx.x; e < k * N; e += SET) sC[e] = a.C[e];
-    for (int e = threadIdx.x; e < k; e += SET) sc2[e] = a.c2[e];
-    for (int e = threadIdx.x; e < d * N; e += SET) {
-        const int q = e / N, i = e - q * N;
-        sW[e] = a.WH[(size_t)i * d + q];
+    const int d = N + k;
+    double* sC = sm;                          // [k][N]
+    double* sc2 = sC + (size_t)k * N;         // [k]
+    double* sW = sc2 + k;                     // [NH][d][N]  (transposed decoder rows of each horizon)
+    for (int e = threadIdx.x; e < k * N; e += LWT) sC[e] = C[e];
+    for (int e = threadIdx.x; e < k; e += LWT) sc2[e] = c2[e];
+    for (int h = 0; h < NH; ++h) {
+        const double* WH = W + (size_t)Hs[h] * N * d;
+        for (int e = threadIdx.x; e < d * N; e += LWT) {
+            const int q = e / N, i = e - q * N;
+            sW[(size_t)h * d * N + e] = WH[(size_t)i * d + q];
+        }
     }
-    if (a.g_in_smem)
-        for (int e = threadIdx.x; e < H * N * R; e += SET) sG[e] = a.G[e];
     __syncthreads();
-    const double* G = a.g_in_smem ? sG : a.G;
-    __shared__ double red[SET / 32];
-
-    // Each thread scores TWO windows of the tile (w and w + SET): every centre, decoder column and FIR tap fetched from
-    // shared memory feeds two multiply-adds instead of one.  A thread whose second window falls off the end shadows the
-    // last window and discards the result.
-    const long long ntiles = (a.nwin + SEB - 1) / SEB;
+    const long long ntiles = (nwin + LWT - 1) / LWT;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long w0 = tile * SEB + threadIdx.x;
-        const long long w1 = w0 + SET;
-        const bool ok0 = w0 < a.nwin, ok1 = w1 < a.nwin;
-        const long long v0 = ok0 ? w0 : a.nwin - 1, v1 = ok1 ? w1 : a.nwin - 1;
-        double x0[N], x1[N], acc0[N], acc1[N], s0 = 0.0, s1 = 0.0;
+        const long long w = tile * LWT + threadIdx.x;
+        if (w >= nwin) continue;
+        double x[N], acc[NH][N], x2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            x0[i] = __ldg(a.X + v0 * N + i);
-            x1[i] = __ldg(a.X + v1 * N + i);
-            s0 = fma(x0[i], x0[i], s0);
-            s1 = fma(x1[i], x1[i], s1);
-            acc0[i] = 0.0;
-            acc1[i] = 0.0;
+            x[i] = __ldg(X + w * N + i);
+            x2 = fma(x[i], x[i], x2);
         }
-        // linear part of the lift
 #pragma unroll
-        for (int q = 0; q < N; ++q) {
+        for (int h = 0; h < NH; ++h)
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double wv = sW[q * N + i];
-                acc0[i] = fma(wv, x0[q], acc0[i]);
-                acc1[i] = fma(wv, x1[q], acc1[i]);
-            }
-        }
-        // radial basis functions
-        const double mg = -a.gamma;
+            for (int i = 0; i < N; ++i) acc[h][i] = 0.0;
+#pragma unroll
+        for (int q = 0; q < N; ++q)
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[h][i] = fma(sW[((size_t)h * d + q) * N + i], x[q], acc[h][i]);
+        const double mg = -gamma;
 #pragma unroll 2
         for (int j = 0; j < k; ++j) {
-            double d0 = 0.0, d1 = 0.0;
+            double dot = 0.0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double cv = sC[j * N + i];
-                d0 = fma(x0[i], cv, d0);
-                d1 = fma(x1[i], cv, d1);
-            }
-            const double cj = sc2[j];
-            const double e0 = exp(mg * (s0 + cj - 2.0 * d0));
-            const double e1 = exp(mg * (s1 + cj - 2.0 * d1));
-            const double* wc = sW + (size_t)(N + j) * N;
+            for (int i = 0; i < N; ++i) dot = fma(x[i], sC[j * N + i], dot);
+            const double e = exp(mg * (x2 + sc2[j] - 2.0 * dot));
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const double wv = wc[i];
-                acc0[i] = fma(wv, e0, acc0[i]);
-                acc1[i] = fma(wv, e1, acc1[i]);
+            for (int h = 0; h < NH; ++h) {
+                const double* wc = sW + ((size_t)h * d + N + j) * N;
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[h][i] = fma(wc[i], e, acc[h][i]);
             }
         }
-        // input FIR: sum_t G_{H-1-t} u_{k+t}
-        for (int t = 0; t < H; ++t) {
-            double u0[R], u1[R];
+#pragma unroll
+        for (int h = 0; h < NH; ++h)
+#pragma unroll
+            for (int i = 0; i < N; ++i) P[((size_t)h * nwin + w) * N + i] = acc[h][i];
+    }
+}
+
+constexpr int FT = 256, FW = 4;   // threads per block and windows per thread of the FIR kernel (1024-window tiles)
+
+// Window w at tap t reads input row w + t: a warp's 32 rows are 64 B apart, so a 128-bit global load touches 16 cache
+// lines and the L1 data pipe saturates (93 % of peak at 27 % of the FP64 pipe in profiles/r01k_koopman_multi_raw.csv).
+// The tile's rows [w0, w0 + FT FW + H) are therefore staged once into shared memory TRANSPOSED ([channel][row]), where
+// the same access is a conflict-free 64-bit load of consecutive words.
+template <int N, int R>
+__global__ void __launch_bounds__(FT) koop_fir_se_kernel(const double* __restrict__ X, const double* __restrict__ U,
+                                                         const double* __restrict__ P, const double* __restrict__ Gg,
+                                                         int H, long long nwin, long long rows, int g_in_smem,
+                                                         int u_in_smem, double* __restrict__ partial) {
+    extern __shared__ double sm[];
+    double* sG = sm;
+    const int TR = FT * FW + H;                      // rows of the input tile
+    double* sU = sm + (g_in_smem ? (size_t)H * N * R : 0);   // [R][TR]
+    const long long w0 = (long long)blockIdx.x * (FT * FW);
+    if (g_in_smem)
+        for (int e = threadIdx.x; e < H * N * R; e += FT) sG[e] = Gg[e];
+    if (u_in_smem) {
+        for (int e = threadIdx.x; e < TR * R; e += FT) {
+            const int row = e / R, c = e - row * R;
+            const long long gr = w0 + row;
+            sU[(size_t)c * TR + row] = gr < rows ? __ldg(U + gr * R + c) : 0.0;
+        }
+    }
+    __syncthreads();
+    const double* G = g_in_smem ? sG : Gg;
+    __shared__ double red[FT / 32];
+    long long v[FW];
+    bool ok[FW];
+    double acc[FW][N];
+#pragma unroll
+    for (int j = 0; j < FW; ++j) {
+        const long long w = w0 + (long long)j * FT + threadIdx.x;
+        ok[j] = w < nwin;
+        v[j] = ok[j] ? w : nwin - 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[j][i] = __ldg(P + v[j] * N + i);
+    }
+    for (int t = 0; t < H; ++t) {
+        double u[FW][R];
+        if (u_in_smem) {
+#pragma unroll
+            for (int j = 0; j < FW; ++j)
+#pragma unroll
+                for (int c = 0; c < R; ++c) u[j][c] = sU[(size_t)c * TR + (v[j] - w0) + t];
+        } else {
+#pragma unroll
+            for (int j = 0; j < FW; ++j)
+#pragma unroll
+                for (int c = 0; c < R; ++c) u[j][c] = __ldg(U + (v[j] + t) * R + c);
+        }
+        const double* g = G + (size_t)(H - 1 - t) * N * R;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
 #pragma unroll
             for (int c = 0; c < R; ++c) {
-                u0[c] = __ldg(a.U + (v0 + t) * R + c);
-                u1[c] = __ldg(a.U + (v1 + t) * R + c);
-            }
-            const double* g = G + (size_t)(H - 1 - t) * N * R;
+                const double gv = g[i * R + c];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-#pragma unroll
-                for (int c = 0; c < R; ++c) {
-                    const double gv = g[i * R + c];
-                    acc0[i] = fma(gv, u0[c], acc0[i]);
-                    acc1[i] = fma(gv, u1[c], acc1[i]);
-                }
+                for (int j = 0; j < FW; ++j) acc[j][i] = fma(gv, u[j][c], acc[j][i]);
             }
-        }
-        double se0 = 0.0, se1 = 0.0;
+    }
+    double se = 0.0;
+#pragma unroll
+    for (int j = 0; j < FW; ++j) {
+        double s = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double e0 = __ldg(a.X + (v0 + H) * N + i) - acc0[i];
-            const double e1 = __ldg(a.X + (v1 + H) * N + i) - acc1[i];
-            se0 = fma(e0, e0, se0);
-            se1 = fma(e1, e1, se1);
+            const double e = __ldg(X + (v[j] + H) * N + i) - acc[j][i];
+            s = fma(e, e, s);
         }
-        double se = (ok0 ? se0 : 0.0) + (ok1 ? se1 : 0.0);
-        // block reduction, fixed order; one partial per tile keeps the final sum independent of the grid size
+        se += ok[j] ? s : 0.0;
+    }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) se += __shfl_down_sync(0xffffffffu, se, off);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
+    for (int off = 16; off > 0; off >>= 1) se += __shfl_down_sync(0xffffffffu, se, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = se;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < SET / 32; ++q) s += red[q];
-            a.partial[tile] = s;
-        }
-        __syncthreads();
+        for (int q = 0; q < FT / 32; ++q) s += red[q];
+        partial[blockIdx.x] = s;
     }
 }
 
@@ -315,6 +336,9 @@ struct brov_koopman {
     size_t cap_partial;
     double* Z0;
     size_t cap_z0;
+    double* P;                  // [n_horizons][windows][n] lifted part of the predictions (multi-horizon scoring)
+    size_t cap_P;
+    int* d_Hs;                  // [BROV_MAX_H]
 };
 
 static int koop_prepare(brov_koopman* h, int T, cudaStream_t st) {
@@ -400,7 +424,7 @@ extern "C" void brov_koopman_destroy(brov_koopman_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->C); cudaFree(h->c2); cudaFree(h->A); cudaFree(h->B); cudaFree(h->W); cudaFree(h->G);
-    cudaFree(h->partial); cudaFree(h->Z0);
+    cudaFree(h->partial); cudaFree(h->Z0); cudaFree(h->P); cudaFree(h->d_Hs);
     delete h;
 }
 
@@ -416,56 +440,113 @@ extern "C" int brov_koopman_lift(brov_koopman_t* h, const double* X_dev, long lo
     return BROV_OK;
 }
 
-template <int N, int R>
-static int koop_se_launch(brov_koopman* h, const KoopSeArgs& a0, size_t smem_base, cudaStream_t st) {
-    KoopSeArgs a = a0;
-    const size_t g_bytes = (size_t)a.H * N * R * sizeof(double);
-    a.g_in_smem = (smem_base + g_bytes <= 200 * 1024) ? 1 : 0;
-    const size_t smem = smem_base + (a.g_in_smem ? g_bytes : 0);
-    if (smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_se_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long ntiles = (a.nwin + SEB - 1) / SEB;
+template <int N, int NH>
+static int koop_liftw_launch(brov_koopman* h, const double* X, long long nwin, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_liftw_kernel<N, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (nwin + LWT - 1) / LWT;
     const unsigned grid = (unsigned)(ntiles < h->num_sms ? ntiles : h->num_sms);
-    koop_se_kernel<N, R><<<grid, SET, smem, st>>>(a);
+    koop_liftw_kernel<N, NH><<<grid, LWT, smem, st>>>(X, h->C, h->c2, h->W, h->d_Hs, h->gamma, nwin, h->k, h->P);
+    BROV_CUDA_TRY(cudaGetLastError());
+    return BROV_OK;
+}
+template <int N>
+static int koop_liftw_nh(brov_koopman* h, int nh, const double* X, long long nwin, size_t smem, cudaStream_t st) {
+    switch (nh) {
+        case 1: return koop_liftw_launch<N, 1>(h, X, nwin, smem, st);
+        case 2: return koop_liftw_launch<N, 2>(h, X, nwin, smem, st);
+        case 3: return koop_liftw_launch<N, 3>(h, X, nwin, smem, st);
+    }
+    return brov::fail_msg(BROV_EINVAL, "internal: %d horizons per lift pass", nh);
+}
+template <int N, int R>
+static int koop_fir_launch(brov_koopman* h, const double* X, const double* U, const double* P, int H, long long nwin,
+                           long long rows, double* partial, cudaStream_t st) {
+    const size_t g_bytes = (size_t)H * N * R * sizeof(double);
+    const size_t u_bytes = (size_t)(FT * FW + H) * R * sizeof(double);
+    const size_t budget = 220 * 1024;
+    const int u_in_smem = u_bytes <= budget;                       // the input tile first: it removes the L1 bottleneck
+    const int g_in_smem = g_bytes + (u_in_smem ? u_bytes : 0) <= budget;
+    const size_t smem = (g_in_smem ? g_bytes : 0) + (u_in_smem ? u_bytes : 0);
+    if (smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_fir_se_kernel<N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((nwin + FT * FW - 1) / (FT * FW));
+    koop_fir_se_kernel<N, R><<<grid, FT, smem, st>>>(X, U, P, h->G, H, nwin, rows, g_in_smem, u_in_smem, partial);
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;
 }
 
-extern "C" int brov_koopman_multistep_se(brov_koopman_t* h, const double* X_dev, const double* U_dev, long long rows,
-                                         long long n_windows, int H, double* se_out_dev, void* stream) {
-    if (!h || !X_dev || !U_dev || !se_out_dev) return brov::fail_msg(BROV_EINVAL, "NULL argument");
-    if (H < 1) return brov::fail_msg(BROV_EINVAL, "H must be >= 1");
-    if (n_windows < 0 || n_windows + H > rows) return brov::fail_msg(BROV_EINVAL, "n_windows + H = %lld exceeds rows = %lld", n_windows + H, rows);
+// windows scored for horizon H: k in [0, min(win_limit, rows - H)); win_limit < 0 = no limit
+static int koop_score(brov_koopman* h, const double* X_dev, const double* U_dev, long long rows, long long win_limit,
+                      int n_horizons, const int* horizons, double* se_out_dev, void* stream) {
+    if (!h || !X_dev || !U_dev || !se_out_dev || !horizons) return brov::fail_msg(BROV_EINVAL, "NULL argument");
+    if (n_horizons < 1 || n_horizons > BROV_MAX_H) return brov::fail_msg(BROV_EINVAL, "n_horizons must be 1..%d", BROV_MAX_H);
+    for (int q = 0; q < n_horizons; ++q)
+        if (horizons[q] < 1 || (q && horizons[q] <= horizons[q - 1])) return brov::fail_msg(BROV_EINVAL, "horizons must be >= 1 and strictly ascending");
+    if (!((h->n == 12 && (h->r == 8 || h->r == 6)) || (h->n == 13 && h->r == 6)))
+        return brov::fail_msg(BROV_EUNSUPPORTED, "compiled for (n, r) = (12, 8), (12, 6), (13, 6); got (%d, %d)", h->n, h->r);
     cudaStream_t st = (cudaStream_t)stream;
     BROV_CUDA_TRY(cudaSetDevice(h->device));
-    if (n_windows == 0) {
-        BROV_CUDA_TRY(cudaMemsetAsync(se_out_dev, 0, sizeof(double), st));
-        return BROV_OK;
-    }
-    int rc = koop_prepare(h, H, st);
+    BROV_CUDA_TRY(cudaMemsetAsync(se_out_dev, 0, n_horizons * sizeof(double), st));
+    long long nwin = rows - horizons[0];              // windows of the shortest horizon: the lift covers all of them
+    if (win_limit >= 0 && nwin > win_limit) nwin = win_limit;
+    if (nwin <= 0) return BROV_OK;
+    int rc = koop_prepare(h, horizons[n_horizons - 1], st);
     if (rc) return rc;
-    const size_t nblocks = (size_t)((n_windows + SEB - 1) / SEB);   // one partial per tile of SEB windows
+    const int n = h->n, d = h->d;
+    // how many horizons' decoder rows fit shared memory beside the centres
+    const size_t base = ((size_t)h->k * n + h->k) * sizeof(double), per = (size_t)d * n * sizeof(double);
+    int fit = (int)((220 * 1024 - (long long)base) / (long long)per);
+    if (fit < 1) return brov::fail_msg(BROV_EUNSUPPORTED, "model with d = %d does not fit shared memory", d);
+    if (fit > 3) fit = 3;
+    const size_t needP = (size_t)fit * nwin * n;
+    if (needP > h->cap_P) {
+        cudaFree(h->P);
+        h->P = nullptr; h->cap_P = 0;
+        BROV_CUDA_TRY(cudaMalloc(&h->P, needP * sizeof(double)));
+        h->cap_P = needP;
+    }
+    if (!h->d_Hs) BROV_CUDA_TRY(cudaMalloc(&h->d_Hs, BROV_MAX_H * sizeof(int)));
+    const size_t nblocks = (size_t)((nwin + FT * FW - 1) / (FT * FW));
     if (nblocks > h->cap_partial) {
         cudaFree(h->partial);
         h->partial = nullptr; h->cap_partial = 0;
         BROV_CUDA_TRY(cudaMalloc(&h->partial, nblocks * sizeof(double)));
         h->cap_partial = nblocks;
     }
-    KoopSeArgs a;
-    a.X = X_dev; a.U = U_dev; a.C = h->C; a.c2 = h->c2;
-    a.WH = h->W + (size_t)H * h->n * h->d;
-    a.G = h->G;
-    a.partial = h->partial; a.gamma = h->gamma; a.nwin = n_windows;
-    a.n = h->n; a.r = h->r; a.k = h->k; a.H = H; a.g_in_smem = 0;
-    const size_t smem_base = ((size_t)h->k * h->n + h->k + (size_t)h->d * h->n) * sizeof(double);
-    if (smem_base > 200 * 1024) return brov::fail_msg(BROV_EUNSUPPORTED, "model with d = %d does not fit shared memory", h->d);
-    if (h->n == 12 && h->r == 8) rc = koop_se_launch<12, 8>(h, a, smem_base, st);
-    else if (h->n == 12 && h->r == 6) rc = koop_se_launch<12, 6>(h, a, smem_base, st);
-    else if (h->n == 13 && h->r == 6) rc = koop_se_launch<13, 6>(h, a, smem_base, st);
-    else return brov::fail_msg(BROV_EUNSUPPORTED, "compiled for (n, r) = (12, 8), (12, 6), (13, 6); got (%d, %d)", h->n, h->r);
-    if (rc) return rc;
-    koop_finish_kernel<<<1, 256, 0, st>>>(h->partial, (int)nblocks, se_out_dev);
-    BROV_CUDA_TRY(cudaGetLastError());
+    for (int q0 = 0; q0 < n_horizons; q0 += fit) {
+        const int nh = (n_horizons - q0 < fit) ? (n_horizons - q0) : fit;
+        BROV_CUDA_TRY(cudaMemcpyAsync(h->d_Hs, horizons + q0, nh * sizeof(int), cudaMemcpyHostToDevice, st));
+        const size_t smem = base + nh * per;
+        rc = (n == 12) ? koop_liftw_nh<12>(h, nh, X_dev, nwin, smem, st) : koop_liftw_nh<13>(h, nh, X_dev, nwin, smem, st);
+        if (rc) return rc;
+        for (int q = 0; q < nh; ++q) {
+            const int H = horizons[q0 + q];
+            long long nw = rows - H;
+            if (win_limit >= 0 && nw > win_limit) nw = win_limit;
+            if (nw <= 0) continue;
+            const double* Pq = h->P + (size_t)q * nwin * n;
+            if (n == 12 && h->r == 8) rc = koop_fir_launch<12, 8>(h, X_dev, U_dev, Pq, H, nw, rows, h->partial, st);
+            else if (n == 12) rc = koop_fir_launch<12, 6>(h, X_dev, U_dev, Pq, H, nw, rows, h->partial, st);
+            else rc = koop_fir_launch<13, 6>(h, X_dev, U_dev, Pq, H, nw, rows, h->partial, st);
+            if (rc) return rc;
+            koop_finish_kernel<<<1, 256, 0, st>>>(h->partial, (int)((nw + FT * FW - 1) / (FT * FW)), se_out_dev + q0 + q);
+            BROV_CUDA_TRY(cudaGetLastError());
+        }
+        if (q0 + fit < n_horizons) BROV_CUDA_TRY(cudaStreamSynchronize(st));   // d_Hs is rewritten by the next pass
+    }
     return BROV_OK;
+}
+
+extern "C" int brov_koopman_multistep_se_multi(brov_koopman_t* h, const double* X_dev, const double* U_dev,
+                                               long long rows, int n_horizons, const int* horizons,
+                                               double* se_out_dev, void* stream) {
+    return koop_score(h, X_dev, U_dev, rows, -1, n_horizons, horizons, se_out_dev, stream);
+}
+
+extern "C" int brov_koopman_multistep_se(brov_koopman_t* h, const double* X_dev, const double* U_dev, long long rows,
+                                         long long n_windows, int H, double* se_out_dev, void* stream) {
+    if (H < 1) return brov::fail_msg(BROV_EINVAL, "H must be >= 1");
+    if (n_windows < 0 || n_windows + H > rows) return brov::fail_msg(BROV_EINVAL, "n_windows + H = %lld exceeds rows = %lld", n_windows + H, rows);
+    return koop_score(h, X_dev, U_dev, rows, n_windows, 1, &H, se_out_dev, stream);
 }
 
 extern "C" int brov_koopman_simulate(brov_koopman_t* h, const double* X0_dev, const double* U_dev, long long T,

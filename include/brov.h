@@ -246,6 +246,11 @@ int brov_koopman_lift(brov_koopman_t* h, const double* X_dev, long long rows, do
  * (rmse = sqrt(se / (n_windows n))), and `evaluate(X, U)` :157-170 for H = 1.  se_out_dev: double[1], dev. */
 int brov_koopman_multistep_se(brov_koopman_t* h, const double* X_dev, const double* U_dev, long long rows,
                               long long n_windows, int H, double* se_out_dev, void* stream);
+/* The same for up to BROV_MAX_H horizons in one call (horizons: host array, strictly ascending): the lift phi(x_k) is
+ * evaluated once per window and pushed through the decoder rows of every horizon; horizon h scores windows
+ * 0 .. rows - H_h - 1.  se_out_dev: double[n_horizons], dev. */
+int brov_koopman_multistep_se_multi(brov_koopman_t* h, const double* X_dev, const double* U_dev, long long rows,
+                                    int n_horizons, const int* horizons, double* se_out_dev, void* stream);
 /* `simulate(x0, U_seq)` :202-216 for nb trajectories at once: X0 [nb][n]; U time-major [T][nb][r] (u_shared = 0) or
  * [T][r] (u_shared = 1); out [T][nb][n] = predicted states after steps 1..T (row 0 of the reference's array is x0). */
 int brov_koopman_simulate(brov_koopman_t* h, const double* X0_dev, const double* U_dev, long long T, long long nb,

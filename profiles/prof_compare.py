@@ -26,6 +26,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "both"
 if which in ("both", "koop"):
     for H in (1, 100):
         print("koopman H", H, K.multistep_rmse(X, U, H))
+    print("koopman multi", K.multistep_rmse_multi(X, U, [1, 10, 100]))
 if which in ("both", "pinc"):
     cg = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_cmp.npz"))
     M = P.PincModel({kk[len("pinc_sd_"):]: cg[kk] for kk in cg.files if kk.startswith("pinc_sd_")})

@@ -296,3 +296,15 @@ def test_koopman_model_edited_in_place_is_reuploaded(cg):
     K.A_ *= 0.5            # same array object, new contents
     ref = CN.koop_multistep_se(X, U, 10, K.centers_, K.gamma, K.A_, K.B_)[2]
     assert np.isclose(K.multistep_rmse(X, U, 10), ref, rtol=TOL64) and not np.isclose(ref, cg["koop_rmse"][1])
+
+
+def test_koopman_multi_horizon_single_lift(KM, cg):
+    """All horizons from one lift pass = the per-horizon calls = the reference."""
+    X, U = cg["koop_X"], cg["koop_U"]
+    hs = [int(h) for h in cg["cmp_H"]]
+    got = KM.multistep_rmse_multi(X, U, hs)
+    assert np.allclose(got, cg["koop_rmse"], rtol=TOL64)
+    assert np.allclose(got, [KM.multistep_rmse(X, U, h) for h in hs], rtol=1e-13)
+    five = KM.multistep_rmse_multi(X, U, [100, 1, 7, 10, 3, 250, 400])   # more than MAX_H, unsorted, one too long
+    assert np.allclose(five[:2], [cg["koop_rmse"][2], cg["koop_rmse"][0]], rtol=TOL64) and np.isnan(five[-1])
+    assert np.isclose(five[2], KM.multistep_rmse(X, U, 7), rtol=1e-13)

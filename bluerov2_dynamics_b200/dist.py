@@ -47,6 +47,36 @@ def window_shard(T: int, horizons: Sequence[int], rank: int, world: int):
     return lo, min(T, hi + hmax) if hi > lo else lo, hi - lo
 
 
+def window_shard_carry(T: int, H: int, rank: int, world: int, carry_steps: int):
+    """Shard of the carried-lag evaluator (one horizon): besides the H-row halo after its last window a rank needs the
+    input rows its first window replays — the last `carry_steps` lag steps of the shared model object's history, i.e.
+    rows back to window (lo * H - carry_steps) // H.  Returns (row_lo, row_hi, n_windows_local, window_lo)."""
+    nwin = max(T - H, 0)
+    lo, hi = shard_range(nwin, rank, world)
+    if hi <= lo:
+        return lo, lo, 0, lo
+    row_lo = max(0, (lo * H - int(carry_steps)) // H)
+    return row_lo, min(T, hi + H), hi - lo, lo
+
+
+def sharded_multistep_rmse_carry(engine, X: np.ndarray, U: np.ndarray, H: int, dt: float, integrator: str, rank: int,
+                                 world: int) -> float:
+    """The reference's literal evaluator semantics (lag state carried from window to window) on `world` GPUs: each
+    rank scores a contiguous block of windows and replays the tail of the shared history from its own copy of the
+    input rows; one all-reduce of the squared-error sum.  `engine`: a thruster-model Engine on the rank's device."""
+    T = len(X)
+    depth = engine.carry_steps(dt, integrator)
+    row_lo, row_hi, nloc, win_lo = window_shard_carry(T, int(H), rank, world, depth)
+    vec = torch.zeros(1, dtype=torch.float64, device=engine.device)
+    if nloc > 0:
+        se, _ = engine.multistep_se(X[row_lo:row_hi], U[row_lo:row_hi], [int(H)], dt=dt, integrator=integrator,
+                                    n_windows=nloc, lag_mode="carry", window0=win_lo, row0=row_lo)
+        vec += se[:1]
+    allreduce_sum_(vec)
+    cnt = max(T - int(H), 0)
+    return float(np.sqrt(vec.item() / (cnt * X.shape[1]))) if cnt > 0 else float("nan")
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -33,8 +33,16 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there on every rank), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a saved
+# copy of the original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 METRIC = "rk4_vehicle_steps_per_s"
 UNIT = "vehicle-steps/s"
@@ -562,7 +570,7 @@ def main_ours(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -597,7 +605,7 @@ def main_reference(args):
             "config": {"workload": "BASELINE configs[1] model and inputs, bounded sample on the host CPU cores"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == "__main__":

@@ -696,3 +696,43 @@ def test_step_entry_point_matches_rollout(B, golden):
     xq = golden["ens_x0_q13"]
     one = q.step(xq, golden["ens_W6"][:, 0], dt=DT, integrator="euler")
     assert torch.equal(one.xT, q.rollout(xq, golden["ens_W6"][:, :1].transpose(1, 0, 2), dt=DT, integrator="euler").xT)
+
+
+@pytest.mark.parametrize("kind", ["wrench12", "quat13"])
+def test_cfg4_monte_carlo_sweep_with_wrench_lag(B, kind):
+    """BASELINE config 4 as a whole: per-vehicle added-mass / damping perturbations U(0.7, 1.3) (Minv rebuilt, trap T5)
+    AND per-vehicle first-order wrench lag T_lag ~ U(0.05, 0.3) s, wrench inputs scaled (40,40,40,5,5,5), both wrench
+    models, fp64 and fp32, against the oracle (the lag is an extension: parity unpinned by the reference)."""
+    rng = np.random.default_rng(21)
+    n, T = 777, 150
+    nx = 13 if kind == "quat13" else 12
+    x0 = np.zeros((n, nx))
+    x0[:, :3] = rng.uniform(-1, 1, (n, 3))
+    if kind == "quat13":
+        q = rng.normal(size=(n, 4))
+        x0[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    else:
+        x0[:, 3:6] = rng.uniform(-0.3, 0.3, (n, 3))
+    U = O.smooth_inputs(rng, T, 6, n=n, scale=np.array([40, 40, 40, 5, 5, 5.0]), sigma=0.05)
+    scales = rng.uniform(0.7, 1.3, (n, 18))
+    Tlag = rng.uniform(0.05, 0.3, n)
+    p = O.default_params()
+    names = ["Xu_dot", "Yv_dot", "Zw_dot", "Kp_dot", "Mq_dot", "Nr_dot", "Xu", "Yv", "Zw", "Kp", "Mq", "Nr",
+             "Xu_abs", "Yv_abs", "Zw_abs", "Kp_abs", "Mq_abs", "Nr_abs"]
+    ph = np.tile(B.default_physical(), (n, 1))
+    for j, k in enumerate(names):
+        p[k] = p[k] * scales[:, j]
+        ph[:, 9 + j] = p[k]
+    p["Minv"] = O.minv_diag(p)
+    ph[:, 27:33] = p["Minv"]
+    ph[:, 36] = Tlag
+    xa = np.concatenate([x0, np.zeros((n, 6))], axis=1)
+    snaps, xT, _ = O.rollout(O.Model(kind, DT, p, lag1_T=Tlag), "rk4", xa, U, stride=50)
+    for dtype, tol in (("f64", TOL64), ("f32", TOL32)):
+        e = B.Engine(kind, dtype)
+        e.set_wrench_lag1(True)
+        e.set_vehicle_physical(ph)
+        r = e.rollout(x0, U, dt=DT, stride=50)
+        assert normwise(cpu(r.xT), xT[:, :nx]) < tol
+        assert normwise(cpu(r.lag), xT[:, nx:]) < tol * 40      # filtered wrench, up to 40 N
+        assert normwise(cpu(r.traj), snaps[:, :, :nx]) < tol

@@ -465,6 +465,48 @@ def run_compare_leg(torch, B, local, windows, fp32_peak, fp64_peak, T=1_000_100,
     return out
 
 
+def run_monte_carlo_leg(torch, B, local, fp32_peak, windows, n=1 << 20, steps=5):
+    """BASELINE configs[3]: Monte-Carlo sweep — per-vehicle added-mass / damping coefficients (table [36][N], staged per
+    block into shared memory) with wrench input and the first-order wrench lag, fp32, 100 RK4 steps per launch."""
+    e = B.Engine("wrench12", "f32", device=local)
+    rng = np.random.default_rng(3)
+    ph = np.tile(B.default_physical(), (n, 1))
+    ph[:, 9:27] *= rng.uniform(0.7, 1.3, (n, 18))
+    ph[:, 27:30] = 1.0 / (ph[:, 0:1] - ph[:, 9:12])
+    ph[:, 30:33] = 1.0 / (ph[:, 6:9] - ph[:, 12:15])
+    ph[:, 36] = rng.uniform(0.05, 0.3, n)
+    e.set_wrench_lag1(True)
+    e.set_vehicle_physical(ph)
+    g = torch.Generator(device=e.device).manual_seed(33)
+    scale = torch.tensor([40, 40, 40, 5, 5, 5.0], device=e.device)
+    U = [((torch.rand((CHUNK, n, 6), device=e.device, generator=g) * 2 - 1) * scale).contiguous() for _ in range(2)]
+    x = torch.zeros((n, 12), device=e.device, dtype=torch.float32)
+    lag = torch.zeros((n, 6), device=e.device, dtype=torch.float32)
+
+    def one(k):
+        e.rollout(x, U[k % 2], dt=DT, integrator="rk4", lag0=lag, xT_out=x, lag_out=lag, step0=k * CHUNK)
+    for k in range(3):
+        one(k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for k in range(steps):
+        one(3 + k)
+    e1.record()
+    torch.cuda.synchronize()
+    windows.append((t0, time.perf_counter()))
+    ms = e0.elapsed_time(e1) / steps
+    rate = n * CHUNK / (ms * 1e-3)
+    flop = FLOP_PER_STEP["wrench12"] + 4 * 12.0     # + first-order lag: 12 flop per RHS evaluation (SURVEY 8d)
+    return {"workload": f"configs[3]: {n} vehicles, per-vehicle coefficients + first-order wrench lag, wrench-input "
+                        "12-state model, fp32, 100 RK4 steps per launch",
+            "ms": ms, "vehicle_steps_per_s": rate, "finite": bool(torch.isfinite(x).all().item()),
+            "roofline": {"bound": "fp32_pipe", "achieved": rate * flop / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": rate * flop / 1e12 / fp32_peak, "flop_per_vehicle_step": flop,
+                         "kernel": "brov::rollout_kernel<float, WRENCH12, RK4, lag1, per-vehicle>"}}
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -510,6 +552,7 @@ def main_ours(args):
     del leg3["U"], leg3["x0"], leg3["eng"]
     torch.cuda.empty_cache()
     rmse = run_rmse_leg(torch, dist, B, local, rank, world, windows) if not args.no_rmse else None
+    mc = run_monte_carlo_leg(torch, B, local, fp32_peak, windows) if rank == 0 and not args.no_compare else None
     compare = (run_compare_leg(torch, B, local, windows, fp32_peak, fp64_peak, cpu=not args.no_cpu_baseline)
                if rank == 0 and not args.no_compare else None)
     try:
@@ -566,6 +609,7 @@ def main_ours(args):
                  "roofline": roof(leg3, CFG3, fp32_peak), "gpu_launches": args.steps},
         "rmse": rmse,
         "reduced9": red9,
+        "monte_carlo": mc,
         "comparison_models": compare,
     }
     if cpu is not None:

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BROV_LIB") or os.path.join(_HERE, "libbrov.so")  # BROV_LIB: a tuning variant
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 THRUSTER8_LAG3, WRENCH_EULER12, WRENCH_QUAT13 = 0, 1, 2
 DI_EULER12_U8, DI_EULER12_U6, DI_QUAT13_U6 = 3, 4, 5
 F64, F32 = 0, 1
@@ -84,7 +84,7 @@ _PROTOS = {
     "brov_get_params": (C.c_int, [C.c_void_p, _DP]),
     "brov_set_allocation": (C.c_int, [C.c_void_p, _DP]),
     "brov_set_di_gains": (C.c_int, [C.c_void_p, _DP, _DP]),
-    "brov_set_vehicle_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong]),
+    "brov_set_vehicle_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int]),
     "brov_set_wrench_lag1": (C.c_int, [C.c_void_p, C.c_int]),
     "brov_lag_discretize": (C.c_int, [C.c_double, _DP, _DP]),
     "brov_set_lag_discrete": (C.c_int, [C.c_void_p, C.c_double, _DP, _DP]),

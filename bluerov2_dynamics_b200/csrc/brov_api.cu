@@ -73,6 +73,7 @@ struct brov_engine {
     int use_lag1;
     const void* pv;
     long long pv_n;
+    int pv_current;      // some row of the per-vehicle table has a non-zero current (relative-velocity terms needed)
     std::vector<LagDisc> lag_overrides;
     LagDisc lag_cache;
     HostStage hs;
@@ -262,7 +263,9 @@ static int make_consts(brov_engine* e, double dt, int nsub, Consts<T>* c) {
         for (int i = 0; i < 16; ++i) c->sc[i] = (T)sc[i];
         for (int i = 0; i < 8; ++i) c->rot[i] = (T)rot[i];
     }
-    c->has_current = (e->kp[KP_CUR] != 0.0 || e->kp[KP_CUR + 1] != 0.0 || e->kp[KP_CUR + 2] != 0.0 || e->pv != nullptr) ? 1 : 0;
+    // per-vehicle tables: the caller says whether any row carries an ocean current (the table is device memory)
+    c->has_current = (e->pv ? e->pv_current != 0
+                            : (e->kp[KP_CUR] != 0.0 || e->kp[KP_CUR + 1] != 0.0 || e->kp[KP_CUR + 2] != 0.0)) ? 1 : 0;
     c->use_lag1 = e->use_lag1;
     if (e->model == BROV_THRUSTER8_LAG3) {
         const LagDisc* d = lag_for_dt(e, dt);
@@ -335,7 +338,7 @@ extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out
     brov_engine* e = new (std::nothrow) brov_engine();
     if (!e) return fail(BROV_ENOMEM, "out of host memory");
     e->model = model; e->dtype = dtype; e->device = device;
-    e->use_lag1 = 0; e->pv = nullptr; e->pv_n = 0;
+    e->use_lag1 = 0; e->pv = nullptr; e->pv_n = 0; e->pv_current = 0;
     e->lag_cache.dt = -1.0;
     e->num_sms = prop.multiProcessorCount; e->d_sched = nullptr; e->cap_sched = 0;
     e->call_pinned = nullptr; e->call_dev = nullptr; e->cap_call = 0; e->call_stream = nullptr;
@@ -413,12 +416,13 @@ extern "C" int brov_set_allocation(brov_engine_t* e, const double* alloc) {
     memcpy(e->alloc, alloc, sizeof(e->alloc));
     return BROV_OK;
 }
-extern "C" int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n) {
+extern "C" int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n, int any_current) {
     if (!e) return fail(BROV_EINVAL, "NULL engine");
     if (kp_soa_dev && n <= 0) return fail(BROV_EINVAL, "vehicle table with n = %lld", n);
     if (kp_soa_dev && model_is_di(e->model)) return fail(BROV_EUNSUPPORTED, "double-integrator engines have no per-vehicle coefficient table");
     e->pv = kp_soa_dev;
     e->pv_n = kp_soa_dev ? n : 0;
+    e->pv_current = (kp_soa_dev && any_current) ? 1 : 0;
     return BROV_OK;
 }
 extern "C" int brov_set_wrench_lag1(brov_engine_t* e, int enable) {

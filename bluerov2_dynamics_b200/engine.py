@@ -112,12 +112,13 @@ class Engine:
         """Per-vehicle (Monte-Carlo) constants: phys_table [N, NPHYS] or None to clear."""
         if phys_table is None:
             self._pv = None
-            L.check(L.lib.brov_set_vehicle_params(self._h, None, 0))
+            L.check(L.lib.brov_set_vehicle_params(self._h, None, 0, 0))
             return
         kp = derive_params(np.asarray(phys_table, float))          # [N, NKP]
         soa = torch.from_numpy(np.ascontiguousarray(kp.T)).to(self.device, self.tdtype).contiguous()  # [NKP, N]
         self._pv = soa
-        L.check(L.lib.brov_set_vehicle_params(self._h, soa.data_ptr(), soa.shape[1]))
+        any_current = bool(np.any(np.asarray(phys_table, float)[..., L.PH_CURRENT:L.PH_CURRENT + 3] != 0.0))
+        L.check(L.lib.brov_set_vehicle_params(self._h, soa.data_ptr(), soa.shape[1], int(any_current)))
 
     def set_wrench_lag1(self, enable: bool, T_lag: Optional[float] = None) -> None:
         """First-order wrench lag tau_dot = (tau_cmd - tau)/T_lag (extension; wrench models only)."""

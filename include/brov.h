@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BROV_ABI_VERSION 5
+#define BROV_ABI_VERSION 6
 
 enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2,
        /* double-integrator comparison model of the reference's evaluation tables (kinematics + a learned linear map
@@ -97,8 +97,9 @@ int brov_set_allocation(brov_engine_t* e, const double* alloc /*[6][8]*/);
  * v_dot = u K_lin, w_dot = u K_ang; K_lin, K_ang are [NU][3] row-major, NU = 8 or 6 by engine model. */
 int brov_set_di_gains(brov_engine_t* e, const double* K_lin, const double* K_ang);
 /* Per-vehicle (Monte-Carlo) coefficient table, dev, engine scalar type, layout [BROV_NKP][n]; NULL clears it.
- * The table is borrowed, not copied: it must outlive the calls that use it. */
-int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n);
+ * The table is borrowed, not copied: it must outlive the calls that use it.  any_current: non-zero if some row has a
+ * non-zero ocean current (rows KP 31..33); zero lets the kernels skip the relative-velocity terms. */
+int brov_set_vehicle_params(brov_engine_t* e, const void* kp_soa_dev, long long n, int any_current);
 /* Optional first-order wrench lag tau_dot = (tau_cmd - tau)/T_lag for the two wrench models (extension). */
 int brov_set_wrench_lag1(brov_engine_t* e, int enable);
 

@@ -736,3 +736,25 @@ def test_cfg4_monte_carlo_sweep_with_wrench_lag(B, kind):
         assert normwise(cpu(r.xT), xT[:, :nx]) < tol
         assert normwise(cpu(r.lag), xT[:, nx:]) < tol * 40      # filtered wrench, up to 40 N
         assert normwise(cpu(r.traj), snaps[:, :, :nx]) < tol
+
+
+def test_monte_carlo_per_vehicle_current(B):
+    """Per-vehicle ocean currents in the Monte-Carlo table (the relative-velocity terms are only compiled in when the
+    caller flags a non-zero current) against the oracle; and a table without currents equals the shared-constant run."""
+    rng = np.random.default_rng(8)
+    n, T = 500, 60
+    x0 = rng.uniform(-0.4, 0.4, (n, 12))
+    U = rng.uniform(-10, 10, (T, n, 6))
+    cur = rng.uniform(-0.3, 0.3, (n, 3))
+    ph = np.tile(B.default_physical(), (n, 1))
+    ph[:, 33:36] = cur
+    p = O.default_params()
+    p["current"] = cur
+    _, xT, _ = O.rollout(O.Model("wrench12", DT, p), "rk4", x0, U)
+    e = B.Engine("wrench12", "f64")
+    e.set_vehicle_physical(ph)
+    assert normwise(cpu(e.rollout(x0, U, dt=DT).xT), xT) < TOL64
+    ph[:, 33:36] = 0.0
+    e.set_vehicle_physical(ph)
+    plain = B.Engine("wrench12", "f64").rollout(x0, U, dt=DT).xT
+    assert normwise(cpu(e.rollout(x0, U, dt=DT).xT), cpu(plain)) < 1e-14

@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(KB) koop_lift_kernel(const double* __restrict_
 //   koop_liftw_kernel   P[h][k][:] = W_{H_h} phi(x_k)                     one thread per window, persistent blocks
 //   koop_fir_se_kernel  x_hat = P[h][k] + sum_t G_{H-1-t} u_{k+t}, squared error vs X[k+H]   four windows per thread
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int LWT = 384;       // threads per block of the lift kernel (one window each; 170 registers available)
+constexpr int LWT = 256;       // threads per block of the lift kernel
+constexpr int LWW = 2;         // windows per thread: every centre / decoder column read from shared memory feeds two windows
 
 template <int N, int NH>
 __global__ void __launch_bounds__(LWT, 1) koop_liftw_kernel(const double* __restrict__ X, const double* __restrict__ C,
@@ -156,44 +157,72 @@ __global__ void __launch_bounds__(LWT, 1) koop_liftw_kernel(const double* __rest
         }
     }
     __syncthreads();
-    const long long ntiles = (nwin + LWT - 1) / LWT;
+    const long long ntiles = (nwin + LWT * LWW - 1) / (LWT * LWW);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long w = tile * LWT + threadIdx.x;
-        if (w >= nwin) continue;
-        double x[N], acc[NH][N], x2 = 0.0;
+        long long v[LWW];
+        bool ok[LWW];
+        double x[LWW][N], acc[LWW][NH][N], x2[LWW];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            x[i] = __ldg(X + w * N + i);
-            x2 = fma(x[i], x[i], x2);
+        for (int j = 0; j < LWW; ++j) {
+            const long long w = tile * (LWT * LWW) + (long long)j * LWT + threadIdx.x;
+            ok[j] = w < nwin;
+            v[j] = ok[j] ? w : nwin - 1;
+            x2[j] = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                x[j][i] = __ldg(X + v[j] * N + i);
+                x2[j] = fma(x[j][i], x[j][i], x2[j]);
+            }
+#pragma unroll
+            for (int h = 0; h < NH; ++h)
+#pragma unroll
+                for (int i = 0; i < N; ++i) acc[j][h][i] = 0.0;
         }
-#pragma unroll
-        for (int h = 0; h < NH; ++h)
-#pragma unroll
-            for (int i = 0; i < N; ++i) acc[h][i] = 0.0;
 #pragma unroll
         for (int q = 0; q < N; ++q)
 #pragma unroll
             for (int h = 0; h < NH; ++h)
 #pragma unroll
-                for (int i = 0; i < N; ++i) acc[h][i] = fma(sW[((size_t)h * d + q) * N + i], x[q], acc[h][i]);
-        const double mg = -gamma;
-#pragma unroll 2
-        for (int j = 0; j < k; ++j) {
-            double dot = 0.0;
+                for (int i = 0; i < N; ++i) {
+                    const double wv = sW[((size_t)h * d + q) * N + i];
 #pragma unroll
-            for (int i = 0; i < N; ++i) dot = fma(x[i], sC[j * N + i], dot);
-            const double e = exp(mg * (x2 + sc2[j] - 2.0 * dot));
+                    for (int j = 0; j < LWW; ++j) acc[j][h][i] = fma(wv, x[j][q], acc[j][h][i]);
+                }
+        const double mg = -gamma;
+#pragma unroll 1
+        for (int c = 0; c < k; ++c) {
+            double dot[LWW];
+#pragma unroll
+            for (int j = 0; j < LWW; ++j) dot[j] = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double cv = sC[c * N + i];
+#pragma unroll
+                for (int j = 0; j < LWW; ++j) dot[j] = fma(x[j][i], cv, dot[j]);
+            }
+            const double cc = sc2[c];
+            double e[LWW];
+#pragma unroll
+            for (int j = 0; j < LWW; ++j) e[j] = exp(mg * (x2[j] + cc - 2.0 * dot[j]));
 #pragma unroll
             for (int h = 0; h < NH; ++h) {
-                const double* wc = sW + ((size_t)h * d + N + j) * N;
+                const double* wc = sW + ((size_t)h * d + N + c) * N;
 #pragma unroll
-                for (int i = 0; i < N; ++i) acc[h][i] = fma(wc[i], e, acc[h][i]);
+                for (int i = 0; i < N; ++i) {
+                    const double wv = wc[i];
+#pragma unroll
+                    for (int j = 0; j < LWW; ++j) acc[j][h][i] = fma(wv, e[j], acc[j][h][i]);
+                }
             }
         }
 #pragma unroll
-        for (int h = 0; h < NH; ++h)
+        for (int j = 0; j < LWW; ++j) {
+            if (!ok[j]) continue;
 #pragma unroll
-            for (int i = 0; i < N; ++i) P[((size_t)h * nwin + w) * N + i] = acc[h][i];
+            for (int h = 0; h < NH; ++h)
+#pragma unroll
+                for (int i = 0; i < N; ++i) P[((size_t)h * nwin + v[j]) * N + i] = acc[j][h][i];
+        }
     }
 }
 
@@ -443,7 +472,7 @@ extern "C" int brov_koopman_lift(brov_koopman_t* h, const double* X_dev, long lo
 template <int N, int NH>
 static int koop_liftw_launch(brov_koopman* h, const double* X, long long nwin, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) BROV_CUDA_TRY(cudaFuncSetAttribute(koop_liftw_kernel<N, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long ntiles = (nwin + LWT - 1) / LWT;
+    const long long ntiles = (nwin + LWT * LWW - 1) / (LWT * LWW);
     const unsigned grid = (unsigned)(ntiles < h->num_sms ? ntiles : h->num_sms);
     koop_liftw_kernel<N, NH><<<grid, LWT, smem, st>>>(X, h->C, h->c2, h->W, h->d_Hs, h->gamma, nwin, h->k, h->P);
     BROV_CUDA_TRY(cudaGetLastError());

@@ -5,7 +5,8 @@
     python bench.py --impl reference [--gpus N] [--steps K] ...     # the reference algorithm on the host CPU cores
 
 One "step" = one pass of the hot path over one batch of synthetic input: ONE rollout-kernel launch that advances
-every vehicle of the ensemble by CHUNK (=100) RK4 steps under per-vehicle random thrust inputs.  K = 100 steps is
+every vehicle of the ensemble by a chunk of RK4 steps (1000 for configs[1], 100 for configs[2]; the inputs of a whole
+10,000-step rollout do not fit HBM for configs[2]) under per-vehicle random thrust inputs.  K = 100 steps is
 the full 10,000-step rollout of BASELINE configs[1] / configs[2].
 
 Primary line (`value`, `roofline`, `e2e`): configs[1] — 65,536 vehicles per GPU, fp64, 8-thruster model with the
@@ -49,8 +50,10 @@ UNIT = "vehicle-steps/s"
 DT = 0.02
 CHUNK = 100                      # RK4 steps per launch ("step" of the bench)
 FLOP_PER_STEP = {"thruster8": 1756.0, "wrench12": 676.0, "quat13": 805.0}   # SURVEY 8(d), algorithmic
-CFG2 = dict(name="cfg2", model="thruster8", dtype="f64", n_per_gpu=65536, stride=0)
-CFG3 = dict(name="cfg3", model="thruster8", dtype="f32", n_per_gpu=1 << 20, stride=10)
+# chunk = RK4 steps per launch.  cfg2: 65,536 vehicles are 1.73 waves of resident blocks, so longer launches amortise the
+# tail (100 steps 14.0e9, 250 steps 14.8e9, 1000 steps 15.1e9 vehicle-steps/s); cfg3 is flat in the chunk length.
+CFG2 = dict(name="cfg2", model="thruster8", dtype="f64", n_per_gpu=65536, stride=0, chunk=1000)
+CFG3 = dict(name="cfg3", model="thruster8", dtype="f32", n_per_gpu=1 << 20, stride=10, chunk=100)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -199,15 +202,15 @@ def make_inputs(torch, eng, n, chunk, ring, seed):
 
 def run_rollout_leg(torch, dist, B, cfg, steps, warmup, local, world, windows):
     eng = B.Engine(cfg["model"], cfg["dtype"], device=local)
-    n, stride = cfg["n_per_gpu"], cfg["stride"]
+    n, stride, chunk = cfg["n_per_gpu"], cfg["stride"], cfg["chunk"]
     ring = 2
-    U, x0 = make_inputs(torch, eng, n, CHUNK, ring, seed=1000 + int(os.environ.get("RANK", "0")))
+    U, x0 = make_inputs(torch, eng, n, chunk, ring, seed=1000 + int(os.environ.get("RANK", "0")))
     x = x0.clone()
     lag = torch.zeros((n, 18), device=eng.device, dtype=eng.tdtype)  # allocation-projected lag carried between chunks
-    traj = [torch.empty((CHUNK // stride, n, 12), device=eng.device, dtype=eng.tdtype) for _ in range(ring)] if stride else None
+    traj = [torch.empty((chunk // stride, n, 12), device=eng.device, dtype=eng.tdtype) for _ in range(ring)] if stride else None
 
     def one(k):
-        eng.rollout(x, U[k % ring], dt=DT, integrator="rk4", lag0=lag, stride=stride, step0=k * CHUNK, xT_out=x,
+        eng.rollout(x, U[k % ring], dt=DT, integrator="rk4", lag0=lag, stride=stride, step0=k * chunk, xT_out=x,
                     lag_out=lag, traj_out=traj[k % ring] if stride else None, lag_repr="projected")
 
     for k in range(warmup):
@@ -232,8 +235,8 @@ def run_rollout_leg(torch, dist, B, cfg, steps, warmup, local, world, windows):
         dist.barrier()
     finite = bool(torch.isfinite(x).all().item())
     sz = 8 if cfg["dtype"] == "f64" else 4
-    bytes_per_launch = n * CHUNK * 8 * sz + (n * 12 * sz * (CHUNK // stride) if stride else 0) + 2 * n * 30 * sz
-    return dict(ms_total=ms, ms_per_step=ms / steps, vehicle_steps=float(n) * world * CHUNK * steps, finite=finite,
+    bytes_per_launch = n * chunk * 8 * sz + (n * 12 * sz * (chunk // stride) if stride else 0) + 2 * n * 30 * sz
+    return dict(ms_total=ms, ms_per_step=ms / steps, vehicle_steps=float(n) * world * chunk * steps, finite=finite,
                 bytes_per_launch=bytes_per_launch, n=n, eng=eng, U=U, x0=x0)
 
 
@@ -241,10 +244,11 @@ def run_e2e_leg(torch, dist, B, cfg, leg, steps, warmup, world, windows):
     """Same workload through the host-buffer API: per step, the chunk's inputs + x0 + lag go host->device from
     pinned memory and the step's final state + lag come back."""
     eng, n = leg["eng"], leg["n"]
+    chunk = min(cfg["chunk"], 250)   # 1.07 GB of inputs per call from pinned memory (keeps 8 ranks' pinned pools small)
     ring = 2
-    Uh = [B.pinned_empty((CHUNK, n, 8), eng.ndtype) for _ in range(ring)]
+    Uh = [B.pinned_empty((chunk, n, 8), eng.ndtype) for _ in range(ring)]
     for r in range(ring):
-        Uh[r][...] = leg["U"][r].cpu().numpy()
+        Uh[r][...] = leg["U"][r][:chunk].cpu().numpy()
     xh = B.pinned_empty((n, 12), eng.ndtype)
     xh[...] = leg["x0"].cpu().numpy()
     lagh = B.pinned_empty((n, 18), eng.ndtype)
@@ -252,7 +256,7 @@ def run_e2e_leg(torch, dist, B, cfg, leg, steps, warmup, world, windows):
 
     def one(k):
         eng.rollout_host(xh, Uh[k % ring], dt=DT, integrator="rk4", lag0=lagh, out_xT=xh, out_lag=lagh,
-                         chunk_steps=CHUNK // 4, lag_repr="projected")
+                         chunk_steps=max(chunk // 10, 25), lag_repr="projected")
 
     for k in range(max(1, min(warmup, 3))):
         one(k)
@@ -272,10 +276,10 @@ def run_e2e_leg(torch, dist, B, cfg, leg, steps, warmup, world, windows):
         sec = float(t.item())
     h2d = Uh[0].nbytes + xh.nbytes + lagh.nbytes
     d2h = xh.nbytes + lagh.nbytes
-    return dict(value=float(n) * world * CHUNK * steps / sec, unit=UNIT, h2d_bytes_per_step=int(h2d),
+    return dict(value=float(n) * world * chunk * steps / sec, unit=UNIT, h2d_bytes_per_step=int(h2d),
                 d2h_bytes_per_step=int(d2h), steps=steps, ms_per_step=1e3 * sec / steps,
                 h2d_gbs=h2d * steps / sec / 1e9,
-                api="Engine.rollout_host -> brov_rollout_host (C ABI), pinned host buffers, 4 sub-chunks per call "
+                api="Engine.rollout_host -> brov_rollout_host (C ABI), pinned host buffers, 250 RK4 steps per call in 10 sub-chunks "
                     "double-buffered on a copy stream")
 
 
@@ -592,9 +596,9 @@ def main_ours(args):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "BASELINE configs[1]: 65,536-vehicle ensemble per GPU, 8-thruster Fossen model with "
                                "3rd-order thruster lag, per-vehicle random thrust inputs U(-0.4,0.4), RK4, dt=0.02, "
-                               f"{args.steps * CHUNK} steps ({CHUNK} per launch), fp64",
-                   "vehicles_per_gpu": CFG2["n_per_gpu"], "rk4_steps_per_launch": CHUNK,
-                   "l2_policy": "inputs larger than L2: two 419 MB input chunks used alternately, read once per launch",
+                               f"{args.steps * CFG2['chunk']} steps ({CFG2['chunk']} per launch), fp64",
+                   "vehicles_per_gpu": CFG2["n_per_gpu"], "rk4_steps_per_launch": CFG2["chunk"],
+                   "l2_policy": "inputs larger than L2: two 4.19 GB input chunks used alternately, read once per launch",
                    "parallelism": f"vehicle-sharded x{world}, no data-path collective"},
         "roofline": roof(leg2, CFG2, fp64_peak),
         "e2e": e2e,
@@ -603,7 +607,7 @@ def main_ours(args):
         "finite": leg2["finite"] and leg3["finite"],
         "fp32": {"value": v3, "unit": UNIT, "ms_per_step": leg3["ms_per_step"], "dtype": "f32",
                  "config": {"workload": "BASELINE configs[2]: 1,048,576-vehicle ensemble per GPU, same model, fp32, "
-                                        f"{args.steps * CHUNK} RK4 steps, trajectory writeback every 10 steps",
+                                        f"{args.steps * CFG3['chunk']} RK4 steps ({CFG3['chunk']} per launch), trajectory writeback every 10 steps",
                             "vehicles_per_gpu": CFG3["n_per_gpu"],
                             "l2_policy": "two 3.36 GB input chunks used alternately"},
                  "roofline": roof(leg3, CFG3, fp32_peak), "gpu_launches": args.steps},

@@ -607,11 +607,17 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
         const long long slots = (long long)per_sm * e->num_sms;
         Q = 1;
         if (slots > 0 && a.nvblocks > slots) {
-            double best = (double)a.nvblocks / (double)(((a.nvblocks + slots - 1) / slots) * slots);
+            // Work items are handed out slice-major by a ticket, so only the LAST slice pays for the partial round:
+            // (ceil(r) - r) * steps / Q block-steps per slot with r = blocks / slots; every item costs a hand-over
+            // (state through L2, flag wait, block start) worth about 3 block-steps.  Measured on B200
+            // (profiles/f64_launch_shape.py, 512 blocks on 296 slots): 100 steps 0.515 / 0.463 / 0.482 / 0.528 ms and
+            // 400 steps 1.997 / 1.745 / 1.737 / 1.774 ms for Q = 1 / 2 / 4 / 8 — the minima of this model.
+            const double r = (double)a.nvblocks / (double)slots;
+            const double frac = std::ceil(r) - r;
+            double best = frac * a.steps + 3.0 * r;
             for (int q = 2; q <= 8 && a.steps / q >= 8; ++q) {
-                const long long items = (long long)a.nvblocks * q;
-                const double eff = (double)items / (double)(((items + slots - 1) / slots) * slots);
-                if (eff > best + 0.03) { best = eff; Q = q; }
+                const double cost = frac * a.steps / q + 3.0 * q * r;
+                if (cost < best) { best = cost; Q = q; }
             }
         }
     }

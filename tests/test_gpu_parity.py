@@ -4,6 +4,8 @@
 
 Tolerances (BASELINE.json north_star): fp64 <= 1e-10 normwise relative, ||a-b||_inf / max(||b||_inf, 1);
 fp32 <= 1e-4 after 1000 steps."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -758,3 +760,15 @@ def test_monte_carlo_per_vehicle_current(B):
     e.set_vehicle_physical(ph)
     plain = B.Engine("wrench12", "f64").rollout(x0, U, dt=DT).xT
     assert normwise(cpu(e.rollout(x0, U, dt=DT).xT), cpu(plain)) < 1e-14
+
+
+def test_randomised_parity_sweep():
+    """profiles/fuzz_parity.py: random model / integrator / size / horizon / stride / input layout / chunking / time
+    slicing / initial lag against the C oracle (150 cases here; 4 x 800 were run on the box when it was written)."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    _c_oracle()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_parity.py"), "150", "2"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "cases OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])

@@ -772,3 +772,15 @@ def test_randomised_parity_sweep():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_parity.py"), "150", "2"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "cases OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+def test_randomised_evaluator_sweep():
+    """profiles/fuzz_evaluator.py: random series lengths, horizon sets, window limits, models, integrators and
+    precisions of the sliding-window evaluator against the C oracle; carried-lag mode against the numpy oracle."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    _c_oracle()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_evaluator.py"), "80", "3"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "cases OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])

@@ -308,3 +308,50 @@ def test_koopman_multi_horizon_single_lift(KM, cg):
     five = KM.multistep_rmse_multi(X, U, [100, 1, 7, 10, 3, 250, 400])   # more than MAX_H, unsorted, one too long
     assert np.allclose(five[:2], [cg["koop_rmse"][2], cg["koop_rmse"][0]], rtol=TOL64) and np.isnan(five[-1])
     assert np.isclose(five[2], KM.multistep_rmse(X, U, 7), rtol=1e-13)
+
+
+def test_koopman_random_shapes_against_oracle():
+    """Random model sizes (n, r) in {(12,8), (12,6), (13,6)}, numbers of centres, series lengths and horizon sets."""
+    from bluerov2_dynamics_b200.Koopman.koopmanEDMDc import KoopmanEDMDc
+    rng = np.random.default_rng(40)
+    for case in range(12):
+        n, r = [(12, 8), (12, 6), (13, 6)][case % 3]
+        k = int(rng.integers(1, 300))
+        T = int(rng.integers(5, 1500))
+        C = rng.uniform(-1, 1, (k, n))
+        X = np.cumsum(0.03 * rng.standard_normal((T, n)), axis=0)
+        U = rng.uniform(-1, 1, (T, r))
+        A = 0.95 * np.linalg.qr(rng.standard_normal((n + k, n + k)))[0]
+        Bm = 0.1 * rng.standard_normal((n + k, r))
+        gam = float(rng.uniform(0.1, 2.0))
+        K = KoopmanEDMDc(state_dim=n, input_dim=r, n_rbfs=k, gamma=gam)
+        K.centers_, K.A_, K.B_ = C, A, Bm
+        hs = sorted(set(int(h) for h in rng.integers(1, min(T + 3, 90), 3)))
+        got = K.multistep_rmse_multi(X, U, hs)
+        for h, g in zip(hs, got):
+            ref = CN.koop_multistep_se(X, U, h, C, gam, A, Bm)[2]
+            assert (np.isnan(g) and np.isnan(ref)) or np.isclose(g, ref, rtol=TOL64), (case, n, r, k, T, h, g, ref)
+        h = hs[0]
+        if T > h:
+            assert np.isclose(K.multistep_rmse(X, U, h), CN.koop_multistep_se(X, U, h, C, gam, A, Bm)[2], rtol=TOL64)
+
+
+def test_pinc_random_shapes_against_oracle(PM, cg):
+    pinc, model = PM
+    rng = np.random.default_rng(41)
+    L = CN.pinc_weights(cg)
+    for case in range(6):
+        n, T = int(rng.integers(1, 1300)), int(rng.integers(1, 40))
+        stride = int(rng.choice([1, 2, 5, T]))
+        x0 = np.zeros((n, 12))
+        x0[:, :3] = rng.uniform(-2, 2, (n, 3))
+        x0[:, 5] = rng.uniform(-3, 3, n)
+        x0[:, 6:9] = rng.uniform(-0.2, 0.2, (n, 3))
+        x0[:, 11] = rng.uniform(-0.2, 0.2, n)
+        shared = bool(rng.random() < 0.4)
+        U = rng.uniform(-0.5, 0.5, (T, 8) if shared else (T, n, 8))
+        lag0 = rng.normal(0, 0.05, (n, 8, 3)) if rng.random() < 0.5 else None
+        snaps, x9, _ = CN.pinc_rollout(x0, U, 0.02, L, lag0=lag0, stride=stride)
+        traj, x9g, _ = model.rollout(x0, U, 0.02, lag0=lag0, stride=stride)
+        assert traj.shape == snaps.shape, (case, traj.shape, snaps.shape)
+        assert normwise(cpu(traj), snaps) < TOL32 and normwise(cpu(x9g), x9) < TOL32, (case, n, T, stride, shared)

@@ -784,3 +784,23 @@ def test_randomised_evaluator_sweep():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_evaluator.py"), "80", "3"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "cases OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+def test_index_space_beyond_32_bits(B):
+    """4,194,304 fp32 vehicles x 160 steps: the per-vehicle input series has 5.4e9 elements (21 GB), so every offset
+    past the first 2^32 elements needs 64-bit index arithmetic; first / middle / last vehicles against the C oracle."""
+    CO = _c_oracle()
+    n, T = 1 << 22, 160
+    e = B.Engine("thruster8", "f32")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    U = torch.rand((T, n, 8), device="cuda", generator=g) * 0.8 - 0.4
+    assert U.numel() > 2 ** 32
+    x0 = torch.zeros((n, 12), device="cuda")
+    x0[:, 5] = torch.rand(n, device="cuda", generator=g) * 6 - 3
+    r = e.rollout(x0, U, dt=DT, stride=80)
+    idx = torch.cat([torch.arange(0, 64), torch.arange(n // 2 - 32, n // 2 + 32), torch.arange(n - 64, n)])
+    snaps, xT, _ = CO.rollout("thruster8", "rk4", DT, cpu(x0[idx]), cpu(U[:, idx]), stride=80)
+    assert r.traj.shape == (2, n, 12)
+    assert normwise(cpu(r.xT[idx]), xT) < TOL32 and normwise(cpu(r.traj[:, idx]), snaps) < TOL32
+    del U, r
+    torch.cuda.empty_cache()

@@ -556,6 +556,11 @@ def main_ours(args):
     del leg3["U"], leg3["x0"], leg3["eng"]
     torch.cuda.empty_cache()
     rmse = run_rmse_leg(torch, dist, B, local, rank, world, windows) if not args.no_rmse else None
+    if rmse is not None:
+        tf = rmse["vehicle_steps_per_s"] / world * FLOP_PER_STEP["thruster8"] / 1e12   # per GPU
+        rmse["roofline"] = {"bound": "fp64_pipe", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac": tf / fp64_peak, "kernel": "brov::se_kernel<double, THRUSTER8, RK4>",
+                            "note": "per GPU; at N > 1 the timed region includes the NCCL all-reduce of the SE vector"}
     mc = run_monte_carlo_leg(torch, B, local, fp32_peak, windows) if rank == 0 and not args.no_compare else None
     compare = (run_compare_leg(torch, B, local, windows, fp32_peak, fp64_peak, cpu=not args.no_cpu_baseline)
                if rank == 0 and not args.no_compare else None)

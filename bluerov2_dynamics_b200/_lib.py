@@ -90,6 +90,7 @@ _PROTOS = {
     "brov_set_lag_discrete": (C.c_int, [C.c_void_p, C.c_double, _DP, _DP]),
     "brov_rhs": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "brov_thruster_wrench": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "brov_thruster_wrench_series": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "brov_rhs_host": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "brov_thruster_wrench_host": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "brov_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutDesc), C.c_void_p]),

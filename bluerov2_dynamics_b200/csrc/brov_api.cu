@@ -708,6 +708,33 @@ static int carry_depth(brov_engine* e, double dt, int nsub, long long* out) {
     return BROV_OK;
 }
 
+template <typename T>
+static int thruster_series_impl(brov_engine* e, long long rows, const void* u, const void* lag0, double dt, void* tau,
+                                void* lag_end, cudaStream_t st) {
+    ThrusterSeriesArgs<T> a;
+    int rc = make_consts<T>(e, dt, 1, &a.c);
+    if (rc) return rc;
+    long long depth = 0;
+    if ((rc = carry_depth(e, dt, 1, &depth))) return rc;
+    a.U = (const T*)u; a.lag0 = (const T*)lag0; a.tau = (T*)tau; a.lag_end = (T*)lag_end;
+    a.rows = rows; a.depth = (int)depth;
+    CUDA_TRY(launch_thruster_series<T>(a, st));
+    return BROV_OK;
+}
+
+extern "C" int brov_thruster_wrench_series(brov_engine_t* e, long long rows, const void* u_dev, const void* lag0_dev,
+                                           double dt, void* tau_dev, void* lag_end_dev, void* stream) {
+    if (!e) return fail(BROV_EINVAL, "NULL engine");
+    if (e->model != BROV_THRUSTER8_LAG3) return fail(BROV_EUNSUPPORTED, "brov_thruster_wrench_series needs a BROV_THRUSTER8_LAG3 engine");
+    if (rows < 0 || rows > 0x7fffffffLL) return fail(BROV_EINVAL, "rows = %lld out of range", rows);
+    if (rows == 0) return BROV_OK;
+    if (!u_dev || !tau_dev) return fail(BROV_EINVAL, "u and tau must not be NULL");
+    if (!(dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
+    CUDA_TRY(cudaSetDevice(e->device));
+    return e->dtype == BROV_F32 ? thruster_series_impl<float>(e, rows, u_dev, lag0_dev, dt, tau_dev, lag_end_dev, (cudaStream_t)stream)
+                                : thruster_series_impl<double>(e, rows, u_dev, lag0_dev, dt, tau_dev, lag_end_dev, (cudaStream_t)stream);
+}
+
 // One integrator step for n vehicles with one input row per vehicle: the body of the reference's simulate_physics loop
 // (training/train_tank_brov2_rk4.py:386-394 RK4, train_tank_brov2_full_comparison.py:462-465 Euler) as a call.
 extern "C" int brov_step(brov_engine_t* e, int integrator, long long n, const void* x_dev, const void* u_dev, double dt,

@@ -450,6 +450,52 @@ __global__ void __launch_bounds__(RHS_BLOCK) thruster_wrench_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// thruster map along a recorded input series with ONE carried lag state — what a loop over
+// rov.compute_thruster_forces(U[k], dt) produces (make_pinc_dataset, training/train_tank_brov2_rk4.py:676-696).  The lag
+// is a stable linear filter of the inputs only, so row k depends on the last `depth` rows to below one ulp: one thread
+// per row replays them (rows are independent, the series is scored in parallel).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct ThrusterSeriesArgs {
+    Consts<T> c;
+    const T* U;        // [rows][8]
+    const T* lag0;     // [8][3] state before row 0, or nullptr (zeros)
+    T* tau;            // [rows][6]
+    T* lag_end;        // [8][3] state after the last row, or nullptr
+    long long rows;
+    int depth;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(RHS_BLOCK) thruster_series_kernel(const __grid_constant__ ThrusterSeriesArgs<T> a) {
+    const long long k = (long long)blockIdx.x * RHS_BLOCK + threadIdx.x;
+    if (k >= a.rows) return;
+    T lag[24];
+    const long long first = (k >= a.depth) ? k - a.depth : 0;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) lag[j] = (first == 0 && a.lag0) ? a.lag0[j] : T(0);
+    const bool vec = (reinterpret_cast<uintptr_t>(a.U) & 15) == 0;
+    T u[8], F[8];
+    for (long long r = first; r < k; ++r) {
+        load_u<T, 8, false>(a.U + r * 8, vec, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
+        lag_advance<T, 1, false, T*>(a.c, lag, F);
+    }
+    load_u<T, 8, false>(a.U + k * 8, vec, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
+    T tau[6];
+    thruster_tau<T, 1, false, const T*>(a.c, 0, lag, F, tau);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) a.tau[k * 6 + j] = tau[j];
+    if (a.lag_end && k == a.rows - 1) {
+        lag_advance<T, 1, false, T*>(a.c, lag, F);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) a.lag_end[j] = lag[j];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // multi-horizon endpoint squared error over sliding windows
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, int INTEG>
@@ -671,5 +717,7 @@ template <typename T>
 cudaError_t launch_fma_peak(int iters, int blocks, T* scratch, cudaStream_t st);
 template <typename T>
 cudaError_t launch_thruster_wrench(const ThrusterArgs<T>& a, cudaStream_t st);
+template <typename T>
+cudaError_t launch_thruster_series(const ThrusterSeriesArgs<T>& a, cudaStream_t st);
 
 }  // namespace brov

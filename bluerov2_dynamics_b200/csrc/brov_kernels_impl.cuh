@@ -174,6 +174,13 @@ cudaError_t launch_thruster_wrench(const ThrusterArgs<T>& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <typename T>
+cudaError_t launch_thruster_series(const ThrusterSeriesArgs<T>& a, cudaStream_t st) {
+    if (a.rows <= 0) return cudaSuccess;
+    thruster_series_kernel<T><<<(unsigned)((a.rows + RHS_BLOCK - 1) / RHS_BLOCK), RHS_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 #define BROV_INSTANTIATE(T)                                                                                         \
     template cudaError_t launch_rollout<T>(int, int, bool, bool, const RolloutArgs<T>&, cudaStream_t);             \
     template int rollout_blocks_per_sm<T>(int, int, bool, bool, bool, bool);                                      \
@@ -183,6 +190,7 @@ cudaError_t launch_thruster_wrench(const ThrusterArgs<T>& a, cudaStream_t st) {
     template int se_blocks<T>(long long);                                                                          \
     template cudaError_t launch_reduced9<T>(const Red9Consts<T>&, const T*, const T*, T*, long long, cudaStream_t); \
     template cudaError_t launch_fma_peak<T>(int, int, T*, cudaStream_t);                                           \
-    template cudaError_t launch_thruster_wrench<T>(const ThrusterArgs<T>&, cudaStream_t);
+    template cudaError_t launch_thruster_wrench<T>(const ThrusterArgs<T>&, cudaStream_t);                          \
+    template cudaError_t launch_thruster_series<T>(const ThrusterSeriesArgs<T>&, cudaStream_t);
 
 }  // namespace brov

@@ -191,6 +191,20 @@ class Engine:
                                                float(dt), out.data_ptr(), self._stream()))
         return out
 
+    def thruster_wrench_series(self, U, lag0=None, dt: float = 0.02):
+        """Body wrench of every row of an input series U [T,8] under ONE lag state carried from row to row — the loop
+        `[rov.compute_thruster_forces(u, dt) for u in U]` as one launch.  Returns (tau [T,6], lag_end [24])."""
+        U = self.tensor(U)
+        self._check_rows(U, 8, "U")
+        T_ = U.shape[0]
+        l0 = self.tensor(lag0).reshape(24) if lag0 is not None else None
+        tau = torch.empty((T_, 6), device=self.device, dtype=self.tdtype)
+        lag_end = torch.zeros(24, device=self.device, dtype=self.tdtype) if l0 is None else l0.clone()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_thruster_wrench_series(self._h, T_, U.data_ptr(), l0.data_ptr() if l0 is not None else None,
+                                                      float(dt), tau.data_ptr(), lag_end.data_ptr(), self._stream()))
+        return tau, lag_end
+
     def rhs_host(self, x: np.ndarray, u: np.ndarray, lag: Optional[np.ndarray] = None, dt: float = 0.02) -> np.ndarray:
         """`rhs` with numpy arrays in host memory (engine dtype): one pinned staging copy each way inside the library,
         no torch tensors — the low-latency path behind the model mirrors' per-call `dynamics()`.  `lag` [N,24]

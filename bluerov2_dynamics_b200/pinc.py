@@ -63,6 +63,24 @@ def thrusters_to_body_wrenches(U8_row: np.ndarray, dt: float, old_model_obj) -> 
     return np.array([tau6[0], tau6[1], tau6[2], tau6[5]], dtype=float)
 
 
+def make_pinc_dataset(X12: np.ndarray, U8: np.ndarray, dt: float, old6):
+    """(x9_k, u4_k, dt) -> x9_{k+1} training pairs of the PINc network: returns (z_in [N-1,14], y [N-1,9], U4 [N,4])
+    like the reference (training/train_tank_brov2_rk4.py:676-696).  The thruster map runs along the whole series with
+    `old6`'s lag state carried from row to row — one launch (Engine.thruster_wrench_series) instead of N Python calls —
+    and `old6` is left with the lag state after the last row."""
+    X12 = np.asarray(X12, dtype=float)
+    U8 = np.asarray(U8, dtype=float)
+    eng = old6.engine("f64")
+    lag0 = _rov_lag(old6)
+    tau, lag_end = eng.thruster_wrench_series(U8, lag0=lag0, dt=dt)
+    if len(U8):
+        old6._store_lag(lag_end.reshape(1, 24), dt)
+    U4 = tau[:, [0, 1, 2, 5]].cpu().numpy()
+    X9 = batch12_to_9(X12)
+    z_in = np.hstack([X9[:-1], U4[:-1], np.full((len(X9) - 1, 1), dt, dtype=float)])
+    return z_in, X9[1:], U4
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # the network
 # ----------------------------------------------------------------------------------------------------------------------

@@ -123,6 +123,14 @@ int brov_rhs(brov_engine_t* e, long long n, const void* x_dev, const void* u_dev
 int brov_thruster_wrench(brov_engine_t* e, long long n, const void* u_dev, void* lag_inout_dev, double dt,
                          void* tau_dev, void* stream);
 
+/* Thruster map along a recorded input series with ONE carried lag state — the loop
+ * `[rov.compute_thruster_forces(u, dt) for u in U]` (make_pinc_dataset, training/train_tank_brov2_rk4.py:676-696) as one
+ * launch: u [rows][8], tau [rows][6]; lag0 [8][3] = lag state before row 0 or NULL (zeros); lag_end [8][3] = state after
+ * the last row or NULL.  Rows are evaluated in parallel by replaying, per row, the tail of the input history that the
+ * stable lag filter still remembers (brov_se_carry_steps(e, dt, BROV_EULER) rows). */
+int brov_thruster_wrench_series(brov_engine_t* e, long long rows, const void* u_dev, const void* lag0_dev, double dt,
+                                void* tau_dev, void* lag_end_dev, void* stream);
+
 /* The same two calls with every array in HOST memory (engine scalar type): what a model object's `dynamics()` /
  * `compute_thruster_forces()` costs per call is launch latency, so inputs and outputs travel in one pinned staging
  * buffer each way and the call returns after the results have landed.  lag_inout_host as above ([n][8][3] or NULL). */

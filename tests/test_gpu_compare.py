@@ -355,3 +355,34 @@ def test_pinc_random_shapes_against_oracle(PM, cg):
         traj, x9g, _ = model.rollout(x0, U, 0.02, lag0=lag0, stride=stride)
         assert traj.shape == snaps.shape, (case, traj.shape, snaps.shape)
         assert normwise(cpu(traj), snaps) < TOL32 and normwise(cpu(x9g), x9) < TOL32, (case, n, T, stride, shared)
+
+
+def test_make_pinc_dataset_series_thruster_map(PM, golden, cg):
+    """make_pinc_dataset: the thruster map along the whole series with a carried lag state in ONE launch equals the
+    reference's loop of stateful compute_thruster_forces calls, and leaves the model object's lag where the loop does."""
+    pinc, _ = PM
+    from bluerov2_dynamics_b200.fossen.BlueROV2 import BlueROV2
+    X12, U8, dt = golden["rmse_X12"], golden["rmse_U8"], float(cg["cmp_dt"])
+    rov = BlueROV2(dt=dt)
+    z_in, y, U4 = pinc.make_pinc_dataset(X12, U8, dt, rov)
+    assert normwise(U4, cg["pinc_U4_carry"]) < TOL64
+    assert normwise(z_in, cg["pinc_dataset_zin"]) < TOL64 and normwise(y, cg["pinc_dataset_y"]) < TOL64
+    ref = BlueROV2(dt=dt)
+    for u in U8:
+        ref.compute_thruster_forces(u, dt)
+    assert normwise(np.stack([l._x for l in rov.thruster_lags]), np.stack([l._x for l in ref.thruster_lags])) < 1e-12
+    # a long series (far beyond the replay depth) and a non-zero initial lag state, fp32 and fp64, against the oracle
+    import bluerov2_dynamics_b200 as B
+    from oracle import fossen_np as O
+    rng = np.random.default_rng(6)
+    T = 5000
+    U = O.smooth_inputs(rng, T, 8, sigma=0.05)
+    lag0 = rng.normal(0, 0.1, (8, 3))
+    m = O.Model("thruster8", dt)
+    lag, rows = lag0[None].copy(), []
+    for u in U:
+        tau, lag = O.thruster_wrench(u[None], lag, m.Ad, m.Bd, m.alloc)
+        rows.append(tau[0])
+    for dtype, tol in (("f64", TOL64), ("f32", TOL32)):
+        tau_g, lag_g = B.Engine("thruster8", dtype).thruster_wrench_series(U, lag0=lag0.reshape(24), dt=dt)
+        assert normwise(cpu(tau_g), np.array(rows)) < tol and normwise(cpu(lag_g).reshape(8, 3), lag[0]) < tol

@@ -35,10 +35,16 @@ for dtype in ("f64", "f32"):
             e.rollout(x0, U, dt=dt, integrator=integ, stride=3, time_slices=3)
             assert torch.isfinite(r.xT).all() and torch.isfinite(r2.xT).all()
         e.rhs(x0, U[0])
+        e.step(x0, U[0], dt=dt, integrator="euler")
+        if model != "thruster8":
+            e.rhs_host(x0.astype(e.ndtype), U[0].astype(e.ndtype), dt=dt)
         X = r.traj[:, 0, :].contiguous()
         e.multistep_rmse(np.tile(X.cpu().numpy(), (8, 1)), np.tile(U[:X.shape[0], 0], (8, 1)), [1, 3, 7], dt=dt)
         if model == "thruster8":
             e.thruster_wrench(U[0], lag=torch.zeros((n, 24), device="cuda", dtype=e.tdtype), dt=dt)
+            e.thruster_wrench_series(U[:, 0], lag0=np.full(24, 0.01), dt=dt)
+            e.thruster_wrench_host(U[0].astype(e.ndtype), lag=np.zeros((n, 24), e.ndtype), dt=dt)
+            e.rhs_host(x0.astype(e.ndtype), U[0].astype(e.ndtype), lag=np.zeros((n, 24), e.ndtype), dt=dt)
             e.multistep_rmse(np.tile(X.cpu().numpy(), (60, 1)), np.tile(U[:X.shape[0], 0], (60, 1)), 5, dt=dt,
                              lag_mode="carry")
             xh, uh = x0.astype(e.ndtype), U.astype(e.ndtype)
@@ -62,6 +68,7 @@ K.B_ = 0.1 * rng.standard_normal((n + k, r))
 Xk, Uk = np.cumsum(0.05 * rng.standard_normal((T, n)), axis=0), rng.uniform(-1, 1, (T, r))
 for H in (1, 7, 150):
     assert np.isfinite(K.multistep_rmse(Xk, Uk, H))
+K.multistep_rmse_multi(Xk, Uk, [1, 7, 150, 2, 33])
 K.simulate(Xk[0], Uk[:77])
 K.simulate_batch(Xk[:5], Uk[:33])
 K._lift(Xk[:19])

@@ -19,7 +19,9 @@ from . import fossen_np as O
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "libbrov_oracle.so")
+_PATH_FMA = os.path.join(_HERE, "libbrov_oracle_fma.so")   # same code, FMA contraction allowed (conditioning studies)
 _lib = None
+_libs = {}
 
 MODEL_ID = {"thruster8": 0, "wrench12": 1, "quat13": 2}
 _PH_NAMES_ADDED = ["Xu_dot", "Yv_dot", "Zw_dot", "Kp_dot", "Mq_dot", "Nr_dot"]
@@ -31,20 +33,30 @@ def available() -> bool:
     return os.path.exists(_PATH)
 
 
-def lib():
+def lib(fma: bool = False):
     global _lib
+    if fma:
+        if "fma" not in _libs:
+            if not os.path.exists(_PATH_FMA):
+                raise RuntimeError(f"{_PATH_FMA} not built: run `make -C oracle`")
+            _libs["fma"] = _bind(C.CDLL(_PATH_FMA))
+        return _libs["fma"]
     if _lib is None:
         if not available():
             raise RuntimeError(f"{_PATH} not built: run `make -C oracle`")
-        L = C.CDLL(_PATH)
+        _lib = _bind(C.CDLL(_PATH))
+    return _lib
+
+
+def _bind(L):
+    if True:
         dp, ll, i, d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
         L.brov_oracle_rollout.argtypes = [i, i, ll, ll, d, dp, i, dp, dp, dp, dp, dp, dp, i, dp, dp, ll]
         L.brov_oracle_rollout.restype = i
         L.brov_oracle_multistep_se.argtypes = [i, i, ll, ll, d, dp, dp, dp, dp, dp, dp, dp]
         L.brov_oracle_multistep_se.restype = d
         L.brov_oracle_threads.restype = i
-        _lib = L
-    return _lib
+    return L
 
 
 def threads() -> int:
@@ -86,9 +98,11 @@ def _model_consts(kind, dt):
     return (np.ascontiguousarray(Ad), np.ascontiguousarray(Bd), np.ascontiguousarray(r), np.ascontiguousarray(e))
 
 
-def rollout(kind: str, integ: str, dt: float, x0, U, params: dict | None = None, lag0=None, stride: int = 0):
-    """Same contract as fossen_np.rollout: x0 [N,nx]; U [T,N,nu] or [T,nu]; returns (snaps [S,N,nx], xT, lagT)."""
-    L = lib()
+def rollout(kind: str, integ: str, dt: float, x0, U, params: dict | None = None, lag0=None, stride: int = 0,
+            fma: bool = False):
+    """Same contract as fossen_np.rollout: x0 [N,nx]; U [T,N,nu] or [T,nu]; returns (snaps [S,N,nx], xT, lagT).
+    fma=True runs the FMA-contracted build of the same code (a second valid rounding, for conditioning studies)."""
+    L = lib(fma)
     x = np.array(x0, float, ndmin=2, order="C")
     N, nx = x.shape
     U = np.ascontiguousarray(U, float)

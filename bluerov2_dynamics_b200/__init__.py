@@ -15,7 +15,7 @@ CPU fallback — importing this package without the built library raises.
 """
 import importlib as _importlib
 
-__all__ = ["Engine", "RolloutResult", "BrovError", "default_physical", "derive_params", "default_allocation",
+__all__ = ["Engine", "RolloutResult", "InputGenerator", "BrovError", "default_physical", "derive_params", "default_allocation",
            "lag_discretize", "reduced9_rhs", "fma_peak", "pinned_empty", "install_as_fossen", "LIB_PATH"]
 
 _FROM_LIB = ("BrovError", "LIB_PATH")

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BROV_LIB") or os.path.join(_HERE, "libbrov.so")  # BROV_LIB: a tuning variant
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 THRUSTER8_LAG3, WRENCH_EULER12, WRENCH_QUAT13 = 0, 1, 2
 DI_EULER12_U8, DI_EULER12_U6, DI_QUAT13_U6 = 3, 4, 5
 F64, F32 = 0, 1
@@ -25,13 +25,28 @@ class BrovError(RuntimeError):
     pass
 
 
+class InputGen(C.Structure):
+    """brov_input_gen: the in-kernel command-signal generator (see include/brov.h)."""
+    _fields_ = [("enable", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64), ("vehicle0", C.c_longlong),
+                ("rho", C.c_double), ("sigma", C.c_double), ("clip", C.c_double), ("scale", C.c_double * 8),
+                ("state_in_dev", C.c_void_p), ("state_out_dev", C.c_void_p)]
+
+
 class RolloutDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("integrator", C.c_int32), ("n", C.c_longlong), ("steps", C.c_longlong),
                 ("dt", C.c_double), ("x0_dev", C.c_void_p), ("xT_dev", C.c_void_p), ("u_dev", C.c_void_p),
                 ("u_stride_t", C.c_longlong), ("u_stride_n", C.c_longlong), ("lag_in_dev", C.c_void_p),
                 ("lag_out_dev", C.c_void_p), ("traj_dev", C.c_void_p), ("stride", C.c_longlong),
                 ("step0", C.c_longlong), ("snap_base", C.c_longlong), ("lag_in_repr", C.c_int32),
-                ("lag_out_repr", C.c_int32), ("time_slices", C.c_int32), ("reserved0", C.c_int32)]
+                ("lag_out_repr", C.c_int32), ("time_slices", C.c_int32), ("min_abs_cos_accumulate", C.c_int32),
+                ("health_dev", C.c_void_p), ("min_abs_cos_dev", C.c_void_p), ("singular_eps", C.c_double),
+                ("gen", InputGen)]
+
+
+class GenInputsDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("dtype", C.c_int32), ("nu", C.c_int32), ("device", C.c_int32),
+                ("first", C.c_longlong), ("vstride", C.c_longlong), ("n_sel", C.c_longlong),
+                ("step0", C.c_longlong), ("steps", C.c_longlong), ("gen", InputGen), ("out_dev", C.c_void_p)]
 
 
 class SeDesc(C.Structure):
@@ -40,7 +55,8 @@ class SeDesc(C.Structure):
                 ("lag0_dev", C.c_void_p), ("n_horizons", C.c_int32), ("horizons", C.c_int32 * MAX_H),
                 ("se_out_dev", C.c_void_p), ("count_out", C.POINTER(C.c_longlong)), ("workspace_dev", C.c_void_p),
                 ("workspace_bytes", C.c_size_t), ("lag_carry", C.c_int32), ("reserved", C.c_int32),
-                ("window0", C.c_longlong), ("row0", C.c_longlong)]
+                ("window0", C.c_longlong), ("row0", C.c_longlong), ("health_dev", C.c_void_p),
+                ("singular_eps", C.c_double)]
 
 
 class RolloutHostDesc(C.Structure):
@@ -48,7 +64,8 @@ class RolloutHostDesc(C.Structure):
                 ("dt", C.c_double), ("x0_host", C.c_void_p), ("xT_host", C.c_void_p), ("u_host", C.c_void_p),
                 ("u_shared", C.c_int32), ("reserved", C.c_int32), ("lag_in_host", C.c_void_p),
                 ("lag_out_host", C.c_void_p), ("traj_host", C.c_void_p), ("stride", C.c_longlong),
-                ("chunk_steps", C.c_longlong), ("lag_in_repr", C.c_int32), ("lag_out_repr", C.c_int32)]
+                ("chunk_steps", C.c_longlong), ("lag_in_repr", C.c_int32), ("lag_out_repr", C.c_int32),
+                ("gen", InputGen), ("health_host", C.POINTER(C.c_ulonglong)), ("singular_eps", C.c_double)]
 
 
 class PincWeights(C.Structure):
@@ -94,6 +111,7 @@ _PROTOS = {
     "brov_rhs_host": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "brov_thruster_wrench_host": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "brov_rollout": (C.c_int, [C.c_void_p, C.POINTER(RolloutDesc), C.c_void_p]),
+    "brov_generate_inputs": (C.c_int, [C.POINTER(GenInputsDesc), C.c_void_p]),
     "brov_step": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "brov_se_workspace_bytes": (C.c_size_t, [C.c_longlong]),
     "brov_multistep_se": (C.c_int, [C.c_void_p, C.POINTER(SeDesc), C.c_void_p]),

@@ -7,6 +7,7 @@ travels to the GPU box with the repository snapshot (it is git-ignored, not gpur
 """
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
@@ -18,7 +19,6 @@ CSRC = os.path.join(PKG, "csrc")
 OUT = os.path.join(PKG, "libbrov.so")
 BUILD = os.path.join(PKG, "build")
 SOURCES = ["brov_api.cu", "brov_kernels_f32.cu", "brov_kernels_f64.cu", "brov_koopman.cu", "brov_pinc.cu"]
-HEADERS = ["brov_device.cuh", "brov_kernels.cuh", "brov_kernels_impl.cuh", "brov_internal.cuh", os.path.join("..", "..", "include", "brov.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -34,7 +34,10 @@ def _stale() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    # every source and header of the library, whatever it is called (a header missing from a hand-kept list once let a
+    # stale binary through)
+    deps = glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        [os.path.join(PKG, "..", "include", "brov.h"), os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -2,6 +2,7 @@
 // precision (mass matrix inverse, Coriolis coefficient differences, thruster allocation from the reference's
 // geometry formula, zero-order-hold discretisation of the thruster lag and its closed form over the sub-steps of an
 // integrator step), argument validation, kernel launches, and the host-buffer streaming rollout.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -57,7 +58,11 @@ struct LagDisc {
 
 struct HostStage {  // resources of brov_rollout_host, grown on demand
     void* d_x = nullptr;
-    void* d_lag = nullptr;
+    void* d_lag = nullptr;       // carried between chunks: allocation-projected [n][18] (thruster model) / [n][6]
+    void* d_lag24 = nullptr;     // per-thruster states [n][24]: caller's lag_in, then the rebuilt lag_out
+    void* d_gen = nullptr;       // AR(1) state of generated inputs [n][NU]
+    void* d_health = nullptr;    // unsigned long long[2] + per-vehicle running min |cos theta| [n]
+    size_t cap_lag24 = 0, cap_gen = 0, cap_health = 0;
     void* d_u[2] = {nullptr, nullptr};
     void* d_traj[2] = {nullptr, nullptr};
     size_t cap_x = 0, cap_lag = 0, cap_u = 0, cap_traj = 0;
@@ -80,6 +85,11 @@ struct brov_engine {
     int num_sms;
     int* d_sched;        // [1 + nvblocks] ticket counter + per-vehicle-block progress flags (temporal tiling)
     size_t cap_sched;    // in ints
+    // engine-owned scratch of brov_rollout (grown on demand): hand-over of the lag / generator state between time slices
+    // when the caller passes no buffer of the right shape, running min |cos theta| for the health counters, and the
+    // generator state snapshot the per-thruster lag epilogue restarts from
+    void* d_scratch[4];
+    size_t cap_scratch[4];
     // staging of the host-buffer single-call entry points (brov_rhs_host, brov_thruster_wrench_host)
     void* call_pinned;   // pinned host buffer
     void* call_dev;      // device mirror
@@ -296,31 +306,6 @@ static int make_consts(brov_engine* e, double dt, int nsub, Consts<T>* c) {
             c->lagB[a] = (T)(double)sb;
         }
     }
-    // operand pairs of the packed-FP32 step (PK_* layout of brov_device_f32x2.cuh)
-    {
-        T* pk = c->pk;
-        auto splat = [&](int pair, T v) { pk[2 * pair] = v; pk[2 * pair + 1] = v; };
-        for (int i = 0; i < 5; ++i) splat(PK_POLY + i, c->poly[i]);
-        for (int j = 0; j < 4; ++j) {
-            for (int b = 0; b < 3; ++b) splat(PK_LAGG + 4 * j + b, c->lagG[j][b]);
-            splat(PK_LAGG + 4 * j + 3, c->lagH[j]);
-        }
-        for (int k = 0; k < 3; ++k) {
-            for (int b = 0; b < 3; ++b) splat(PK_LAGA + 4 * k + b, c->lagA[k][b]);
-            splat(PK_LAGA + 4 * k + 3, c->lagB[k]);
-        }
-        for (int i = 0; i < 6; ++i) {
-            pk[2 * PK_DL + i] = c->kp[KP_DL + i];
-            pk[2 * PK_DQ + i] = c->kp[KP_DQ + i];
-            pk[2 * PK_MINV + i] = c->kp[KP_MINV + i];
-        }
-        const double rot[6] = {8.3333333e-3, -1.6666667e-1, -1.3888889e-3, 4.1666667e-2, -0.5, 1.0};
-        for (int i = 0; i < 6; ++i) splat(PK_ROT + i, (T)rot[i]);
-        splat(PK_RK + 0, (T)0.5 * c->dt);
-        splat(PK_RK + 1, c->dt);
-        splat(PK_RK + 2, c->dt * (T)(1.0 / 6.0));
-        splat(PK_RK + 3, (T)2);
-    }
     return BROV_OK;
 }
 
@@ -341,6 +326,7 @@ extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out
     e->use_lag1 = 0; e->pv = nullptr; e->pv_n = 0; e->pv_current = 0;
     e->lag_cache.dt = -1.0;
     e->num_sms = prop.multiProcessorCount; e->d_sched = nullptr; e->cap_sched = 0;
+    for (int i = 0; i < 4; ++i) { e->d_scratch[i] = nullptr; e->cap_scratch[i] = 0; }
     e->call_pinned = nullptr; e->call_dev = nullptr; e->cap_call = 0; e->call_stream = nullptr;
     double ph[BROV_NPHYS];
     brov_default_physical(1000.0, ph);
@@ -354,7 +340,7 @@ extern "C" int brov_create(int model, int dtype, int device, brov_engine_t** out
 static void hs_release(brov_engine* e) {
     HostStage& h = e->hs;
     cudaSetDevice(e->device);
-    cudaFree(h.d_x); cudaFree(h.d_lag);
+    cudaFree(h.d_x); cudaFree(h.d_lag); cudaFree(h.d_lag24); cudaFree(h.d_gen); cudaFree(h.d_health);
     for (int b = 0; b < 2; ++b) {
         cudaFree(h.d_u[b]); cudaFree(h.d_traj[b]);
         if (h.ev_in[b]) cudaEventDestroy(h.ev_in[b]);
@@ -371,6 +357,7 @@ extern "C" void brov_destroy(brov_engine_t* e) {
     if (!e) return;
     hs_release(e);
     if (e->d_sched) cudaFree(e->d_sched);
+    for (int i = 0; i < 4; ++i) if (e->d_scratch[i]) cudaFree(e->d_scratch[i]);
     if (e->call_pinned) cudaFreeHost(e->call_pinned);
     if (e->call_dev) cudaFree(e->call_dev);
     if (e->call_stream) cudaStreamDestroy(e->call_stream);
@@ -576,34 +563,106 @@ extern "C" int brov_thruster_wrench_host(brov_engine_t* e, long long n, const vo
     return BROV_OK;
 }
 
+static int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return BROV_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    cudaError_t er = cudaMalloc(p, need);
+    if (er != cudaSuccess) return fail(BROV_ENOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(er));
+    *cap = need;
+    return BROV_OK;
+}
+enum { SCR_LAG = 0, SCR_GEN = 1, SCR_MINCOS = 2, SCR_GENSNAP = 3 };
+static int scratch(brov_engine* e, int which, size_t bytes, void** out) {
+    int rc = grow(&e->d_scratch[which], &e->cap_scratch[which], bytes);
+    *out = e->d_scratch[which];
+    return rc;
+}
+
+static int carry_depth(brov_engine* e, double dt, int nsub, long long* out);
+
 template <typename T>
-static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t st) {
+static int fill_gen(const brov_input_gen& g, int nu, InputGen<T>* out) {
+    memset(out, 0, sizeof(*out));
+    if (!g.enable) return BROV_OK;
+    if (!(g.rho >= 0.0 && g.rho <= 1.0) || !(g.sigma >= 0.0) || !(g.clip > 0.0) || !std::isfinite(g.sigma))
+        return fail(BROV_EINVAL, "input generator: need 0 <= rho <= 1, sigma >= 0, clip > 0");
+    if (g.vehicle0 < 0) return fail(BROV_EINVAL, "input generator: vehicle0 < 0");
+    out->on = 1;
+    out->rho = (T)g.rho;
+    for (int j = 0; j < 8; ++j) {
+        const double sc = j < nu ? g.scale[j] : 0.0;
+        if (!(sc >= 0.0) || !std::isfinite(sc)) return fail(BROV_EINVAL, "input generator: scale[%d] must be finite and >= 0", j);
+        out->sigma[j] = (T)(g.sigma * sc);
+        out->clip[j] = (T)(std::isfinite(g.clip) ? g.clip * sc : g.clip);
+    }
+    out->vehicle0 = (unsigned long long)g.vehicle0;
+    out->k0 = (uint32_t)(g.seed & 0xffffffffu);
+    out->k1 = (uint32_t)(g.seed >> 32);
+    out->state_in = (const T*)g.state_in_dev;
+    out->state_out = (T*)g.state_out_dev;
+    return BROV_OK;
+}
+
+// Per-thruster lag epilogue of a rollout call (thruster model): out = state of the eight ThrusterLag filters after the
+// call; in = their state before it (NULL = zeros; only consulted by calls of at most `depth` steps).
+struct Lag24 {
+    const void* in;
+    void* out;
+};
+
+template <typename T>
+static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t st, Lag24 l24) {
     const int NX = model_nx(e->model), NU = model_nu(e->model);
+    const bool thr = e->model == BROV_THRUSTER8_LAG3;
+    const int nsub = d->integrator == BROV_RK4 ? 4 : 1;
     RolloutArgs<T> a;
-    int rc = make_consts<T>(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &a.c);
+    memset(&a, 0, sizeof(a));
+    int rc = make_consts<T>(e, d->dt, nsub, &a.c);
     if (rc) return rc;
+    if ((rc = fill_gen<T>(d->gen, NU, &a.gen))) return rc;
+    const bool gen = a.gen.on != 0;
     a.x0 = (const T*)d->x0_dev; a.xT = (T*)d->xT_dev; a.U = (const T*)d->u_dev;
     a.u_stride_t = d->u_stride_t; a.u_stride_n = d->u_stride_n;
-    a.lag_in = (const T*)d->lag_in_dev; a.lag_out = (T*)d->lag_out_dev;
     a.pv = (const T*)e->pv;
     a.traj = (T*)d->traj_dev;
     a.snap_base = d->snap_base; a.step0 = d->step0;
     a.n = (int)d->n; a.steps = (int)d->steps; a.stride = (int)(d->traj_dev ? d->stride : 1);
-    const bool lagw = e->model == BROV_THRUSTER8_LAG3 && (d->lag_out_repr == BROV_LAG_PROJECTED || d->lag_out_dev == nullptr);
-    a.lag_in_w = (e->model == BROV_THRUSTER8_LAG3 && d->lag_in_repr == BROV_LAG_PROJECTED) ? 1 : 0;
     const size_t ualign = (sizeof(T) == 4 && NU == 6) ? 8 : 16;
-    a.u_vec = aligned(d->u_dev, ualign) && (d->u_stride_t * sizeof(T)) % ualign == 0 && (d->u_stride_n * sizeof(T)) % ualign == 0;
+    a.u_vec = !gen && aligned(d->u_dev, ualign) && (d->u_stride_t * sizeof(T)) % ualign == 0 && (d->u_stride_n * sizeof(T)) % ualign == 0;
+    // per-vehicle time-major series with 16-byte aligned rows of 32 vehicles: the TMA bulk ring
+    a.u_tma = !gen && d->u_stride_n == NU && d->u_stride_t > 0 && aligned(d->u_dev, 16) && (d->u_stride_t * sizeof(T)) % 16 == 0;
     a.traj_vec = d->traj_dev && aligned(d->traj_dev, 16) && ((size_t)d->n * NX * sizeof(T)) % 16 == 0;
+
+    // lag state.  The thruster model integrates the allocation-projected filters; per-thruster states for the caller
+    // come from the epilogue below.
+    const bool has_lag = thr || e->use_lag1;
+    const int nl_kernel = thr ? 18 : 6;
+    const bool want_thr_out = thr && l24.out != nullptr;
+    a.lag_in = has_lag ? (const T*)d->lag_in_dev : nullptr;
+    a.lag_in_w = (thr && d->lag_in_repr == BROV_LAG_PROJECTED) ? 1 : 0;
+    a.lag_out = has_lag ? (thr ? (d->lag_out_repr == BROV_LAG_PROJECTED ? (T*)d->lag_out_dev : nullptr) : (T*)d->lag_out_dev) : nullptr;
+    long long depth = 0;
+    if (want_thr_out) {
+        if ((rc = carry_depth(e, d->dt, nsub, &depth))) return rc;
+        if (d->lag_in_dev && d->lag_in_repr == BROV_LAG_PROJECTED && !l24.in && d->steps < depth)
+            return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in in a call of fewer than %lld steps", depth);
+    }
+
+    // health accounting
+    a.health.counters = (unsigned long long*)d->health_dev;
+    a.health.eps = d->singular_eps > 0.0 ? d->singular_eps : 1e-3;
+    a.mincos = (T*)d->min_abs_cos_dev;
+    a.mincos_init = d->min_abs_cos_accumulate ? 0 : 1;
+    if (d->health_dev) CUDA_TRY(cudaMemsetAsync(d->health_dev, 0, 2 * sizeof(unsigned long long), st));
+
     // Temporal tiling: when the vehicle blocks do not fill a whole number of waves of resident slots, cut the launch
     // into time slices so that ceil(blocks*Q/slots) rounds of steps/Q replace ceil(blocks/slots) rounds of steps.
-    const int bt = rollout_block_threads<T>();
-    a.nvblocks = (a.n + bt - 1) / bt;
+    a.nvblocks = (a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK;
     a.quanta = 1; a.ticket = nullptr; a.progress = nullptr;
-    const bool has_lag = (e->model == BROV_THRUSTER8_LAG3) || e->use_lag1;
-    const bool can_slice = a.steps >= 16 && (!has_lag || d->lag_out_dev != nullptr);
+    const bool can_slice = a.steps >= 16;
     int Q = d->time_slices;
     if (Q == 0 && can_slice) {
-        const int per_sm = rollout_blocks_per_sm<T>(e->model, d->integrator, e->use_lag1 != 0, lagw, e->pv != nullptr, d->traj_dev != nullptr);
+        const int per_sm = rollout_blocks_per_sm<T>(e->model, d->integrator, e->use_lag1 != 0, e->pv != nullptr, gen, d->traj_dev != nullptr);
         const long long slots = (long long)per_sm * e->num_sms;
         Q = 1;
         if (slots > 0 && a.nvblocks > slots) {
@@ -633,8 +692,41 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
         }
         CUDA_TRY(cudaMemsetAsync(e->d_sched, 0, need * sizeof(int), st));
         a.quanta = Q; a.ticket = e->d_sched; a.progress = e->d_sched + 1;
+        // slices hand their state over through xT and the lag / generator / min-cos arrays: scratch where the caller
+        // gave none
+        void* p = nullptr;
+        if (has_lag && !a.lag_out) { if ((rc = scratch(e, SCR_LAG, (size_t)a.n * nl_kernel * sizeof(T), &p))) return rc; a.lag_out = (T*)p; }
+        if (gen && !a.gen.state_out) { if ((rc = scratch(e, SCR_GEN, (size_t)a.n * NU * sizeof(T), &p))) return rc; a.gen.state_out = (T*)p; }
     }
-    CUDA_TRY(launch_rollout<T>(e->model, d->integrator, e->use_lag1 != 0, lagw, a, st));
+    if (a.health.counters && !a.mincos && a.quanta > 1) {
+        void* p = nullptr;
+        if ((rc = scratch(e, SCR_MINCOS, (size_t)a.n * sizeof(T), &p))) return rc;
+        a.mincos = (T*)p; a.mincos_init = 1;
+    }
+    // generated inputs + per-thruster lag_out: the epilogue restarts the generator from the AR(1) state before its
+    // first replayed step, which the rollout kernel snapshots on the way
+    const long long tail_first = want_thr_out ? (d->steps > depth ? d->steps - depth : 0) : 0;
+    if (want_thr_out && gen && tail_first > 0) {
+        void* p = nullptr;
+        if ((rc = scratch(e, SCR_GENSNAP, (size_t)a.n * NU * sizeof(T), &p))) return rc;
+        a.gen_snap = (T*)p; a.gen_snap_step = (int)tail_first;
+    }
+    CUDA_TRY(launch_rollout<T>(e->model, d->integrator, e->use_lag1 != 0, a, st));
+
+    if (want_thr_out) {
+        LagTailArgs<T> t;
+        memset(&t, 0, sizeof(t));
+        t.c = a.c;
+        t.gen = a.gen;
+        t.U = a.U; t.u_stride_t = a.u_stride_t; t.u_stride_n = a.u_stride_n;
+        // a call of at most `depth` steps continues from the caller's per-thruster state; a longer one has forgotten it
+        t.lag_in = tail_first == 0 ? (const T*)l24.in : nullptr;
+        t.lag_out = (T*)l24.out;
+        t.gen_state = tail_first > 0 ? a.gen_snap : (const T*)d->gen.state_in_dev;
+        t.step0 = d->step0;
+        t.n = a.n; t.first = (int)tail_first; t.steps = a.steps;
+        CUDA_TRY(launch_lag_tail<T>(t, st));
+    }
     return BROV_OK;
 }
 
@@ -642,12 +734,20 @@ static int check_rollout_common(brov_engine* e, int integrator, long long n, lon
     if (!e) return fail(BROV_EINVAL, "NULL engine");
     if (integrator != BROV_RK4 && integrator != BROV_EULER) return fail(BROV_EINVAL, "unknown integrator %d", integrator);
     if (n < 0 || n > 0x7fffffffLL) return fail(BROV_EINVAL, "n = %lld out of range", n);
-    if (steps < 0 || steps > 0x7fffffffLL) return fail(BROV_EINVAL, "steps = %lld out of range", steps);
-    // the fp64 kernels re-base their constant block by (step + stage) >> 30, which must stay zero (brov_device.cuh)
-    if (steps > (1LL << 29)) return fail(BROV_EINVAL, "steps = %lld: at most 2^29 steps per call; continue from xT / lag_out with step0", steps);
+    if (steps < 0 || steps > (1LL << 30)) return fail(BROV_EINVAL, "steps = %lld: at most 2^30 steps per call; continue from xT / lag_out with step0", steps);
     if (!(dt > 0.0) || !std::isfinite(dt)) return fail(BROV_EINVAL, "dt must be a positive finite number");
     if (e->pv && e->pv_n != n) return fail(BROV_EINVAL, "vehicle table has %lld rows, call has n = %lld", e->pv_n, n);
     return BROV_OK;
+}
+
+// public semantics of lag_in / lag_out -> the kernel call plus the per-thruster epilogue
+static int rollout_dev(brov_engine* e, const brov_rollout_desc* d, cudaStream_t st) {
+    Lag24 l24 = {nullptr, nullptr};
+    if (e->model == BROV_THRUSTER8_LAG3) {
+        if (d->lag_out_dev && d->lag_out_repr == BROV_LAG_THRUSTER) l24.out = d->lag_out_dev;
+        if (d->lag_in_dev && d->lag_in_repr == BROV_LAG_THRUSTER) l24.in = d->lag_in_dev;
+    }
+    return e->dtype == BROV_F32 ? rollout_impl<float>(e, d, st, l24) : rollout_impl<double>(e, d, st, l24);
 }
 
 extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* stream) {
@@ -656,30 +756,65 @@ extern "C" int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* 
     if (rc) return rc;
     if (d->n == 0) return BROV_OK;
     if (!d->x0_dev || !d->xT_dev) return fail(BROV_EINVAL, "x0 and xT must not be NULL");
-    if (d->steps > 0 && !d->u_dev) return fail(BROV_EINVAL, "u is NULL");
+    if (d->steps > 0 && !d->u_dev && !d->gen.enable) return fail(BROV_EINVAL, "u is NULL");
     if (d->u_stride_t < 0 || d->u_stride_n < 0) return fail(BROV_EINVAL, "negative input stride");
     if (d->traj_dev && d->stride < 1) return fail(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
     if (d->time_slices < 0 || d->time_slices > 64) return fail(BROV_EINVAL, "time_slices must be 0 (auto) .. 64");
     if (d->lag_in_repr < 0 || d->lag_in_repr > 1 || d->lag_out_repr < 0 || d->lag_out_repr > 1) return fail(BROV_EINVAL, "unknown lag representation");
-    if (e->model == BROV_THRUSTER8_LAG3 && d->lag_in_dev && d->lag_in_repr == BROV_LAG_PROJECTED && d->lag_out_dev && d->lag_out_repr == BROV_LAG_THRUSTER)
-        return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in");
-    if (d->traj_dev && (d->step0 < 0 || d->step0 / d->stride < d->snap_base)) return fail(BROV_EINVAL, "snap_base lies after the first snapshot of this call");
+    if (d->step0 < 0) return fail(BROV_EINVAL, "step0 < 0");
+    if (d->traj_dev && d->step0 / d->stride < d->snap_base) return fail(BROV_EINVAL, "snap_base lies after the first snapshot of this call");
+    const bool thr = e->model == BROV_THRUSTER8_LAG3;
+    if (thr && d->lag_in_dev && d->lag_out_dev && d->lag_in_dev == d->lag_out_dev && d->lag_in_repr != d->lag_out_repr)
+        return fail(BROV_EINVAL, "lag_in and lag_out alias but differ in representation");
     CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = (cudaStream_t)stream;
     if (d->steps == 0) {
         const size_t sz = scalar_size(e->dtype);
         if (d->xT_dev != d->x0_dev)
-            CUDA_TRY(cudaMemcpyAsync(d->xT_dev, d->x0_dev, (size_t)d->n * model_nx(e->model) * sz, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            CUDA_TRY(cudaMemcpyAsync(d->xT_dev, d->x0_dev, (size_t)d->n * model_nx(e->model) * sz, cudaMemcpyDeviceToDevice, st));
         if (d->lag_out_dev && model_nlag(e)) {
-            if (d->lag_in_dev && d->lag_in_repr != d->lag_out_repr && e->model == BROV_THRUSTER8_LAG3)
+            if (d->lag_in_dev && d->lag_in_repr != d->lag_out_repr && thr)
                 return fail(BROV_EUNSUPPORTED, "a zero-step rollout cannot change the lag representation");
-            const int nl = (e->model == BROV_THRUSTER8_LAG3 && d->lag_out_repr == BROV_LAG_PROJECTED) ? 18 : model_nlag(e);
+            const int nl = (thr && d->lag_out_repr == BROV_LAG_PROJECTED) ? 18 : model_nlag(e);
             const size_t lb = (size_t)d->n * nl * sz;
-            if (d->lag_in_dev) { if (d->lag_in_dev != d->lag_out_dev) CUDA_TRY(cudaMemcpyAsync(d->lag_out_dev, d->lag_in_dev, lb, cudaMemcpyDeviceToDevice, (cudaStream_t)stream)); }
-            else CUDA_TRY(cudaMemsetAsync(d->lag_out_dev, 0, lb, (cudaStream_t)stream));
+            if (d->lag_in_dev) { if (d->lag_in_dev != d->lag_out_dev) CUDA_TRY(cudaMemcpyAsync(d->lag_out_dev, d->lag_in_dev, lb, cudaMemcpyDeviceToDevice, st)); }
+            else CUDA_TRY(cudaMemsetAsync(d->lag_out_dev, 0, lb, st));
         }
+        if (d->gen.enable && d->gen.state_out_dev) {
+            const size_t gb = (size_t)d->n * model_nu(e->model) * sz;
+            if (d->gen.state_in_dev) { if (d->gen.state_in_dev != d->gen.state_out_dev) CUDA_TRY(cudaMemcpyAsync(d->gen.state_out_dev, d->gen.state_in_dev, gb, cudaMemcpyDeviceToDevice, st)); }
+            else CUDA_TRY(cudaMemsetAsync(d->gen.state_out_dev, 0, gb, st));
+        }
+        if (d->health_dev) CUDA_TRY(cudaMemsetAsync(d->health_dev, 0, 2 * sizeof(unsigned long long), st));
         return BROV_OK;
     }
-    return e->dtype == BROV_F32 ? rollout_impl<float>(e, d, (cudaStream_t)stream) : rollout_impl<double>(e, d, (cudaStream_t)stream);
+    return rollout_dev(e, d, st);
+}
+
+template <typename T>
+static int gen_inputs_impl(const brov_gen_inputs_desc* d, cudaStream_t st) {
+    GenInputsArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    int rc = fill_gen<T>(d->gen, d->nu, &a.gen);
+    if (rc) return rc;
+    a.out = (T*)d->out_dev;
+    a.first = d->first; a.vstride = d->vstride; a.n_sel = d->n_sel;
+    a.step0 = d->step0; a.steps = (int)d->steps;
+    CUDA_TRY(launch_gen_inputs<T>(d->nu, a, st));
+    return BROV_OK;
+}
+
+extern "C" int brov_generate_inputs(const brov_gen_inputs_desc* d, void* stream) {
+    if (!d || d->struct_size != sizeof(brov_gen_inputs_desc)) return fail(BROV_EINVAL, "brov_gen_inputs_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
+    if (d->dtype != BROV_F64 && d->dtype != BROV_F32) return fail(BROV_EINVAL, "unknown dtype %d", d->dtype);
+    if (d->nu != 8 && d->nu != 6) return fail(BROV_EINVAL, "nu must be 8 or 6");
+    if (!d->gen.enable) return fail(BROV_EINVAL, "gen.enable is 0");
+    if (d->first < 0 || d->vstride < 1 || d->n_sel < 0 || d->n_sel > 0x7fffffffLL) return fail(BROV_EINVAL, "vehicle selection out of range");
+    if (d->step0 < 0 || d->steps < 0 || d->steps > 0x7fffffffLL) return fail(BROV_EINVAL, "step range out of range");
+    if (d->n_sel == 0 || d->steps == 0) return BROV_OK;
+    if (!d->out_dev) return fail(BROV_EINVAL, "out is NULL");
+    CUDA_TRY(cudaSetDevice(d->device));
+    return d->dtype == BROV_F32 ? gen_inputs_impl<float>(d, (cudaStream_t)stream) : gen_inputs_impl<double>(d, (cudaStream_t)stream);
 }
 
 // Replay depth of the carried lag: smallest m with ||A^m||_inf * (1 + ||b||) below 1e-22 (A, b: lag map of ONE
@@ -763,7 +898,7 @@ extern "C" int brov_se_carry_steps(brov_engine_t* e, double dt, int integrator, 
 
 extern "C" size_t brov_se_workspace_bytes(long long n_windows) {
     if (n_windows < 1) n_windows = 1;
-    return (size_t)((n_windows + 63) / 64) * MAX_H * sizeof(double);  // the smaller (fp64) block size
+    return (size_t)((n_windows + 63) / 64) * MAX_H * sizeof(double);  // covers blocks down to 64 windows
 }
 
 template <typename T>
@@ -780,7 +915,16 @@ static int se_impl(brov_engine* e, const brov_se_desc* d, cudaStream_t st) {
         long long m = 0;
         if ((rc = carry_depth(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &m))) return rc;
         a.carry_steps = (int)m;
+        // the replay of window0's history reads input rows back to window (window0 * H - m) / H: they must be local
+        const long long H = d->horizons[0];
+        const long long first_hist = d->window0 * H - m;
+        const long long need_row = first_hist > 0 ? first_hist / H : 0;
+        if (d->row0 > need_row)
+            return fail(BROV_EINVAL, "lag_carry: the shard must start at row %lld or earlier (row0 = %lld): window %lld replays %lld steps of history", need_row, d->row0, d->window0, m);
     }
+    a.health.counters = (unsigned long long*)d->health_dev;
+    a.health.eps = d->singular_eps > 0.0 ? d->singular_eps : 1e-3;
+    if (d->health_dev) CUDA_TRY(cudaMemsetAsync(d->health_dev, 0, 2 * sizeof(unsigned long long), st));
     CUDA_TRY(launch_se<T>(e->model, d->integrator, a, d->se_out_dev, st));
     return BROV_OK;
 }
@@ -798,6 +942,9 @@ extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* 
     for (int h = 0; h < d->n_horizons; ++h)
         if (d->horizons[h] < 1 || d->horizons[h] > (1 << 29) || (h && d->horizons[h] <= d->horizons[h - 1])) return fail(BROV_EINVAL, "horizons must be in [1, 2^29] and strictly ascending");
     if (d->rows < 0 || d->rows > 0x7fffffffLL || d->n_windows < 0 || d->n_windows > d->rows) return fail(BROV_EINVAL, "rows / n_windows out of range");
+    // every window's first row must be local: window k starts at local row k + (window0 - row0)
+    if (d->n_windows + (d->window0 - d->row0) > d->rows)
+        return fail(BROV_EINVAL, "n_windows = %lld starting at local row %lld exceed the %lld rows of the series", d->n_windows, d->window0 - d->row0, d->rows);
     if (!(d->dt > 0.0)) return fail(BROV_EINVAL, "dt must be > 0");
     if (!d->se_out_dev) return fail(BROV_EINVAL, "se_out is NULL");
     CUDA_TRY(cudaSetDevice(e->device));
@@ -812,6 +959,7 @@ extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* 
     }
     if (d->n_windows == 0 || d->rows < 2) {
         CUDA_TRY(cudaMemsetAsync(d->se_out_dev, 0, MAX_H * sizeof(double), (cudaStream_t)stream));
+        if (d->health_dev) CUDA_TRY(cudaMemsetAsync(d->health_dev, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
         return BROV_OK;
     }
     if (!d->X_dev || !d->U_dev) return fail(BROV_EINVAL, "X and U must not be NULL");
@@ -846,34 +994,46 @@ extern "C" int brov_reduced9_rhs(int dtype, const void* x, const void* u, void* 
 // host-buffer rollout: time-chunked H2D of inputs on a copy stream, double buffered against the rollout kernels;
 // snapshots return on a third stream
 // ---------------------------------------------------------------------------------------------------------------
-static int grow(void** p, size_t* cap, size_t need) {
-    if (need <= *cap) return BROV_OK;
-    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
-    cudaError_t er = cudaMalloc(p, need);
-    if (er != cudaSuccess) return fail(BROV_ENOMEM, "cudaMalloc(%zu): %s", need, cudaGetErrorString(er));
-    *cap = need;
-    return BROV_OK;
-}
-
 extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc* d) {
     if (!d || d->struct_size != sizeof(brov_rollout_host_desc)) return fail(BROV_EINVAL, "brov_rollout_host_desc size mismatch (ABI %d)", BROV_ABI_VERSION);
     int rc = check_rollout_common(e, d->integrator, d->n, d->steps, d->dt);
     if (rc) return rc;
     if (d->n == 0) return BROV_OK;
+    const bool gen = d->gen.enable != 0;
     if (!d->x0_host || !d->xT_host) return fail(BROV_EINVAL, "x0 and xT must not be NULL");
-    if (d->steps > 0 && !d->u_host) return fail(BROV_EINVAL, "u is NULL");
+    if (d->steps > 0 && !d->u_host && !gen) return fail(BROV_EINVAL, "u is NULL");
     if (d->traj_host && d->stride < 1) return fail(BROV_EINVAL, "stride must be >= 1 with a trajectory buffer");
+    if (d->lag_in_repr < 0 || d->lag_in_repr > 1 || d->lag_out_repr < 0 || d->lag_out_repr > 1) return fail(BROV_EINVAL, "unknown lag representation");
     CUDA_TRY(cudaSetDevice(e->device));
     const size_t sz = scalar_size(e->dtype);
-    const int NX = model_nx(e->model), NU = model_nu(e->model), NLAG = model_nlag(e);
+    const int NX = model_nx(e->model), NU = model_nu(e->model);
+    const bool thr = e->model == BROV_THRUSTER8_LAG3;
+    const int nl_carry = thr ? 18 : (e->use_lag1 ? 6 : 0);   // what the chunks carry on the device
     const long long n = d->n;
-    const size_t row_u = (d->u_shared ? 1 : (size_t)n) * NU * sz;  // bytes of one time step of inputs
-    long long chunk = d->chunk_steps > 0 ? d->chunk_steps : (long long)((256ull << 20) / row_u);
+    const size_t row_u = gen ? 0 : (d->u_shared ? 1 : (size_t)n) * NU * sz;  // bytes of one time step of inputs
+    const size_t snap_bytes = (size_t)n * NX * sz;
+    long long chunk = d->chunk_steps;
+    if (chunk <= 0) {
+        chunk = gen ? d->steps : (long long)((256ull << 20) / row_u);
+        if (d->traj_host) {   // about 256 MiB of snapshots per chunk
+            const long long by_traj = d->stride * (long long)std::max<size_t>(1, (256ull << 20) / snap_bytes);
+            if (by_traj < chunk) chunk = by_traj;
+        }
+    }
     if (chunk < 1) chunk = 1;
     if (d->traj_host) chunk = ((chunk + d->stride - 1) / d->stride) * d->stride;  // whole snapshots per chunk
     if (chunk > d->steps) chunk = d->steps > 0 ? d->steps : 1;
     const long long snaps_per_chunk = d->traj_host ? (chunk + d->stride - 1) / d->stride + 1 : 0;
-    const size_t snap_bytes = (size_t)n * NX * sz;
+
+    // per-thruster lag states: wanted back / supplied
+    const bool want24 = thr && d->lag_out_host && d->lag_out_repr == BROV_LAG_THRUSTER;
+    const bool in24 = thr && d->lag_in_host && d->lag_in_repr == BROV_LAG_THRUSTER;
+    long long depth = 0;
+    if (want24) {
+        if ((rc = carry_depth(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &depth))) return rc;
+        if (d->lag_in_host && !in24 && d->steps < depth)
+            return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in in a call of fewer than %lld steps", depth);
+    }
 
     HostStage& h = e->hs;
     if (!h.ready) {
@@ -888,40 +1048,48 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
         h.ready = true;
     }
     if ((rc = grow(&h.d_x, &h.cap_x, snap_bytes))) return rc;
-    if (NLAG && (rc = grow(&h.d_lag, &h.cap_lag, (size_t)n * NLAG * sz))) return rc;
-    {
+    if (nl_carry && (rc = grow(&h.d_lag, &h.cap_lag, (size_t)n * nl_carry * sz))) return rc;
+    if ((want24 || in24) && (rc = grow(&h.d_lag24, &h.cap_lag24, (size_t)n * 24 * sz))) return rc;
+    if (gen && (rc = grow(&h.d_gen, &h.cap_gen, (size_t)n * NU * sz))) return rc;
+    if (d->health_host && (rc = grow(&h.d_health, &h.cap_health, 16 + (size_t)n * sz))) return rc;
+    if (!gen && d->steps > 0) {
         size_t need_u = (size_t)chunk * row_u, cap = h.cap_u;
         for (int b = 0; b < 2; ++b) { cap = h.cap_u; if ((rc = grow(&h.d_u[b], &cap, need_u))) return rc; }
         h.cap_u = cap;
-        if (d->traj_host) {
-            size_t need_t = (size_t)snaps_per_chunk * snap_bytes;
-            for (int b = 0; b < 2; ++b) { cap = h.cap_traj; if ((rc = grow(&h.d_traj[b], &cap, need_t))) return rc; }
-            h.cap_traj = cap;
-        }
+    }
+    if (d->traj_host) {
+        size_t need_t = (size_t)snaps_per_chunk * snap_bytes, cap = h.cap_traj;
+        for (int b = 0; b < 2; ++b) { cap = h.cap_traj; if ((rc = grow(&h.d_traj[b], &cap, need_t))) return rc; }
+        h.cap_traj = cap;
     }
 
     CUDA_TRY(cudaMemcpyAsync(h.d_x, d->x0_host, snap_bytes, cudaMemcpyHostToDevice, h.s_compute));
-    // thruster model: chunks carry the allocation-projected lag unless per-thruster states are wanted back
-    const bool thr = e->model == BROV_THRUSTER8_LAG3;
-    if (d->lag_in_repr < 0 || d->lag_in_repr > 1 || d->lag_out_repr < 0 || d->lag_out_repr > 1) return fail(BROV_EINVAL, "unknown lag representation");
-    const int carry_repr = (thr && (d->lag_out_host == nullptr || d->lag_out_repr == BROV_LAG_PROJECTED)) ? BROV_LAG_PROJECTED : BROV_LAG_THRUSTER;
-    if (thr && d->lag_in_host && d->lag_in_repr == BROV_LAG_PROJECTED && carry_repr == BROV_LAG_THRUSTER)
-        return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in");
-    const int nl_in = (thr && d->lag_in_repr == BROV_LAG_PROJECTED) ? 18 : NLAG;
-    const int nl_out = (thr && carry_repr == BROV_LAG_PROJECTED) ? 18 : NLAG;
-    if (NLAG) {
-        if (d->lag_in_host) CUDA_TRY(cudaMemcpyAsync(h.d_lag, d->lag_in_host, (size_t)n * nl_in * sz, cudaMemcpyHostToDevice, h.s_compute));
-        else CUDA_TRY(cudaMemsetAsync(h.d_lag, 0, (size_t)n * NLAG * sz, h.s_compute));
+    if (nl_carry) {
+        if (in24) CUDA_TRY(cudaMemcpyAsync(h.d_lag24, d->lag_in_host, (size_t)n * 24 * sz, cudaMemcpyHostToDevice, h.s_compute));
+        else if (d->lag_in_host) CUDA_TRY(cudaMemcpyAsync(h.d_lag, d->lag_in_host, (size_t)n * nl_carry * sz, cudaMemcpyHostToDevice, h.s_compute));
+        else CUDA_TRY(cudaMemsetAsync(h.d_lag, 0, (size_t)n * nl_carry * sz, h.s_compute));
+    }
+    if (gen) {
+        if (d->gen.state_in_dev) CUDA_TRY(cudaMemcpyAsync(h.d_gen, d->gen.state_in_dev, (size_t)n * NU * sz, cudaMemcpyHostToDevice, h.s_compute));
+        else CUDA_TRY(cudaMemsetAsync(h.d_gen, 0, (size_t)n * NU * sz, h.s_compute));
+    }
+    if (d->steps == 0 && want24) {   // nothing to integrate: per-thruster states pass through
+        if (in24) CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag24, (size_t)n * 24 * sz, cudaMemcpyDeviceToHost, h.s_compute));
+        else if (d->lag_in_host) return fail(BROV_EUNSUPPORTED, "a zero-step rollout cannot change the lag representation");
+        else memset(d->lag_out_host, 0, (size_t)n * 24 * sz);
     }
     long long done = 0;
     int b = 0;
+    bool tail_started = false;
     for (long long c = 0; done < d->steps; ++c, b ^= 1) {
         const long long len = (d->steps - done < chunk) ? (d->steps - done) : chunk;
-        // inputs of chunk c -> d_u[b] once the kernel that last read d_u[b] (chunk c-2) has finished
-        if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h.s_in, h.ev_done[b], 0));
-        CUDA_TRY(cudaMemcpyAsync(h.d_u[b], (const char*)d->u_host + (size_t)done * row_u, (size_t)len * row_u, cudaMemcpyHostToDevice, h.s_in));
-        CUDA_TRY(cudaEventRecord(h.ev_in[b], h.s_in));
-        CUDA_TRY(cudaStreamWaitEvent(h.s_compute, h.ev_in[b], 0));
+        if (!gen) {
+            // inputs of chunk c -> d_u[b] once the kernel that last read d_u[b] (chunk c-2) has finished
+            if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(h.s_in, h.ev_done[b], 0));
+            CUDA_TRY(cudaMemcpyAsync(h.d_u[b], (const char*)d->u_host + (size_t)done * row_u, (size_t)len * row_u, cudaMemcpyHostToDevice, h.s_in));
+            CUDA_TRY(cudaEventRecord(h.ev_in[b], h.s_in));
+            CUDA_TRY(cudaStreamWaitEvent(h.s_compute, h.ev_in[b], 0));
+        }
         const long long first_snap = d->traj_host ? done / d->stride : 0;
         const long long last_snap = d->traj_host ? (done + len) / d->stride : 0;  // snapshots [first, last)
         if (d->traj_host && c >= 2) CUDA_TRY(cudaStreamWaitEvent(h.s_compute, h.ev_out[b], 0));
@@ -929,16 +1097,37 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
         memset(&r, 0, sizeof(r));
         r.struct_size = sizeof(r);
         r.integrator = d->integrator; r.n = n; r.steps = len; r.dt = d->dt;
-        r.x0_dev = h.d_x; r.xT_dev = h.d_x; r.u_dev = h.d_u[b];
+        r.x0_dev = h.d_x; r.xT_dev = h.d_x; r.u_dev = gen ? nullptr : h.d_u[b];
         r.u_stride_t = d->u_shared ? NU : n * NU;
         r.u_stride_n = d->u_shared ? 0 : NU;
-        r.lag_in_dev = NLAG ? h.d_lag : nullptr; r.lag_out_dev = NLAG ? h.d_lag : nullptr;
+        // chunk 0 reads the caller's lag in its own representation; every chunk leaves the projected lag in d_lag
+        const bool first24 = c == 0 && in24;
+        r.lag_in_dev = nl_carry ? (first24 ? h.d_lag24 : h.d_lag) : nullptr;
+        r.lag_in_repr = first24 ? BROV_LAG_THRUSTER : BROV_LAG_PROJECTED;
+        r.lag_out_dev = nl_carry ? h.d_lag : nullptr;
+        r.lag_out_repr = BROV_LAG_PROJECTED;
         r.traj_dev = d->traj_host ? h.d_traj[b] : nullptr;
         r.stride = d->traj_host ? d->stride : 1; r.step0 = done; r.snap_base = first_snap;
-        r.lag_in_repr = (c == 0) ? (d->lag_in_host ? d->lag_in_repr : carry_repr) : carry_repr;
-        r.lag_out_repr = carry_repr;
         r.time_slices = 0;
-        if ((rc = brov_rollout(e, &r, h.s_compute))) return rc;
+        if (gen) {
+            r.gen = d->gen;
+            r.gen.state_in_dev = h.d_gen; r.gen.state_out_dev = h.d_gen;
+        }
+        if (d->health_host) {
+            r.health_dev = h.d_health;
+            r.min_abs_cos_dev = (char*)h.d_health + 16;
+            r.min_abs_cos_accumulate = c > 0;
+            r.singular_eps = d->singular_eps;
+        }
+        // per-thruster states: rebuilt by the chunks that cover the last `depth` steps of the call
+        Lag24 l24 = {nullptr, nullptr};
+        if (want24 && done + len > d->steps - depth) {
+            l24.out = h.d_lag24;
+            l24.in = (tail_started || (done == 0 && in24)) ? h.d_lag24 : nullptr;
+            tail_started = true;
+        }
+        rc = e->dtype == BROV_F32 ? rollout_impl<float>(e, &r, h.s_compute, l24) : rollout_impl<double>(e, &r, h.s_compute, l24);
+        if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h.ev_done[b], h.s_compute));
         if (d->traj_host && last_snap > first_snap) {
             CUDA_TRY(cudaStreamWaitEvent(h.s_out, h.ev_done[b], 0));
@@ -948,7 +1137,17 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
         done += len;
     }
     CUDA_TRY(cudaMemcpyAsync(d->xT_host, h.d_x, snap_bytes, cudaMemcpyDeviceToHost, h.s_compute));
-    if (NLAG && d->lag_out_host) CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag, (size_t)n * nl_out * sz, cudaMemcpyDeviceToHost, h.s_compute));
+    if (nl_carry && d->lag_out_host && d->steps > 0) {
+        if (want24) CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag24, (size_t)n * 24 * sz, cudaMemcpyDeviceToHost, h.s_compute));
+        else CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag, (size_t)n * nl_carry * sz, cudaMemcpyDeviceToHost, h.s_compute));
+    } else if (nl_carry && d->lag_out_host && !want24) {
+        CUDA_TRY(cudaMemcpyAsync(d->lag_out_host, h.d_lag, (size_t)n * nl_carry * sz, cudaMemcpyDeviceToHost, h.s_compute));
+    }
+    if (gen && d->gen.state_out_dev) CUDA_TRY(cudaMemcpyAsync(d->gen.state_out_dev, h.d_gen, (size_t)n * NU * sz, cudaMemcpyDeviceToHost, h.s_compute));
+    if (d->health_host) {
+        if (d->steps > 0) CUDA_TRY(cudaMemcpyAsync(d->health_host, h.d_health, 16, cudaMemcpyDeviceToHost, h.s_compute));
+        else { d->health_host[0] = 0; d->health_host[1] = 0; }
+    }
     CUDA_TRY(cudaStreamSynchronize(h.s_in));
     CUDA_TRY(cudaStreamSynchronize(h.s_compute));
     CUDA_TRY(cudaStreamSynchronize(h.s_out));

@@ -18,20 +18,11 @@
 #include <stdint.h>
 #include <type_traits>
 
-// Measured on B200 (profiles/tune_variants.py, 65,536 vehicles x 100 RK4 steps, fp64): constants as kernel-argument
-// members, hoisted + R2UR/UMOV shuffling 0.491 ms; constants in shared memory, hoisted 0.481 ms (default); re-based
-// kernel-argument constants (LDC.64 c[0][R+off] at every use, 450 fewer instructions per step) 0.542 ms; re-based
-// shared-memory constants (LDS.64 at every use) 0.527 ms.  The instruction savings of re-basing lose to the load
-// latency they put in front of the FP64 pipe at 2 warps per scheduler, so it is off by default.
-#ifndef BROV_F64_REBASE
-#define BROV_F64_REBASE 0
-#endif
-#ifndef BROV_STAGE_UNROLL
-#define BROV_STAGE_UNROLL 3
-#endif
+// Layout alternatives measured and rejected in round 1 (lag state / RK4 accumulator in shared memory, 64-thread fp64
+// blocks, re-based constant loads, a rolled stage loop, packed FFMA2 fp32 step) are recorded with their timings in
+// profiles/r01e_fp64_const_variants.json, r01g_tune_variants.json and DESIGN.md; their code left the tree in round 2.
 
 namespace brov {
-constexpr int kStageUnroll = BROV_STAGE_UNROLL;
 
 // ---------------------------------------------------------------------------------------------------------------
 // kernel-parameter vector (derived coefficients; see brov_derive_params in brov_api.cu and include/brov.h)
@@ -89,25 +80,9 @@ template <typename T> struct Consts {
     T poly[5];     // -140.3, 389.9, -404.1, 176.0, 8.9
     T sc[16];      // see kSinCos64
     T rot[8];      // sin: -1/6, 1/120, -1/5040 ; cos: -1/2, 1/24, -1/720, 1/40320 ; pad
-    // operand pairs of the packed-FP32 step (brov_device_f32x2.cuh, PK_* layout); 8-byte aligned by construction
-    T pk[104];
     int has_current;
     int use_lag1;
 };
-
-// fp64 only, experimental (BROV_F64_REBASE).  sm_100 FP instructions take constants from UNIFORM REGISTERS, not from the constant bank directly; an fp64
-// step touches ~130 distinct 64-bit constants = 260 uniform registers against ~80 available.  Left alone, the compiler
-// hoists every constant load out of the step loop and then spends ~450 instructions per step moving them between
-// regular and uniform registers (R2UR / MOV.SPILL / UMOV).  Re-basing the constant block by a loop-variant offset that
-// is always zero (`z` = step index >> 30) makes the loads non-hoistable: each use becomes ONE `LDCU.64 UR, c[0][UR+off]`
-// next to its consumer.  fp32 constants are half the size and fit; that build keeps the plain reference.
-template <typename T>
-__device__ __forceinline__ const Consts<T>& rebase(const Consts<T>& c, int z) {
-    if constexpr (sizeof(T) == 8 && BROV_F64_REBASE)
-        return *reinterpret_cast<const Consts<T>*>(reinterpret_cast<const char*>(&c) + (long long)z * 8);
-    else
-        return c;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // scalar helpers
@@ -197,6 +172,13 @@ template <typename T> struct ParamsShared {
     int pitch;      // blockDim.x
     __device__ __forceinline__ T operator[](int i) const { return base[i * pitch]; }
 };
+// per-vehicle coefficients held in registers for the whole launch (fp32 Monte-Carlo rollouts: every coefficient is used
+// once per RHS evaluation, i.e. the shared-memory table costs ~130 LDS per RK4 step; indices are compile-time constants
+// after unrolling, unused entries are dropped by the compiler)
+template <typename T> struct ParamsRegs {
+    T v[KP_COUNT];
+    __device__ __forceinline__ T operator[](int i) const { return v[i]; }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // model pieces
@@ -226,30 +208,32 @@ template <typename T> __device__ __forceinline__ T thrust_poly(const Consts<T>& 
 }
 
 // nu_dot = Minv (tau - C(nu) nu - D(nu_r) nu_r - g); g from (sin th, cos th sin phi, cos th cos phi).
+// Every axis is ONE chain of fused multiply-adds onto tau_i: the Coriolis terms (closed form of C_RB + C_A times nu,
+// fossen/BlueROV2.py:280-325), the restoring terms (:340-355) and the damping term (:327-338) are accumulated with
+// their signs instead of being formed as separate vectors and subtracted (47 instead of 62 operations).
 template <typename T, class P>
 __device__ __forceinline__ void nu_dot(const T* __restrict__ nu, const T* __restrict__ nur, const T* __restrict__ tau,
                                        T sth, T cs, T cc, const P& p, T* __restrict__ out) {
     const T u = nu[0], v = nu[1], w = nu[2], pp = nu[3], q = nu[4], r = nu[5];
     const T a1u = p[KP_A + 0] * u, a2v = p[KP_A + 1] * v, a3w = p[KP_A + 2] * w;
-    T c[6];
-    c[0] = a3w * q - a2v * r;
-    c[1] = a1u * r - a3w * pp;
-    c[2] = a2v * pp - a1u * q;
-    c[3] = p[KP_DA + 0] * (v * w) + p[KP_DB + 0] * (q * r);
-    c[4] = p[KP_DA + 1] * (u * w) + p[KP_DB + 1] * (pp * r);
-    c[5] = p[KP_DA + 2] * (u * v) + p[KP_DB + 2] * (pp * q);
     const T wmb = p[KP_WMB], xbB = p[KP_XBB + 0], ybB = p[KP_XBB + 1], zbB = p[KP_XBB + 2];
-    T g[6];
-    g[0] = wmb * sth;
-    g[1] = -wmb * cs;
-    g[2] = -wmb * cc;
-    g[3] = ybB * cc - zbB * cs;
-    g[4] = -zbB * sth - xbB * cc;
-    g[5] = xbB * cs + ybB * sth;
+    T t[6];
+    // [C nu]_0 = a3 w q - a2 v r          g_0 = (W-B) sin th
+    t[0] = tau[0] - a3w * q;   t[0] += a2v * r;   t[0] -= wmb * sth;
+    // [C nu]_1 = a1 u r - a3 w p          g_1 = -(W-B) cos th sin phi
+    t[1] = tau[1] - a1u * r;   t[1] += a3w * pp;  t[1] += wmb * cs;
+    // [C nu]_2 = a2 v p - a1 u q          g_2 = -(W-B) cos th cos phi
+    t[2] = tau[2] - a2v * pp;  t[2] += a1u * q;   t[2] += wmb * cc;
+    // [C nu]_3 = (a3-a2) v w + (b3-b2) q r     g_3 = yb B cc - zb B cs
+    t[3] = tau[3] - p[KP_DA + 0] * (v * w);  t[3] -= p[KP_DB + 0] * (q * r);   t[3] -= ybB * cc;  t[3] += zbB * cs;
+    // [C nu]_4 = (a1-a3) u w + (b1-b3) p r     g_4 = -zb B sth - xb B cc
+    t[4] = tau[4] - p[KP_DA + 1] * (u * w);  t[4] -= p[KP_DB + 1] * (pp * r);  t[4] += zbB * sth; t[4] += xbB * cc;
+    // [C nu]_5 = (a2-a1) u v + (b2-b1) p q     g_5 = xb B cs + yb B sth
+    t[5] = tau[5] - p[KP_DA + 2] * (u * v);  t[5] -= p[KP_DB + 2] * (pp * q);  t[5] -= xbB * cs;  t[5] -= ybB * sth;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         T d = p[KP_DQ + i] * abs_(nur[i]) + p[KP_DL + i];
-        out[i] = p[KP_MINV + i] * (tau[i] - c[i] - d * nur[i] - g[i]);
+        out[i] = p[KP_MINV + i] * (t[i] - d * nur[i]);
     }
 }
 
@@ -450,15 +434,16 @@ __device__ __forceinline__ void rhs_diq13(const T* __restrict__ x, const T* __re
 
 // ---------------------------------------------------------------------------------------------------------------
 // 3rd-order thruster lag, closed form over the sub-steps of one integrator step (input held).
-// The lag state lives either in registers (LS = 1) or in shared memory laid out [component][thread] (LS = block size).
 //
 // LAGW = false: thruster coordinates, lag[8][3] = ThrusterLag._x of each thruster (the reference's hidden state).
 //     y_i = G_j . lag_i + H_j F_i ; tau = alloc y                                   (128 + 124 ops per RK4 step)
+//     Used by the single-evaluation kernels (rhs_kernel, thruster_wrench_kernel, thruster_series_kernel).
 // LAGW = true : allocation-projected coordinates Z[6][3] = sum_i alloc[c][i] lag_i.  The eight lags are copies of ONE
 //     linear filter, so any fixed linear combination of their states obeys the same recurrence driven by the same
 //     combination of the inputs: tau_c = G_j . Z_c + H_j (alloc F)_c ; Z_c <- A Z_c + B (alloc F)_c.   (31 + 96 ops)
-//     Identical dynamics (rounding differs at 1e-16), 18 instead of 24 hidden values, but the per-thruster states
-//     cannot be recovered from Z — used when the caller does not ask for them.
+//     Identical dynamics (rounding differs at 1e-16), 18 instead of 24 hidden values.  Every rollout and evaluator
+//     kernel integrates in this form; per-thruster states, when the caller wants them back, come from
+//     lag_tail_kernel (brov_kernels.cuh), which replays the tail of the input history the filter still remembers.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void allocate_wrench(const Consts<T>& c, const T* __restrict__ y, T* __restrict__ tau) {
@@ -476,38 +461,41 @@ __device__ __forceinline__ void allocate_wrench(const Consts<T>& c, const T* __r
     }
 }
 
-template <typename T, int LS, bool LAGW, class LP>
-__device__ __forceinline__ void thruster_tau(const Consts<T>& c, int j, LP lag, const T* __restrict__ F,
-                                             T* __restrict__ tau) {
+template <typename T, bool LAGW>
+__device__ __forceinline__ void thruster_tau(const Consts<T>& c, int j, const T* __restrict__ lag,
+                                             const T* __restrict__ F, T* __restrict__ tau) {
     if constexpr (LAGW) {  // F holds alloc*F (6 values)
 #pragma unroll
         for (int r = 0; r < 6; ++r)
-            tau[r] = c.lagG[j][0] * lag[(3 * r) * LS] + c.lagG[j][1] * lag[(3 * r + 1) * LS] +
-                     c.lagG[j][2] * lag[(3 * r + 2) * LS] + c.lagH[j] * F[r];
+            tau[r] = c.lagG[j][0] * lag[3 * r] + c.lagG[j][1] * lag[3 * r + 1] + c.lagG[j][2] * lag[3 * r + 2] +
+                     c.lagH[j] * F[r];
     } else {
         T y[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            y[i] = c.lagG[j][0] * lag[(3 * i) * LS] + c.lagG[j][1] * lag[(3 * i + 1) * LS] +
-                   c.lagG[j][2] * lag[(3 * i + 2) * LS] + c.lagH[j] * F[i];
+            y[i] = c.lagG[j][0] * lag[3 * i] + c.lagG[j][1] * lag[3 * i + 1] + c.lagG[j][2] * lag[3 * i + 2] +
+                   c.lagH[j] * F[i];
         allocate_wrench<T>(c, y, tau);
     }
 }
 
-template <typename T, int LS, bool LAGW, class LP>
-__device__ __forceinline__ void lag_advance(const Consts<T>& c, LP lag, const T* __restrict__ F) {
+// one filter: x <- lagA x + lagB F
+template <typename T>
+__device__ __forceinline__ void lag_advance1(const Consts<T>& c, T* __restrict__ x, T F) {
+    const T a = x[0], b = x[1], d = x[2];
+    x[0] = c.lagA[0][0] * a + c.lagA[0][1] * b + c.lagA[0][2] * d + c.lagB[0] * F;
+    x[1] = c.lagA[1][0] * a + c.lagA[1][1] * b + c.lagA[1][2] * d + c.lagB[1] * F;
+    x[2] = c.lagA[2][0] * a + c.lagA[2][1] * b + c.lagA[2][2] * d + c.lagB[2] * F;
+}
+template <typename T, bool LAGW>
+__device__ __forceinline__ void lag_advance(const Consts<T>& c, T* __restrict__ lag, const T* __restrict__ F) {
 #pragma unroll
-    for (int i = 0; i < (LAGW ? 6 : 8); ++i) {
-        T a = lag[(3 * i) * LS], b = lag[(3 * i + 1) * LS], d = lag[(3 * i + 2) * LS];
-        lag[(3 * i + 0) * LS] = c.lagA[0][0] * a + c.lagA[0][1] * b + c.lagA[0][2] * d + c.lagB[0] * F[i];
-        lag[(3 * i + 1) * LS] = c.lagA[1][0] * a + c.lagA[1][1] * b + c.lagA[1][2] * d + c.lagB[1] * F[i];
-        lag[(3 * i + 2) * LS] = c.lagA[2][0] * a + c.lagA[2][1] * b + c.lagA[2][2] * d + c.lagB[2] * F[i];
-    }
+    for (int i = 0; i < (LAGW ? 6 : 8); ++i) lag_advance1<T>(c, lag + 3 * i, F[i]);
 }
 
-// thruster-coordinate lag state (registers) -> allocation-projected state Z[6][3] (storage stride LS)
-template <typename T, int LS, class LP>
-__device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restrict__ lag24, LP Z) {
+// thruster-coordinate lag state -> allocation-projected state Z[6][3]
+template <typename T>
+__device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restrict__ lag24, T* __restrict__ Z) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         T y[8], t[6];
@@ -515,28 +503,27 @@ __device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restr
         for (int i = 0; i < 8; ++i) y[i] = lag24[3 * i + k];
         allocate_wrench<T>(c, y, t);
 #pragma unroll
-        for (int r = 0; r < 6; ++r) Z[(3 * r + k) * LS] = t[r];
+        for (int r = 0; r < 6; ++r) Z[3 * r + k] = t[r];
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// one integrator step of one vehicle
-//   x[NX]   state (registers, in/out)
-//   lag     THRUSTER8: lag state, 8x3 (LAGW = false) or 6x3 (LAGW = true), storage stride LS;
-//           wrench models with LAG1: the 6 filtered wrench components (registers, LS = 1)
-//   u[NU]   input held over the step
+// one right-hand-side evaluation
+//   lag     THRUSTER8: lag state, 8x3 (LAGW = false) or 6x3 (LAGW = true);
+//           wrench models with LAG1: the 6 filtered wrench components
+//   Fu      THRUSTER8 -> static thrust F[8] of this step (alloc*F[6] when LAGW); wrench models -> commanded wrench;
+//           double-integrator models -> accelerations
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODEL, bool LAG1, int LS, bool LAGW, class P, class LP>
+template <typename T, int MODEL, bool LAG1, bool LAGW, class P>
 __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int substep, const T* __restrict__ x,
-                                          const Trig<T>& tr, LP lag, const T* __restrict__ Fu,
+                                          const Trig<T>& tr, const T* __restrict__ lag, const T* __restrict__ Fu,
                                           T* __restrict__ xd, T* __restrict__ lagd) {
-    // Fu: THRUSTER8 -> static thrust F[8] of this step (or alloc*F[6] when LAGW); wrench models -> commanded wrench
     if constexpr (MODEL == MODEL_THRUSTER8) {
         T tau[6];
-        thruster_tau<T, LS, LAGW, LP>(c, substep, lag, Fu, tau);
+        thruster_tau<T, LAGW>(c, substep, lag, Fu, tau);
         rhs_euler12<T>(x, tr, tau, p, c.has_current != 0, xd);
     } else if constexpr (MODEL == MODEL_DIQ13_U6) {
-        rhs_diq13<T>(x, Fu, xd);     // Fu = accelerations
+        rhs_diq13<T>(x, Fu, xd);
     } else if constexpr (ModelDim<MODEL>::DI) {
         rhs_di12<T>(x, tr, Fu, xd);
     } else {
@@ -553,57 +540,29 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
     }
 }
 
-}  // namespace brov
-// Packed-FP32 step (brov_device_f32x2.cuh).  Measured on B200: 1,048,576 vehicles x 100 RK4 steps take 3.17 ms packed
-// against 3.13 ms scalar although the packed step issues 235 fewer instructions: an FMA with three register operands is
-// bound by register-file read bandwidth, which a packed instruction does not relieve.  Off by default; the build with
-// BROV_F32_PACKED=1 passes the same parity tests.
-#ifndef BROV_F32_PACKED
-#define BROV_F32_PACKED 0
-#endif
-#include "brov_device_f32x2.cuh"
-namespace brov {
-
-template <typename T, class P>
-__device__ __forceinline__ P params_at(const P& p, const Consts<T>& cz) {
-    if constexpr (std::is_same<P, ParamsConst<T>>::value) {
-        P q;
-        q.kp = cz.kp;
-        return q;
-    } else {
-        return p;
-    }
-}
-
-// AS: element stride of the RK4 accumulator: 1 = registers; otherwise `acc_sm` points at this thread's column of a
-// shared-memory array [NX][AS] (fp64 build: frees 24 registers so that 14 warps fit an SM without spilling).
-// zk: the caller's step counter (any uniform value < 2^30): the fp64 build re-bases the constant block by
-// (zk + stage) >> 30 = 0 so that constant loads stay next to their uses (see rebase()).
-template <typename T, int MODEL, int INTEG, bool LAG1, int LS, bool LAGW, int AS, class P, class LP, class AP>
-__device__ __forceinline__ void integrate_step(const Consts<T>& c_, const P& p_, T* __restrict__ x, LP lag,
-                                               const T* __restrict__ u, AP acc_sm, int zk = 0) {
+// ---------------------------------------------------------------------------------------------------------------
+// one integrator step of one vehicle (the body of simulate_physics' loop: RK4 training/train_tank_brov2_rk4.py:386-394,
+// Euler training/train_tank_brov2_full_comparison.py:462-465, quaternion re-normalisation
+// training/train_tank_brov2_wrench_quat.py:262-263)
+//   x[NX]   state (registers, in/out)
+//   lag     THRUSTER8: allocation-projected lag state Z[6][3]; wrench models with LAG1: filtered wrench [6]
+//   u[NU]   input held over the step
+//   abs_cth |cos theta| of the state the step starts from (Euler-angle Fossen models; 1 otherwise): how close the
+//           vehicle is to the singularity of the Euler-rate kinematics (fossen/BlueROV2.py:43-62)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODEL, int INTEG, bool LAG1, class P>
+__device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x, T* __restrict__ lag,
+                                               const T* __restrict__ u, T& abs_cth) {
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NL = LAG1 ? 6 : 1;  // continuous auxiliary states integrated with x
-    if constexpr (BROV_F32_PACKED && std::is_same<T, float>::value && MODEL == MODEL_THRUSTER8 && INTEG == INTEG_RK4 &&
-                  !LAG1 && LAGW && LS == 1 && AS == 1 && std::is_same<P, ParamsConst<float>>::value &&
-                  std::is_same<LP, float*>::value) {
-        integrate_step_packed(c_, x, lag, u);
-        return;
-    }
-    const Consts<T>& c = rebase<T>(c_, zk >> 30);
-    const P p = params_at<T, P>(p_, c);
+    constexpr bool LAGW = true;
     const T dt = c.dt;
     T Fu[ModelDim<MODEL>::NU];
     if constexpr (MODEL == MODEL_THRUSTER8) {
         T F[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(c, u[i]);
-        if constexpr (LAGW) {
-            allocate_wrench<T>(c, F, Fu);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) Fu[i] = F[i];
-        }
+        allocate_wrench<T>(c, F, Fu);
     } else if constexpr (ModelDim<MODEL>::DI) {
         di_accel<T, ModelDim<MODEL>::NU>(c, u, Fu);
         // the quaternion twin normalises the stored quaternion BEFORE the step (wrench_quat.py:345)
@@ -616,8 +575,9 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c_, const P& p_,
     constexpr bool EULER_ANGLES = !ModelDim<MODEL>::QUAT;
     Trig<T> tr0;
     if constexpr (EULER_ANGLES) trig_full<T>(c, x + 3, tr0);
+    abs_cth = (EULER_ANGLES && !ModelDim<MODEL>::DI) ? abs_(tr0.cth) : T(1);
     if constexpr (INTEG == INTEG_EULER) {
-        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, tr0, lag, Fu, k, kl);
+        model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, 0, x, tr0, lag, Fu, k, kl);
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt * k[i];
         if constexpr (LAG1) {
@@ -626,24 +586,18 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c_, const P& p_,
         }
     } else {
         // classic RK4 in low-storage form: acc accumulates k1 + 2 k2 + 2 k3 + k4, xs is the stage state
-        T acc_regs[AS == 1 ? NX : 1], xs[NX], accl[NL], ls[NL];
-        typename std::conditional<AS == 1, T*, AP>::type acc;
-        if constexpr (AS == 1) acc = acc_regs; else acc = acc_sm;
+        T acc[NX], xs[NX], accl[NL], ls[NL];
         const T hdt = T(0.5) * dt;
         Trig<T> trs;
         T dang[3];
-        model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(c, p, 0, x, tr0, lag, Fu, k, kl);
-        // stages 2..4 share one body; BROV_STAGE_UNROLL = 1 keeps it a real loop (a third of the code size: the fully
-        // unrolled step does not fit the 32 KB instruction cache), 3 unrolls it completely
-#pragma unroll kStageUnroll
+        model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, 0, x, tr0, lag, Fu, k, kl);
+#pragma unroll
         for (int s = 1; s <= 3; ++s) {
-            const Consts<T>& cs = rebase<T>(c_, (zk + s) >> 30);
-            const P ps = params_at<T, P>(p_, cs);
             const T w = (s == 1) ? T(1) : T(2);   // weight of the stage just evaluated
             const T h = (s == 3) ? dt : hdt;      // offset of the next stage
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
-                if (s == 1) acc[i * AS] = k[i]; else acc[i * AS] += w * k[i];
+                if (s == 1) acc[i] = k[i]; else acc[i] += w * k[i];
                 xs[i] = x[i] + h * k[i];
             }
             if constexpr (LAG1) {
@@ -656,21 +610,89 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c_, const P& p_,
             if constexpr (EULER_ANGLES) {
 #pragma unroll
                 for (int i = 0; i < 3; ++i) dang[i] = h * k[3 + i];
-                trig_stage(cs, tr0, dang, xs + 3, trs);
+                trig_stage(c, tr0, dang, xs + 3, trs);
             }
-            if constexpr (LAG1) model_rhs<T, MODEL, LAG1, LS, LAGW, P, const T*>(cs, ps, s, xs, trs, ls, Fu, k, kl);
-            else model_rhs<T, MODEL, LAG1, LS, LAGW, P, LP>(cs, ps, s, xs, trs, lag, Fu, k, kl);
+            model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, s, xs, trs, LAG1 ? ls : lag, Fu, k, kl);
         }
         const T dt6 = dt * T(1.0 / 6.0);
 #pragma unroll
-        for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i * AS] + k[i]);
+        for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i] + k[i]);
         if constexpr (LAG1) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) lag[i] += dt6 * (accl[i] + kl[i]);
         }
     }
-    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LS, LAGW, LP>(rebase<T>(c_, (zk + 4) >> 30), lag, Fu);
+    if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LAGW>(c, lag, Fu);
     if constexpr (ModelDim<MODEL>::QUAT) quat_renorm<T>(x + 3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// counter-based input generator: the reference's "random thrust" command signal
+//     u_k = clip(0.98 u_{k-1} + 0.02 N(0,1), -1, 1)        training/train_sim_brov2_koopmanEDMDc.py:161-164,180
+// generated inside the kernels instead of being streamed from HBM.  The normal deviates of (vehicle, step) come from
+// Philox4x32-10 (Salmon et al., SC'11) keyed on the seed with the counter (vehicle lo, vehicle hi, step lo,
+// step hi << 1 | block): any step of any vehicle can be regenerated independently, chunked / sliced / sharded rollouts
+// see the identical stream.  The AR(1) state is the only thing carried (NU values per vehicle).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* __restrict__ out) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// two N(0,1) deviates from two 32-bit words: Box-Muller on 23-bit uniforms, fast-math transcendentals (MUFU).
+// u1 in (0, 1), u2 in [0, 1): n0 = sqrt(-2 ln u1) cos(2 pi u2), n1 = sqrt(-2 ln u1) sin(2 pi u2); |n| < 5.7.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* __restrict__ n0, float* __restrict__ n1) {
+    const float f1 = __uint_as_float(0x3f800000u | (a >> 9));            // [1, 2)
+    const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
+    const float u1 = f1 - 0.99999994f;                                    // (0, 1]: never 0
+    const float th = fmaf(f2, 6.2831855f, -6.2831855f);                   // 2 pi (f2 - 1)
+    const float r = sqrtf(-1.3862944f * __log2f(u1));                     // sqrt(-2 ln u1), ln = ln2 * log2
+    float s, c;
+    __sincosf(th, &s, &c);
+    *n0 = r * c;
+    *n1 = r * s;
+}
+
+template <typename T> struct InputGen {
+    T rho;
+    T sigma[8];           // sigma * scale_j
+    T clip[8];            // clip * scale_j
+    unsigned long long vehicle0;   // global index of local vehicle 0
+    uint32_t k0, k1;      // seed
+    const T* state_in;    // [n][NU] or nullptr (zeros)
+    T* state_out;         // [n][NU] or nullptr
+    int on;
+};
+
+// advance the AR(1) input state s[NU] of global vehicle `veh` to global step `step`: s <- clip(rho s + sigma n)
+template <typename T, int NU>
+__device__ __forceinline__ void gen_advance(const InputGen<T>& g, unsigned long long veh, long long step,
+                                            T* __restrict__ s) {
+    const uint32_t v0 = (uint32_t)veh, v1 = (uint32_t)(veh >> 32);
+    const uint32_t s0 = (uint32_t)step, s1 = (uint32_t)((unsigned long long)step >> 32) << 1;
+    uint32_t w[8];
+    philox4x32_10(v0, v1, s0, s1, g.k0, g.k1, w);
+    philox4x32_10(v0, v1, s0, s1 | 1u, g.k0, g.k1, w + 4);
+    float n[8];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) box_muller(w[j], w[j + 1], &n[j], &n[j + 1]);
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+        T v = g.rho * s[j] + g.sigma[j] * T(n[j]);
+        v = v > g.clip[j] ? g.clip[j] : v;
+        s[j] = v < -g.clip[j] ? -g.clip[j] : v;
+    }
 }
 
 }  // namespace brov

@@ -20,57 +20,57 @@ namespace brov {
 constexpr int MAX_H = 4;          // horizons per se launch
 constexpr int RHS_BLOCK = 128;
 constexpr int RED9_BLOCK = 256;
-// Compile-time tuning knobs of the per-vehicle kernels; the defaults are the fastest configuration measured on B200
-// (profiles/tune_variants.py builds the alternatives, profiles/r01e / r01g *.json hold their timings):
+constexpr int TAIL_BLOCK = 256;
+// Launch shape of the per-vehicle kernels — the fastest configuration measured on B200 (alternatives and their
+// timings: profiles/r01e / r01g / r01i *.json):
 //   fp32: 128-thread blocks, 128-register cap (16 warps per SM), everything in registers;
-//   fp64: 128-thread blocks, no register cap (~248 registers, 8 warps per SM), lag state and RK4 accumulator in
-//         registers, next-step inputs prefetched, constant block in shared memory.  The smaller-footprint layouts
-//         (64-thread blocks, 144-192 register caps, lag / accumulator in shared memory) buy more warps but lose to
-//         spills and shared-memory round trips (0.59-0.71 ms against 0.48 ms per 65,536 x 100 steps).
-#ifndef BROV_F64_BLOCK
-#define BROV_F64_BLOCK 128
-#endif
-#ifndef BROV_F64_MAXREG
-#define BROV_F64_MAXREG 255
-#endif
-#ifndef BROV_F64_LAG_SMEM
-#define BROV_F64_LAG_SMEM 0
-#endif
-#ifndef BROV_F64_ACC_SMEM
-#define BROV_F64_ACC_SMEM 0
-#endif
-#ifndef BROV_F64_PREFETCH
-#define BROV_F64_PREFETCH 1
-#endif
-#ifndef BROV_F64_CONST_SMEM
-#define BROV_F64_CONST_SMEM 1
-#endif
+//   fp64: 128-thread blocks, no register cap (~250 registers, 8 warps per SM), lag state and RK4 accumulator in
+//         registers, next-step inputs prefetched, constant block in shared memory.
+constexpr int ROLLOUT_BLOCK = 128;
 #ifndef BROV_F32_MAXREG
 #define BROV_F32_MAXREG 128
 #endif
-template <typename T> struct BlockOf { static constexpr int N = sizeof(T) == 8 ? BROV_F64_BLOCK : 128; };
-template <typename T> struct MaxReg { static constexpr int N = sizeof(T) == 8 ? BROV_F64_MAXREG : BROV_F32_MAXREG; };
-template <typename T> struct Prefetch { static constexpr bool V = sizeof(T) == 8 ? (BROV_F64_PREFETCH != 0) : true; };
-// optional fp64 layouts: thruster-lag state in shared memory ([component][thread]) ...
-template <typename T> struct LagInSmem { static constexpr bool V = sizeof(T) == 8 && BROV_F64_LAG_SMEM; };
-// ... and the RK4 accumulator in shared memory
-template <typename T> struct AccInSmem { static constexpr bool V = sizeof(T) == 8 && BROV_F64_ACC_SMEM; };
+#ifndef BROV_F32_PV_MAXREG
+#define BROV_F32_PV_MAXREG 168    // Monte-Carlo fp32 kernels keep the per-vehicle coefficients in registers
+#endif
+#ifndef BROV_F32_PV_REGS
+#define BROV_F32_PV_REGS 1
+#endif
+template <typename T, bool PV> struct MaxReg {
+    static constexpr int N = sizeof(T) == 8 ? 255 : (PV && BROV_F32_PV_REGS ? BROV_F32_PV_MAXREG : BROV_F32_MAXREG);
+};
+// where the per-vehicle coefficient table lives during a launch: fp32 registers, fp64 shared memory [36][BLOCK]
+template <typename T, bool PV> struct PvInRegs { static constexpr bool V = PV && sizeof(T) == 4 && BROV_F32_PV_REGS; };
+
+// per-launch health accounting (optional): vehicles whose final state is not finite, vehicles that came within eps of
+// the Euler-angle singularity theta = +-pi/2 (fossen/BlueROV2.py:43-62 clamps cos theta there)
+struct Health {
+    unsigned long long* counters;   // [2]: non-finite, near-singular; zeroed by the library before the launch
+    double eps;
+};
 
 template <typename T> struct RolloutArgs {
     Consts<T> c;
+    InputGen<T> gen;    // gen.on: inputs are generated in the kernel, U is ignored
     const T* x0;        // [n][NX]
     T* xT;              // [n][NX] (may alias x0)
     const T* U;         // element (k, i, j) at U[k*u_stride_t + i*u_stride_n + j]
     long long u_stride_t, u_stride_n;
-    const T* lag_in;    // [n][NLAG] or nullptr (zeros); thruster model: 24 values, or 18 if lag_in_w
-    T* lag_out;         // [n][NLAG] or nullptr; thruster model: 24 values (LAGW = false) or 18 (LAGW = true)
+    const T* lag_in;    // [n][NLAG] or nullptr (zeros); thruster model: 18 values if lag_in_w, else 24 (projected on load)
+    T* lag_out;         // [n][NLAG] or nullptr; thruster model: allocation-projected [n][6][3]
     const T* pv;        // [KP_COUNT][n] or nullptr
     T* traj;            // snapshot s (global step (s+1)*stride) at traj[(s - snap_base)*n*NX ...] or nullptr
+    T* mincos;          // [n] running min of |cos theta| (in/out) or nullptr
+    T* gen_snap;        // generated inputs: AR(1) state before local step gen_snap_step is stored here ([n][NU]) or nullptr
+    Health health;      // counters == nullptr: off
     long long snap_base;
     long long step0;    // global index of the first step of this launch
     int n, steps, stride;
     int u_vec, traj_vec;
+    int u_tma;          // inputs are the per-vehicle time-major layout, 16-byte aligned: TMA bulk ring
     int lag_in_w;       // lag_in holds allocation-projected states [n][6][3]
+    int mincos_init;    // 1: ignore the incoming mincos values (first chunk)
+    int gen_snap_step;
     // Temporal tiling against wave quantisation (see rollout_kernel): the launch is cut into `quanta` time slices
     // per vehicle block; blocks take (slice, vehicle-block) work items from `ticket` in slice-major order and wait on
     // `progress[vehicle-block]` for their predecessor slice.  quanta <= 1: plain one-block-per-vehicle-block launch.
@@ -104,6 +104,7 @@ template <typename T> struct SeArgs {
     int carry_steps;      // 0 = off
     long long win0;       // global index of local window 0
     long long row0;       // global index of local row 0 of X / U
+    Health health;        // windows with a non-finite endpoint error / that came within eps of the singularity
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -139,6 +140,59 @@ __device__ __forceinline__ void load_u(const T* __restrict__ p, bool vec, T* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// per-warp input ring filled by the TMA engine: one cp.async.bulk per warp and step moves the warp's 32 input rows
+// (contiguous in the time-major per-vehicle layout [T][N][NU]) global -> shared, completion on an mbarrier.
+// No register staging, no load scoreboard in the step: the r02a capture showed the register prefetch (LDG into
+// registers one step ahead) costing the wrench fp64 kernel 20 % of its cycles in long-scoreboard stalls because the
+// loads shared a scoreboard with the first shared-memory constant load of the step.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int U_STAGES = 4;   // steps in flight per warp
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// arm the barrier with the byte count, then start the bulk copy that completes on it (bytes % 16 == 0, 16 B aligned)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+// this lane's input row out of a ring slot (rows are NU scalars, row stride = NU)
+template <typename T, int NU>
+__device__ __forceinline__ void load_u_smem(const T* __restrict__ row, T* __restrict__ u) {
+    if constexpr (sizeof(T) * NU % 16 == 0) {
+        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+        constexpr int VEC = 16 / sizeof(T);
+#pragma unroll
+        for (int j = 0; j < NU / VEC; ++j) {
+            V v = reinterpret_cast<const V*>(row)[j];
+            if constexpr (sizeof(T) == 4) { u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w; }
+            else { u[2 * j] = v.x; u[2 * j + 1] = v.y; }
+        }
+    } else {   // fp32, 6 inputs: 24-byte rows
+        const float2* q = reinterpret_cast<const float2*>(row);
+#pragma unroll
+        for (int j = 0; j < NU / 2; ++j) { float2 v = q[j]; u[2 * j] = v.x; u[2 * j + 1] = v.y; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // trajectory snapshot: registers -> per-warp shared-memory tile [32][NX] -> 128-bit coalesced streaming stores
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int NX>
@@ -170,47 +224,57 @@ __device__ __forceinline__ void snapshot_warp(T* __restrict__ tile, const T* __r
 // ---------------------------------------------------------------------------------------------------------------
 // rollout
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODEL, bool LAG1, bool LAGW = false> struct LagRegs {
-    static constexpr int N = (MODEL == MODEL_THRUSTER8) ? (LAGW ? 18 : 24) : (LAG1 ? 6 : 1);
+template <typename T, int MODEL, bool LAG1> struct LagRegs {
+    static constexpr int N = (MODEL == MODEL_THRUSTER8) ? 18 : (LAG1 ? 6 : 1);
     static constexpr bool HAS = (MODEL == MODEL_THRUSTER8) || LAG1;
-    static constexpr bool SMEM = (MODEL == MODEL_THRUSTER8) && LagInSmem<T>::V;
 };
 
-// Loads the lag state of vehicle i into its storage (registers or shared memory, stride LS).
-template <typename T, int MODEL, bool LAG1, bool LAGW, int LS, class LP>
+// Loads the lag state of vehicle i into registers; a per-thruster state [8][3] is projected on the way in.
+template <typename T, int MODEL, bool LAG1>
 __device__ __forceinline__ void load_lag(const Consts<T>& c, const T* __restrict__ src, bool src_is_w, long long i,
-                                         LP lag) {
-    constexpr int NL = LagRegs<T, MODEL, LAG1, LAGW>::N;
-    if (!LagRegs<T, MODEL, LAG1, LAGW>::HAS || src == nullptr) {
+                                         T* __restrict__ lag) {
+    constexpr int NL = LagRegs<T, MODEL, LAG1>::N;
+    if (!LagRegs<T, MODEL, LAG1>::HAS || src == nullptr) {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) lag[j * LS] = T(0);
+        for (int j = 0; j < NL; ++j) lag[j] = T(0);
         return;
     }
-    if constexpr (MODEL == MODEL_THRUSTER8 && LAGW) {
+    if constexpr (MODEL == MODEL_THRUSTER8) {
         if (src_is_w) {
 #pragma unroll
-            for (int j = 0; j < 18; ++j) lag[j * LS] = __ldcg(src + i * 18 + j);
+            for (int j = 0; j < 18; ++j) lag[j] = __ldcg(src + i * 18 + j);
         } else {
             T t[24];
 #pragma unroll
             for (int j = 0; j < 24; ++j) t[j] = __ldcg(src + i * 24 + j);
-            project_lag<T, LS, LP>(c, t, lag);
+            project_lag<T>(c, t, lag);
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < NL; ++j) lag[j * LS] = __ldcg(src + i * NL + j);
+        for (int j = 0; j < NL; ++j) lag[j] = __ldcg(src + i * NL + j);
     }
 }
 
-template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool LAGW>
-__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(MaxReg<T>::N)
+template <typename T> __device__ __forceinline__ bool finite_(T v) { return abs_(v) <= (sizeof(T) == 8 ? T(1.7976931348623157e308) : T(3.4028234663852886e38)); }
+
+// warp-aggregated health counters: one atomic per warp and counter
+__device__ __forceinline__ void count_health(const Health& h, bool bad, bool near_singular, int lane) {
+    const unsigned bm = __ballot_sync(0xffffffffu, bad), sm = __ballot_sync(0xffffffffu, near_singular);
+    if (lane == 0) {
+        if (bm) atomicAdd(h.counters + 0, (unsigned long long)__popc(bm));
+        if (sm) atomicAdd(h.counters + 1, (unsigned long long)__popc(sm));
+    }
+}
+
+// GEN: the inputs are generated in the kernel (gen_advance) instead of being read from a.U
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__((MaxReg<T, PV>::N))
 rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
-    constexpr int BLOCK = BlockOf<T>::N;
+    constexpr int BLOCK = ROLLOUT_BLOCK;
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NU = ModelDim<MODEL>::NU;
-    using LR = LagRegs<T, MODEL, LAG1, LAGW>;
+    using LR = LagRegs<T, MODEL, LAG1>;
     constexpr int NL = LR::N;
-    constexpr int LS = LR::SMEM ? BLOCK : 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
 
@@ -229,9 +293,8 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
         __shared__ int s_item;
         if (tid == 0) s_item = atomicAdd(a.ticket, 1);
         __syncthreads();
-        // the ticket is the same for every thread of the block; passing it through a warp reduction lets the compiler see
-        // that (REDUX writes a uniform register), so slice bounds, the step loop and the re-based constant loads of the
-        // fp64 build all run on the uniform datapath
+        // the ticket is the same for every thread of the block; passing it through a warp reduction lets the compiler
+        // see that (REDUX writes a uniform register), so slice bounds and the step loop run on the uniform datapath
         const int item = __reduce_max_sync(0xffffffffu, s_item);
         slice = item / a.nvblocks;
         vb = item - slice * a.nvblocks;
@@ -251,9 +314,10 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const bool live = gi < a.n;
     const long long i = live ? gi : (long long)a.n - 1;  // dead lanes shadow the last vehicle, never store
 
-    // fp64: the constant block is staged into shared memory and read from there (BROV_F64_CONST_SMEM): sm_100 feeds
-    // FP instructions from uniform registers, and the ~130 64-bit constants of a step do not fit them (see rebase())
-    constexpr bool CSM = sizeof(T) == 8 && BROV_F64_CONST_SMEM;
+    // fp64: the constant block is staged into shared memory and read from there: sm_100 feeds FP instructions from
+    // uniform registers, and the ~130 64-bit constants of a step do not fit them (kernel-argument operands end up
+    // hoisted into regular registers and shuffled back through R2UR / UMOV: 0.491 against 0.481 ms, r01e)
+    constexpr bool CSM = sizeof(T) == 8;
     __shared__ __align__(16) unsigned char cs_raw[CSM ? sizeof(Consts<T>) : 16];
     if constexpr (CSM) {
         const T* src = reinterpret_cast<const T*>(&a.c);
@@ -263,38 +327,24 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     }
     const Consts<T>& cc = CSM ? *reinterpret_cast<const Consts<T>*>(cs_raw) : a.c;
 
-    // shared memory: [per-vehicle coefficient table][lag state (fp64)][snapshot tiles]
-    typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type p;
-    if constexpr (PV) {
+    // per-vehicle (Monte-Carlo) coefficients: registers (fp32) or a shared-memory table [36][BLOCK] (fp64)
+    constexpr bool PVR = PvInRegs<T, PV>::V;
+    typename std::conditional<PVR, ParamsRegs<T>,
+                              typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type>::type p;
+    if constexpr (PVR) {
+#pragma unroll
+        for (int j = 0; j < KP_COUNT; ++j) p.v[j] = __ldg(a.pv + (long long)j * a.n + i);
+    } else if constexpr (PV) {
 #pragma unroll 4
         for (int j = 0; j < KP_COUNT; ++j) smem[j * BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
         p.base = smem + tid;
         p.pitch = BLOCK;
         smem += KP_COUNT * BLOCK;
+        __syncthreads();
     } else {
         p.kp = cc.kp;
     }
-    // shared-memory residents are accessed through volatile pointers: without it the compiler promotes them back
-    // into registers for the whole step, which is exactly what the placement is meant to avoid
-    using LP = typename std::conditional<LR::SMEM, volatile T*, T*>::type;
-    T lag_regs[LR::SMEM ? 1 : NL];
-    LP lag;
-    if constexpr (LR::SMEM) {
-        lag = smem + tid;
-        smem += NL * BLOCK;
-    } else {
-        lag = lag_regs;
-    }
-    constexpr bool ACC_SM = AccInSmem<T>::V && INTEG == INTEG_RK4;
-    constexpr int AS = ACC_SM ? BLOCK : 1;
-    using AP = typename std::conditional<ACC_SM, volatile T*, T*>::type;
-    AP acc_sm = nullptr;
-    if constexpr (ACC_SM) {
-        acc_sm = smem + tid;
-        smem += NX * BLOCK;
-    }
     T* tiles = smem;
-    if constexpr (PV) __syncthreads();
 
     // slice 0 starts from (x0, lag_in); later slices continue from what the predecessor left in (xT, lag_out).
     // L2-only loads: another SM may have written these lines during this launch.
@@ -302,50 +352,82 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     T x[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) x[j] = __ldcg(xsrc + i * NX + j);
-    if (slice > 0) load_lag<T, MODEL, LAG1, LAGW, LS, LP>(a.c, a.lag_out, LAGW, i, lag);
-    else load_lag<T, MODEL, LAG1, LAGW, LS, LP>(a.c, a.lag_in, a.lag_in_w != 0, i, lag);
+    T lag[NL];
+    if (slice > 0) load_lag<T, MODEL, LAG1>(a.c, a.lag_out, true, i, lag);
+    else load_lag<T, MODEL, LAG1>(a.c, a.lag_in, a.lag_in_w != 0, i, lag);
+    T mc = T(1);   // running min of |cos theta|
+    if (a.mincos && (slice > 0 || !a.mincos_init)) mc = __ldcg(a.mincos + i);
 
-    const T* up = a.U + i * a.u_stride_n + (long long)k_begin * a.u_stride_t;
-    const bool uvec = a.u_vec != 0;
-    const bool stream = a.u_stride_n != 0;  // per-vehicle inputs are read exactly once: evict-first
     const int nsteps = k_end - k_begin;
+    const long long warp_v0 = (long long)vb * BLOCK + warp * 32;
+    const long long rem = (long long)a.n - warp_v0;
+    const int warp_n = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem));   // live vehicles of this warp
+    const int n_valid = warp_n * NX;
+
+    // Inputs.  Generated: u is the AR(1) state of the command signal, advanced in registers.  Streamed, per-vehicle
+    // time-major layout: the warp's rows of step k are one contiguous block, fetched U_STAGES - 1 steps ahead by the
+    // TMA engine into the warp's shared-memory ring.  Other layouts (one series shared by all vehicles, one constant
+    // row per vehicle, unaligned buffers): plain loads, which hit L1 after the first touch.
     T u[NU];
-    if (nsteps > 0) {
-        if (stream) load_u<T, NU, true>(up, uvec, u); else load_u<T, NU, false>(up, uvec, u);
+    constexpr uint32_t ROW_BYTES = NU * sizeof(T);
+    __shared__ __align__(8) uint64_t u_bar[BLOCK / 32][U_STAGES];
+    T* ring = tiles + (a.traj ? BLOCK * NX : 0) + warp * (U_STAGES * 32 * NU);
+    const uint32_t warp_bytes = (uint32_t)warp_n * ROW_BYTES;
+    const bool tma = !GEN && a.u_tma && warp_n > 0 && (warp_bytes % 16u) == 0;   // uniform per warp
+    const T* up = a.U + i * a.u_stride_n + (long long)k_begin * a.u_stride_t;
+    const T* wsrc = a.U + warp_v0 * NU + (long long)k_begin * a.u_stride_t;     // row of the warp's first vehicle
+    const T* myrow = ring + (lane < warp_n ? lane : (warp_n > 0 ? warp_n - 1 : 0)) * NU;
+    const bool uvec = a.u_vec != 0;
+    if constexpr (GEN) {
+        const T* ssrc = slice > 0 ? a.gen.state_out : a.gen.state_in;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) u[j] = ssrc ? __ldcg(ssrc + i * NU + j) : T(0);
+    } else if (tma) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < U_STAGES; ++s) mbar_init(&u_bar[warp][s], 1);
+            mbar_init_fence();
+#pragma unroll
+            for (int s = 0; s < U_STAGES - 1; ++s)
+                if (s < nsteps) tma_load_1d(ring + s * 32 * NU, wsrc + (long long)s * a.u_stride_t, warp_bytes, &u_bar[warp][s]);
+        }
+        __syncwarp();
     }
 
     const long long gstep0 = a.step0 + k_begin;
+    const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)i;
     int countdown = a.traj ? (int)(a.stride - (gstep0 % a.stride)) : 0x7fffffff;
     long long snap = a.traj ? (gstep0 / a.stride - a.snap_base) : 0;
-    const long long warp_v0 = (long long)vb * BLOCK + warp * 32;
-    const long long rem = (long long)a.n - warp_v0;
-    const int n_valid = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem)) * NX;
 
-    constexpr bool PREFETCH = Prefetch<T>::V;  // next step's inputs ride in registers across the step
-    // uniform counter feeding rebase(): derived from kernel arguments only, so that it lives in a uniform register and
-    // the re-based constant loads become LDCU.64 c[0][UR + off] (a per-thread register index would make them LDC)
-    int zc = a.stride & 1;
-    for (int k = 0; k < nsteps; ++k, zc += 8) {
-        T un[NU];
-        if constexpr (PREFETCH) {
-            const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
-            if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
-        } else if (k > 0) {
-            const T* cur = up + (long long)k * a.u_stride_t;
-            if (stream) load_u<T, NU, true>(cur, uvec, u); else load_u<T, NU, false>(cur, uvec, u);
+    for (int k = 0; k < nsteps; ++k) {
+        if constexpr (GEN) {
+            if (a.gen_snap && k_begin + k == a.gen_snap_step && live) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) a.gen_snap[i * NU + j] = u[j];
+            }
+            gen_advance<T, NU>(a.gen, veh, gstep0 + k, u);
+        } else if (tma) {
+            // refill the slot read one step ago (all lanes are past those reads: they sit before the previous step)
+            const int kn = k + U_STAGES - 1;
+            __syncwarp();
+            if (lane == 0 && kn < nsteps)
+                tma_load_1d(ring + (kn % U_STAGES) * 32 * NU, wsrc + (long long)kn * a.u_stride_t, warp_bytes,
+                            &u_bar[warp][kn % U_STAGES]);
+            mbar_wait(&u_bar[warp][k % U_STAGES], (uint32_t)(k / U_STAGES) & 1u);
+            load_u_smem<T, NU>(myrow + (k % U_STAGES) * 32 * NU, u);
+        } else {
+            load_u<T, NU, false>(up + (long long)k * a.u_stride_t, uvec, u);
         }
 
-        integrate_step<T, MODEL, INTEG, LAG1, LS, LAGW, AS, decltype(p), LP, AP>(cc, p, x, lag, u, acc_sm, zc);
+        T acth;
+        integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth);
+        mc = acth < mc ? acth : mc;
 
         if (--countdown == 0) {
             countdown = a.stride;
             T* dst = a.traj + (snap * a.n + warp_v0) * NX;
             snapshot_warp<T, NX>(tiles + warp * 32 * NX, x, dst, n_valid, a.traj_vec != 0, lane);
             ++snap;
-        }
-        if constexpr (PREFETCH) {
-#pragma unroll
-            for (int j = 0; j < NU; ++j) u[j] = un[j];
         }
     }
 
@@ -354,8 +436,21 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
         for (int j = 0; j < NX; ++j) a.xT[i * NX + j] = x[j];
         if (LR::HAS && a.lag_out) {
 #pragma unroll
-            for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j * LS];
+            for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j];
         }
+        if (a.mincos) a.mincos[i] = mc;
+        if constexpr (GEN) {
+            if (a.gen.state_out) {
+#pragma unroll
+                for (int j = 0; j < NU; ++j) a.gen.state_out[i * NU + j] = u[j];
+            }
+        }
+    }
+    if (a.health.counters && (a.quanta <= 1 || slice == a.quanta - 1)) {
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < NX; ++j) bad |= !finite_(x[j]);
+        count_health(a.health, live && bad, live && ((double)mc < a.health.eps), lane);
     }
     if (a.quanta > 1) {  // publish this slice: state stores first, then the flag
         __threadfence();
@@ -365,26 +460,117 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// per-thruster lag states after a rollout (thruster model): ThrusterLag._x of each thruster, [n][8][3]
+// (fossen/BlueROV2.py:503-510).  The rollout kernel integrates the six allocation-projected filters; the per-thruster
+// states are not recoverable from those, but each is a STABLE linear filter of its own thruster's input alone, so its
+// state after the call is determined — to below one ulp — by the last `depth` inputs (brov_se_carry_steps: ||A^depth||
+// < 1e-22) or, for a shorter call, by lag_in and all of them.  One thread per (vehicle, thruster) replays steps
+// [first, steps): consecutive threads read consecutive scalars of the input rows and write consecutive triples.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct LagTailArgs {
+    Consts<T> c;
+    InputGen<T> gen;        // gen.on: regenerate the inputs from gen_state (one thread per vehicle)
+    const T* U;
+    long long u_stride_t, u_stride_n;
+    const T* lag_in;        // [n][8][3] state before step `first`, or nullptr = zeros
+    T* lag_out;             // [n][8][3] (may alias lag_in)
+    const T* gen_state;     // generated inputs: AR(1) state before step `first`, [n][8], or nullptr = zeros
+    long long step0;
+    int n, first, steps;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(TAIL_BLOCK) lag_tail_kernel(const __grid_constant__ LagTailArgs<T> a) {
+    const long long g = (long long)blockIdx.x * TAIL_BLOCK + threadIdx.x;
+    if (g >= (long long)a.n * 8) return;
+    const long long i = g >> 3;
+    const int t = (int)(g & 7);
+    T x[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) x[j] = a.lag_in ? a.lag_in[g * 3 + j] : T(0);
+    const T* up = a.U + i * a.u_stride_n + t;
+    for (int k = a.first; k < a.steps; ++k) {
+        const T F = thrust_poly<T>(__ldg(up + (long long)k * a.u_stride_t));
+        lag_advance1<T>(a.c, x, F);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a.lag_out[g * 3 + j] = x[j];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(RHS_BLOCK) lag_tail_gen_kernel(const __grid_constant__ LagTailArgs<T> a) {
+    const long long i = (long long)blockIdx.x * RHS_BLOCK + threadIdx.x;
+    if (i >= a.n) return;
+    T lag[24], s[8];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) lag[j] = a.lag_in ? a.lag_in[i * 24 + j] : T(0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = a.gen_state ? a.gen_state[i * 8 + j] : T(0);
+    const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)i;
+    for (int k = a.first; k < a.steps; ++k) {
+        gen_advance<T, 8>(a.gen, veh, a.step0 + k, s);
+        T F[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(s[j]);
+        lag_advance<T, false>(a.c, lag, F);
+    }
+#pragma unroll
+    for (int j = 0; j < 24; ++j) a.lag_out[i * 24 + j] = lag[j];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the generated command signal, materialised: U[k][j][:] for steps step0 .. step0+steps-1 and the selected vehicles
+// first, first + vstride, ... (n_sel of them).  Same device function as the rollout kernels (gen_advance): a rollout
+// fed with this array reproduces the generated-input rollout bit for bit, and the CPU oracle consumes the same values.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T> struct GenInputsArgs {
+    InputGen<T> gen;        // state_in / state_out are indexed by SELECTED vehicle j: [n_sel][NU]
+    T* out;                 // [steps][n_sel][NU]
+    long long first, vstride, n_sel;
+    long long step0;
+    int steps;
+};
+
+template <typename T, int NU>
+__global__ void __launch_bounds__(RHS_BLOCK) gen_inputs_kernel(const __grid_constant__ GenInputsArgs<T> a) {
+    const long long j = (long long)blockIdx.x * RHS_BLOCK + threadIdx.x;
+    if (j >= a.n_sel) return;
+    const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)(a.first + j * a.vstride);
+    T s[NU];
+#pragma unroll
+    for (int q = 0; q < NU; ++q) s[q] = a.gen.state_in ? a.gen.state_in[j * NU + q] : T(0);
+    for (int k = 0; k < a.steps; ++k) {
+        gen_advance<T, NU>(a.gen, veh, a.step0 + k, s);
+#pragma unroll
+        for (int q = 0; q < NU; ++q) a.out[((long long)k * a.n_sel + j) * NU + q] = s[q];
+    }
+    if (a.gen.state_out) {
+#pragma unroll
+        for (int q = 0; q < NU; ++q) a.gen.state_out[j * NU + q] = s[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // single state-derivative evaluation (the reference's dynamics(): the 3rd-order lag advances by ONE sub-step)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, bool LAG1, bool PV>
 __global__ void __launch_bounds__(RHS_BLOCK) rhs_kernel(const __grid_constant__ RhsArgs<T> a) {
-    constexpr int ROLLOUT_BLOCK = RHS_BLOCK;
+    constexpr int BLOCK = RHS_BLOCK;
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NU = ModelDim<MODEL>::NU;
-    constexpr int NL = LagRegs<T, MODEL, LAG1>::N;
+    constexpr int NL = (MODEL == MODEL_THRUSTER8) ? 24 : (LAG1 ? 6 : 1);   // per-thruster lag states here
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* smem = reinterpret_cast<T*>(smem_raw);
     const int tid = threadIdx.x;
-    const long long gi = (long long)blockIdx.x * ROLLOUT_BLOCK + tid;
+    const long long gi = (long long)blockIdx.x * BLOCK + tid;
     const bool live = gi < a.n;
     const long long i = live ? gi : (long long)a.n - 1;
     typename std::conditional<PV, ParamsShared<T>, ParamsConst<T>>::type p;
     if constexpr (PV) {
-        for (int j = 0; j < KP_COUNT; ++j) smem[j * ROLLOUT_BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
+        for (int j = 0; j < KP_COUNT; ++j) smem[j * BLOCK + tid] = __ldg(a.pv + (long long)j * a.n + i);
         __syncthreads();
         p.base = smem + tid;
-        p.pitch = ROLLOUT_BLOCK;
+        p.pitch = BLOCK;
     } else {
         p.kp = a.c.kp;
     }
@@ -400,7 +586,7 @@ __global__ void __launch_bounds__(RHS_BLOCK) rhs_kernel(const __grid_constant__ 
     if constexpr (ModelDim<MODEL>::DI) di_accel<T, NU>(a.c, u, Fu);
     Trig<T> tr;
     if constexpr (!ModelDim<MODEL>::QUAT) trig_full<T>(x + 3, tr);
-    model_rhs<T, MODEL, LAG1, 1, false, decltype(p), const T*>(a.c, p, 0, x, tr, lag, Fu, xd, lagd);
+    model_rhs<T, MODEL, LAG1, false, decltype(p)>(a.c, p, 0, x, tr, lag, Fu, xd, lagd);
     if (!live) return;
 #pragma unroll
     for (int j = 0; j < NX; ++j) a.xdot[i * (NX + (LAG1 ? 6 : 0)) + j] = xd[j];
@@ -410,7 +596,7 @@ __global__ void __launch_bounds__(RHS_BLOCK) rhs_kernel(const __grid_constant__ 
     }
     if constexpr (MODEL == MODEL_THRUSTER8) {
         if (a.lag) {
-            lag_advance<T, 1, false, T*>(a.c, lag, Fu);
+            lag_advance<T, false>(a.c, lag, Fu);
 #pragma unroll
             for (int j = 0; j < NL; ++j) a.lag[i * NL + j] = lag[j];
         }
@@ -439,11 +625,11 @@ __global__ void __launch_bounds__(RHS_BLOCK) thruster_wrench_kernel(const __grid
     for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
 #pragma unroll
     for (int j = 0; j < 24; ++j) lag[j] = a.lag ? a.lag[i * 24 + j] : T(0);
-    thruster_tau<T, 1, false, const T*>(a.c, 0, lag, F, tau);
+    thruster_tau<T, false>(a.c, 0, lag, F, tau);
 #pragma unroll
     for (int j = 0; j < 6; ++j) a.tau[i * 6 + j] = tau[j];
     if (a.lag) {
-        lag_advance<T, 1, false, T*>(a.c, lag, F);
+        lag_advance<T, false>(a.c, lag, F);
 #pragma unroll
         for (int j = 0; j < 24; ++j) a.lag[i * 24 + j] = lag[j];
     }
@@ -479,17 +665,17 @@ __global__ void __launch_bounds__(RHS_BLOCK) thruster_series_kernel(const __grid
         load_u<T, 8, false>(a.U + r * 8, vec, u);
 #pragma unroll
         for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
-        lag_advance<T, 1, false, T*>(a.c, lag, F);
+        lag_advance<T, false>(a.c, lag, F);
     }
     load_u<T, 8, false>(a.U + k * 8, vec, u);
 #pragma unroll
     for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(u[j]);
     T tau[6];
-    thruster_tau<T, 1, false, const T*>(a.c, 0, lag, F, tau);
+    thruster_tau<T, false>(a.c, 0, lag, F, tau);
 #pragma unroll
     for (int j = 0; j < 6; ++j) a.tau[k * 6 + j] = tau[j];
     if (a.lag_end && k == a.rows - 1) {
-        lag_advance<T, 1, false, T*>(a.c, lag, F);
+        lag_advance<T, false>(a.c, lag, F);
 #pragma unroll
         for (int j = 0; j < 24; ++j) a.lag_end[j] = lag[j];
     }
@@ -499,17 +685,15 @@ __global__ void __launch_bounds__(RHS_BLOCK) thruster_series_kernel(const __grid
 // multi-horizon endpoint squared error over sliding windows
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, int INTEG>
-__global__ void __launch_bounds__(BlockOf<T>::N) __maxnreg__(MaxReg<T>::N)
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__((MaxReg<T, false>::N))
 se_kernel(const __grid_constant__ SeArgs<T> a) {
-    constexpr int BLOCK = BlockOf<T>::N;
+    constexpr int BLOCK = ROLLOUT_BLOCK;
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NU = ModelDim<MODEL>::NU;
-    // the evaluator never returns lag states: the thruster model always runs on the allocation-projected lag
-    using LR = LagRegs<T, MODEL, false, true>;
+    // the evaluator never returns lag states: the thruster model runs on the allocation-projected lag
+    using LR = LagRegs<T, MODEL, false>;
     constexpr int NL = LR::N;
-    constexpr int LS = LR::SMEM ? BLOCK : 1;
     __shared__ double red[BLOCK / 32][MAX_H];
-    __shared__ T lag_sm[LR::SMEM ? NL * BLOCK : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long gk = (long long)blockIdx.x * BLOCK + tid;
     const bool live = gk < a.nwin;
@@ -521,17 +705,8 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     T x[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + kr * NX + j);
-    using LP = typename std::conditional<LR::SMEM, volatile T*, T*>::type;
-    constexpr bool ACC_SM = AccInSmem<T>::V && INTEG == INTEG_RK4;
-    constexpr int AS = ACC_SM ? BLOCK : 1;
-    using AP = typename std::conditional<ACC_SM, volatile T*, T*>::type;
-    __shared__ T acc_store[ACC_SM ? NX * BLOCK : 1];
-    T lag_regs[LR::SMEM ? 1 : NL];
-    LP lag;
-    if constexpr (LR::SMEM) lag = lag_sm + tid; else lag = lag_regs;
-    AP acc_sm = nullptr;
-    if constexpr (ACC_SM) acc_sm = acc_store + tid;
-    load_lag<T, MODEL, false, true, LS, LP>(a.c, a.lag0, false, k, lag);
+    T lag[NL];
+    load_lag<T, MODEL, false>(a.c, a.lag0, false, k, lag);
     const bool uvec = ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && (sizeof(T) * NU % 16 == 0);
     if constexpr (MODEL == MODEL_THRUSTER8) {
         if (a.carry_steps > 0 && live) {
@@ -547,7 +722,7 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(u[i]);
                 allocate_wrench<T>(a.c, F, TF);
-                lag_advance<T, LS, true, LP>(a.c, lag, TF);
+                lag_advance<T, true>(a.c, lag, TF);
             }
         }
     }
@@ -559,11 +734,14 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     // window k may run j steps while row k + j exists
     long long room = (long long)a.rows - 1 - kr;
     const int nsteps = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
-    int zc = a.nH & 1;   // uniform counter for rebase(), see rollout_kernel
-    for (int j = 0; j < nsteps; ++j, zc += 8) {
+    T mc = T(1);
+    bool bad = false;
+    for (int j = 0; j < nsteps; ++j) {
         T u[NU];
         load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
-        integrate_step<T, MODEL, INTEG, false, LS, true, AS, decltype(p), LP, AP>(a.c, p, x, lag, u, acc_sm, zc);
+        T acth;
+        integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth);
+        mc = acth < mc ? acth : mc;
 #pragma unroll
         for (int h = 0; h < MAX_H; ++h) {
             if (h < a.nH && j + 1 == a.H[h]) {
@@ -575,9 +753,11 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
                     s += e * e;
                 }
                 se[h] = s;
+                bad |= !(s <= 1.7976931348623157e308);
             }
         }
     }
+    if (a.health.counters) count_health(a.health, live && bad, live && ((double)mc < a.health.eps), lane);
 #pragma unroll
     for (int h = 0; h < MAX_H; ++h) {
         double v = se[h];
@@ -703,9 +883,10 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 // launchers (defined in brov_kernels_impl.cuh, instantiated per scalar type)
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
-cudaError_t launch_rollout(int model, int integ, bool lag1, bool lagw, const RolloutArgs<T>& a, cudaStream_t st);
-template <typename T> int rollout_blocks_per_sm(int model, int integ, bool lag1, bool lagw, bool pv, bool traj);
-template <typename T> int rollout_block_threads();
+cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st);
+template <typename T> int rollout_blocks_per_sm(int model, int integ, bool lag1, bool pv, bool gen, bool traj);
+template <typename T> cudaError_t launch_lag_tail(const LagTailArgs<T>& a, cudaStream_t st);
+template <typename T> cudaError_t launch_gen_inputs(int nu, const GenInputsArgs<T>& a, cudaStream_t st);
 template <typename T>
 cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t st);
 template <typename T>

@@ -1,22 +1,24 @@
 // brov_kernels_impl.cuh — runtime -> template dispatch.  Included by brov_kernels_f32.cu / brov_kernels_f64.cu; each
-// instantiates every (model, integrator, lag1, per-vehicle, lag representation) combination for its scalar type.
+// instantiates every (model, integrator, lag1, per-vehicle, generated-input) combination for its scalar type.
 #pragma once
 #include "brov_kernels.cuh"
 
 namespace brov {
 
-template <typename T, int MODEL, int INTEG, bool LAG1, bool LAGW>
-static cudaError_t rollout_go(const RolloutArgs<T>& a, cudaStream_t st) {
-    constexpr int BLOCK = BlockOf<T>::N;
+// dynamic shared memory of a rollout launch: snapshot tiles, fp64 per-vehicle coefficient table
+template <typename T, int MODEL, bool PV> static size_t rollout_smem(bool traj) {
     constexpr int NX = ModelDim<MODEL>::NX;
-    using LR = LagRegs<T, MODEL, LAG1, LAGW>;
-    const int grid = ((a.n + BLOCK - 1) / BLOCK) * (a.quanta > 1 ? a.quanta : 1);
-    size_t smem = a.traj ? (size_t)(BLOCK / 32) * 32 * NX * sizeof(T) : 0;
-    if (LR::SMEM) smem += (size_t)LR::N * BLOCK * sizeof(T);
-    if (AccInSmem<T>::V && INTEG == INTEG_RK4) smem += (size_t)NX * BLOCK * sizeof(T);
-    if (a.pv) {
-        smem += (size_t)KP_COUNT * BLOCK * sizeof(T);
-        auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, true, LAGW>;
+    size_t smem = traj ? (size_t)(ROLLOUT_BLOCK / 32) * 32 * NX * sizeof(T) : 0;
+    if (PV && !PvInRegs<T, PV>::V) smem += (size_t)KP_COUNT * ROLLOUT_BLOCK * sizeof(T);
+    return smem;
+}
+
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
+static cudaError_t rollout_launch(const RolloutArgs<T>& a, cudaStream_t st) {
+    const int grid = ((a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK) * (a.quanta > 1 ? a.quanta : 1);
+    const size_t smem = rollout_smem<T, MODEL, PV>(a.traj != nullptr);
+    auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN>;
+    if (smem > 16 * 1024) {
         // static + dynamic shared memory beyond 48 KB needs the opt-in (the fp64 coefficient table alone is 36 KB)
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, kern);
@@ -25,77 +27,91 @@ static cudaError_t rollout_go(const RolloutArgs<T>& a, cudaStream_t st) {
             e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        kern<<<grid, BLOCK, smem, st>>>(a);
-    } else {
-        rollout_kernel<T, MODEL, INTEG, LAG1, false, LAGW><<<grid, BLOCK, smem, st>>>(a);
     }
+    kern<<<grid, ROLLOUT_BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 // resident blocks per SM of the kernel that launch_rollout would pick (for the temporal-tiling heuristic)
-template <typename T, int MODEL, int INTEG, bool LAG1, bool LAGW>
-static int rollout_occ(bool pv, bool traj) {
-    constexpr int BLOCK = BlockOf<T>::N;
-    constexpr int NX = ModelDim<MODEL>::NX;
-    using LR = LagRegs<T, MODEL, LAG1, LAGW>;
-    size_t smem = traj ? (size_t)(BLOCK / 32) * 32 * NX * sizeof(T) : 0;
-    if (LR::SMEM) smem += (size_t)LR::N * BLOCK * sizeof(T);
-    if (AccInSmem<T>::V && INTEG == INTEG_RK4) smem += (size_t)NX * BLOCK * sizeof(T);
-    if (pv) smem += (size_t)KP_COUNT * BLOCK * sizeof(T);
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
+static int rollout_occ(bool traj) {
     int nb = 0;
-    cudaError_t e = pv ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, true, LAGW>, BLOCK, smem)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, false, LAGW>, BLOCK, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN>,
+                                                                  ROLLOUT_BLOCK, rollout_smem<T, MODEL, PV>(traj));
     return e == cudaSuccess ? nb : 0;
 }
 
-template <typename T>
-int rollout_blocks_per_sm(int model, int integ, bool lag1, bool lagw, bool pv, bool traj) {
-    const bool rk4 = integ == INTEG_RK4;
+// runtime -> template dispatch; F is a generic lambda called with std::integral_constant tags
+template <typename T, class F>
+static auto rollout_dispatch(int model, int integ, bool lag1, bool pv, bool gen, F&& f) {
+    auto with_flags = [&](auto M, auto L1) {
+        auto with_integ = [&](auto I) {
+            if (pv) return gen ? f(M, I, L1, std::true_type{}, std::true_type{}) : f(M, I, L1, std::true_type{}, std::false_type{});
+            return gen ? f(M, I, L1, std::false_type{}, std::true_type{}) : f(M, I, L1, std::false_type{}, std::false_type{});
+        };
+        return integ == INTEG_RK4 ? with_integ(std::integral_constant<int, INTEG_RK4>{})
+                                  : with_integ(std::integral_constant<int, INTEG_EULER>{});
+    };
+    using std::integral_constant;
     switch (model) {
-        case MODEL_THRUSTER8:
-            if (lagw) return rk4 ? rollout_occ<T, MODEL_THRUSTER8, INTEG_RK4, false, true>(pv, traj) : rollout_occ<T, MODEL_THRUSTER8, INTEG_EULER, false, true>(pv, traj);
-            return rk4 ? rollout_occ<T, MODEL_THRUSTER8, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_THRUSTER8, INTEG_EULER, false, false>(pv, traj);
+        case MODEL_THRUSTER8: return with_flags(integral_constant<int, MODEL_THRUSTER8>{}, std::false_type{});
         case MODEL_WRENCH12:
-            if (lag1) return rk4 ? rollout_occ<T, MODEL_WRENCH12, INTEG_RK4, true, false>(pv, traj) : rollout_occ<T, MODEL_WRENCH12, INTEG_EULER, true, false>(pv, traj);
-            return rk4 ? rollout_occ<T, MODEL_WRENCH12, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_WRENCH12, INTEG_EULER, false, false>(pv, traj);
+            return lag1 ? with_flags(integral_constant<int, MODEL_WRENCH12>{}, std::true_type{})
+                        : with_flags(integral_constant<int, MODEL_WRENCH12>{}, std::false_type{});
         case MODEL_QUAT13:
-            if (lag1) return rk4 ? rollout_occ<T, MODEL_QUAT13, INTEG_RK4, true, false>(pv, traj) : rollout_occ<T, MODEL_QUAT13, INTEG_EULER, true, false>(pv, traj);
-            return rk4 ? rollout_occ<T, MODEL_QUAT13, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_QUAT13, INTEG_EULER, false, false>(pv, traj);
-        case MODEL_DI12_U8:
-            return rk4 ? rollout_occ<T, MODEL_DI12_U8, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_DI12_U8, INTEG_EULER, false, false>(pv, traj);
-        case MODEL_DI12_U6:
-            return rk4 ? rollout_occ<T, MODEL_DI12_U6, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_DI12_U6, INTEG_EULER, false, false>(pv, traj);
-        case MODEL_DIQ13_U6:
-            return rk4 ? rollout_occ<T, MODEL_DIQ13_U6, INTEG_RK4, false, false>(pv, traj) : rollout_occ<T, MODEL_DIQ13_U6, INTEG_EULER, false, false>(pv, traj);
+            return lag1 ? with_flags(integral_constant<int, MODEL_QUAT13>{}, std::true_type{})
+                        : with_flags(integral_constant<int, MODEL_QUAT13>{}, std::false_type{});
+        case MODEL_DI12_U8: return with_flags(integral_constant<int, MODEL_DI12_U8>{}, std::false_type{});
+        case MODEL_DI12_U6: return with_flags(integral_constant<int, MODEL_DI12_U6>{}, std::false_type{});
+        default: return with_flags(integral_constant<int, MODEL_DIQ13_U6>{}, std::false_type{});
     }
-    return 0;
 }
-template <typename T> int rollout_block_threads() { return BlockOf<T>::N; }
 
-template <typename T, int MODEL, bool LAG1, bool LAGW>
-static cudaError_t rollout_integ(int integ, const RolloutArgs<T>& a, cudaStream_t st) {
-    return integ == INTEG_RK4 ? rollout_go<T, MODEL, INTEG_RK4, LAG1, LAGW>(a, st)
-                              : rollout_go<T, MODEL, INTEG_EULER, LAG1, LAGW>(a, st);
+// the double-integrator models have no per-vehicle table (brov_set_vehicle_params refuses it): their PV kernels are
+// never instantiated
+template <int MODEL, bool PV> struct RolloutExists { static constexpr bool V = !(PV && ModelDim<MODEL>::DI); };
+
+template <typename T>
+int rollout_blocks_per_sm(int model, int integ, bool lag1, bool pv, bool gen, bool traj) {
+    if (model < MODEL_THRUSTER8 || model > MODEL_DIQ13_U6) return 0;
+    return rollout_dispatch<T>(model, integ, lag1, pv, gen, [&](auto M, auto I, auto L1, auto PV, auto G) -> int {
+        if constexpr (RolloutExists<decltype(M)::value, decltype(PV)::value>::V)
+            return rollout_occ<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value>(traj);
+        else
+            return 0;
+    });
 }
 
 template <typename T>
-cudaError_t launch_rollout(int model, int integ, bool lag1, bool lagw, const RolloutArgs<T>& a, cudaStream_t st) {
+cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st) {
     if (a.n <= 0 || a.steps <= 0) return cudaSuccess;
-    switch (model) {
-        case MODEL_THRUSTER8:
-            return lagw ? rollout_integ<T, MODEL_THRUSTER8, false, true>(integ, a, st)
-                        : rollout_integ<T, MODEL_THRUSTER8, false, false>(integ, a, st);
-        case MODEL_WRENCH12:
-            return lag1 ? rollout_integ<T, MODEL_WRENCH12, true, false>(integ, a, st)
-                        : rollout_integ<T, MODEL_WRENCH12, false, false>(integ, a, st);
-        case MODEL_QUAT13:
-            return lag1 ? rollout_integ<T, MODEL_QUAT13, true, false>(integ, a, st)
-                        : rollout_integ<T, MODEL_QUAT13, false, false>(integ, a, st);
-        case MODEL_DI12_U8: return rollout_integ<T, MODEL_DI12_U8, false, false>(integ, a, st);
-        case MODEL_DI12_U6: return rollout_integ<T, MODEL_DI12_U6, false, false>(integ, a, st);
-        case MODEL_DIQ13_U6: return rollout_integ<T, MODEL_DIQ13_U6, false, false>(integ, a, st);
+    if (model < MODEL_THRUSTER8 || model > MODEL_DIQ13_U6) return cudaErrorInvalidValue;
+    return rollout_dispatch<T>(model, integ, lag1, a.pv != nullptr, a.gen.on != 0,
+                               [&](auto M, auto I, auto L1, auto PV, auto G) -> cudaError_t {
+        if constexpr (RolloutExists<decltype(M)::value, decltype(PV)::value>::V)
+            return rollout_launch<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value>(a, st);
+        else
+            return cudaErrorInvalidValue;
+    });
+}
+
+template <typename T> cudaError_t launch_lag_tail(const LagTailArgs<T>& a, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    if (a.gen.on) {
+        lag_tail_gen_kernel<T><<<(a.n + RHS_BLOCK - 1) / RHS_BLOCK, RHS_BLOCK, 0, st>>>(a);
+    } else {
+        const long long threads = (long long)a.n * 8;
+        lag_tail_kernel<T><<<(unsigned)((threads + TAIL_BLOCK - 1) / TAIL_BLOCK), TAIL_BLOCK, 0, st>>>(a);
     }
-    return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+template <typename T> cudaError_t launch_gen_inputs(int nu, const GenInputsArgs<T>& a, cudaStream_t st) {
+    if (a.n_sel <= 0 || a.steps <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((a.n_sel + RHS_BLOCK - 1) / RHS_BLOCK);
+    if (nu == 8) gen_inputs_kernel<T, 8><<<grid, RHS_BLOCK, 0, st>>>(a);
+    else gen_inputs_kernel<T, 6><<<grid, RHS_BLOCK, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 template <typename T, int MODEL, bool LAG1>
@@ -125,14 +141,14 @@ cudaError_t launch_rhs(int model, bool lag1, const RhsArgs<T>& a, cudaStream_t s
 }
 
 template <typename T> int se_blocks(long long nwin) {
-    return (int)((nwin + BlockOf<T>::N - 1) / BlockOf<T>::N);
+    return (int)((nwin + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK);
 }
 
 template <typename T, int MODEL>
 static cudaError_t se_go(int integ, const SeArgs<T>& a, cudaStream_t st) {
     const int nblocks = se_blocks<T>(a.nwin);
-    if (integ == INTEG_RK4) se_kernel<T, MODEL, INTEG_RK4><<<nblocks, BlockOf<T>::N, 0, st>>>(a);
-    else se_kernel<T, MODEL, INTEG_EULER><<<nblocks, BlockOf<T>::N, 0, st>>>(a);
+    if (integ == INTEG_RK4) se_kernel<T, MODEL, INTEG_RK4><<<nblocks, ROLLOUT_BLOCK, 0, st>>>(a);
+    else se_kernel<T, MODEL, INTEG_EULER><<<nblocks, ROLLOUT_BLOCK, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -182,9 +198,10 @@ cudaError_t launch_thruster_series(const ThrusterSeriesArgs<T>& a, cudaStream_t 
 }
 
 #define BROV_INSTANTIATE(T)                                                                                         \
-    template cudaError_t launch_rollout<T>(int, int, bool, bool, const RolloutArgs<T>&, cudaStream_t);             \
+    template cudaError_t launch_rollout<T>(int, int, bool, const RolloutArgs<T>&, cudaStream_t);                   \
     template int rollout_blocks_per_sm<T>(int, int, bool, bool, bool, bool);                                      \
-    template int rollout_block_threads<T>();                                                                       \
+    template cudaError_t launch_lag_tail<T>(const LagTailArgs<T>&, cudaStream_t);                                  \
+    template cudaError_t launch_gen_inputs<T>(int, const GenInputsArgs<T>&, cudaStream_t);                         \
     template cudaError_t launch_rhs<T>(int, bool, const RhsArgs<T>&, cudaStream_t);                                \
     template cudaError_t launch_se<T>(int, int, const SeArgs<T>&, double*, cudaStream_t);                          \
     template int se_blocks<T>(long long);                                                                          \

@@ -666,6 +666,18 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     if (d->carry_steps < 0 || (d->carry_steps > 0 && d->n_horizons != 1)) return brov::fail_msg(BROV_EINVAL, "a carried lag scores one horizon per call");
     if (d->window0 < 0 || d->row0 < 0 || d->row0 > d->window0) return brov::fail_msg(BROV_EINVAL, "window0 / row0 out of range");
     if (d->rows < 0 || d->n_windows < 0 || d->n_windows > d->rows) return brov::fail_msg(BROV_EINVAL, "rows / n_windows out of range");
+    // every window's first row must be local: window k starts at local row k + (window0 - row0)
+    if (d->n_windows + (d->window0 - d->row0) > d->rows)
+        return brov::fail_msg(BROV_EINVAL, "n_windows = %lld starting at local row %lld exceed the %lld rows of the series", d->n_windows, d->window0 - d->row0, d->rows);
+    if (d->carry_steps == 0 && d->window0 != d->row0) return brov::fail_msg(BROV_EINVAL, "rows before the first window are only meaningful with a carried lag");
+    if (d->carry_steps > 0) {
+        // the replay of window0's history reads input rows back to window (window0 * H - carry_steps) / H
+        const long long H = d->horizons[0];
+        const long long first_hist = d->window0 * H - d->carry_steps;
+        const long long need_row = first_hist > 0 ? first_hist / H : 0;
+        if (d->row0 > need_row)
+            return brov::fail_msg(BROV_EINVAL, "carried lag: the shard must start at row %lld or earlier (row0 = %lld)", need_row, d->row0);
+    }
     if (!d->se_out_dev || (d->n_windows > 0 && (!d->X_dev || !d->U_dev))) return brov::fail_msg(BROV_EINVAL, "NULL array");
     cudaStream_t st = (cudaStream_t)stream;
     BROV_CUDA_TRY(cudaSetDevice(h->device));

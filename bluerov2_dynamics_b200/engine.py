@@ -62,6 +62,36 @@ class RolloutResult:
     xT: torch.Tensor                 # [N, NX]
     lag: Optional[torch.Tensor]      # [N, NLAG] or None
     traj: Optional[torch.Tensor]     # [S, N, NX] or None
+    gen_state: Optional[torch.Tensor] = None     # [N, NU] AR(1) state of the generated command signal after the call
+    health: Optional[torch.Tensor] = None        # int64 [2]: vehicles with a non-finite final state / near theta = +-pi/2
+    min_abs_cos: Optional[torch.Tensor] = None   # [N] running minimum of |cos theta|
+
+
+@dataclass
+class InputGenerator:
+    """The reference's smooth random command signal (training/train_sim_brov2_koopmanEDMDc.py:161-164,180)
+        u_k = scale * s_k,   s_k = clip(rho s_{k-1} + sigma N(0,1), -clip, clip),   s_{-1} = 0
+    generated INSIDE the rollout kernels from the counter-based Philox4x32-10 stream keyed on (seed, vehicle0 + i,
+    step0 + k): no input array in HBM, the same numbers whatever the chunking / slicing / sharding."""
+    seed: int = 0
+    rho: float = 0.98
+    sigma: float = 0.02
+    clip: float = 1.0
+    scale: Optional[Sequence[float]] = None      # per input channel, default 1
+    vehicle0: int = 0                            # global index of the engine's vehicle 0 (rank offset of a shard)
+
+    def fill(self, g: "L.InputGen", nu: int, state_in=None, state_out=None) -> None:
+        g.enable = 1
+        g.seed = int(self.seed) & 0xFFFFFFFFFFFFFFFF
+        g.vehicle0 = int(self.vehicle0)
+        g.rho, g.sigma, g.clip = float(self.rho), float(self.sigma), float(self.clip)
+        sc = [1.0] * nu if self.scale is None else [float(v) for v in self.scale]
+        if len(sc) != nu:
+            raise ValueError(f"scale must have {nu} entries")
+        for j in range(8):
+            g.scale[j] = sc[j] if j < nu else 0.0
+        g.state_in_dev = state_in
+        g.state_out_dev = state_out
 
 
 class Engine:
@@ -86,6 +116,7 @@ class Engine:
         self._h = h
         self._pv = None
         self._ws = None
+        self._alloc = None if self.is_di else default_allocation()[0]   # last allocation pushed to the library
         self.phys = default_physical(rho)
         if current is not None:
             self.phys[L.PH_CURRENT:L.PH_CURRENT + 3] = np.asarray(current, float).reshape(3)
@@ -140,6 +171,7 @@ class Engine:
     def set_allocation(self, alloc: np.ndarray) -> None:
         a = np.ascontiguousarray(alloc, dtype=np.float64).reshape(6, 8)
         L.check(L.lib.brov_set_allocation(self._h, L.dptr(a)))
+        self._alloc = a.copy()
 
     def set_lag_discrete(self, dt: float, Ad: np.ndarray, Bd: np.ndarray) -> None:
         """Override the native ZOH for one dt (e.g. with scipy.signal.cont2discrete's result)."""
@@ -160,6 +192,14 @@ class Engine:
         if t.dim() != 2 or t.shape[1] != cols:
             raise ValueError(f"{what} must have shape [N, {cols}], got {tuple(t.shape)}")
 
+    def _check_lag_inout(self, lag, n: int, per_row: int) -> None:
+        """An in/out lag buffer is handed to the library as a raw pointer: it must already be what the kernel expects."""
+        if lag is None:
+            return
+        if (not isinstance(lag, torch.Tensor) or lag.device != self.device or lag.dtype != self.tdtype
+                or not lag.is_contiguous() or lag.numel() != n * per_row):
+            raise ValueError(f"lag must be a contiguous {self.tdtype} tensor on {self.device} with N*{per_row} elements")
+
     # ------------------------------------------------------------------ device API
     def rhs(self, x, u, lag: Optional[torch.Tensor] = None, dt: float = 0.02) -> torch.Tensor:
         """xdot for N vehicles (`rov.dynamics(x, u, dt)`).  For the thruster model `lag` [N,24] is advanced in place
@@ -171,9 +211,7 @@ class Engine:
         n = x.shape[0]
         if u.shape[0] != n:
             raise ValueError("x and u disagree on N")
-        if lag is not None:
-            if lag.dtype != self.tdtype or not lag.is_contiguous() or lag.numel() != n * self.nlag:
-                raise ValueError(f"lag must be a contiguous {self.tdtype} tensor with N*{self.nlag} elements")
+        self._check_lag_inout(lag, n, self.nlag)
         out = torch.empty((n, self.nx + (6 if self._lag1 else 0)), device=self.device, dtype=self.tdtype)
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_rhs(self._h, n, x.data_ptr(), u.data_ptr(), lag.data_ptr() if lag is not None else None,
@@ -185,6 +223,7 @@ class Engine:
         u = self.tensor(u)
         self._check_rows(u, 8, "u")
         n = u.shape[0]
+        self._check_lag_inout(lag, n, 24)
         out = torch.empty((n, 6), device=self.device, dtype=self.tdtype)
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_thruster_wrench(self._h, n, u.data_ptr(), lag.data_ptr() if lag is not None else None,
@@ -230,10 +269,14 @@ class Engine:
                                                 lag.ctypes.data if lag is not None else None, float(dt), out.ctypes.data))
         return out
 
-    def rollout(self, x0, U, dt: float = 0.02, integrator: str = "rk4", lag0=None, stride: int = 0,
+    def rollout(self, x0, U=None, dt: float = 0.02, integrator: str = "rk4", lag0=None, stride: int = 0,
                 u_layout: str = "auto", step0: int = 0, xT_out: Optional[torch.Tensor] = None,
                 lag_out: Optional[torch.Tensor] = None, traj_out: Optional[torch.Tensor] = None,
-                want_lag: bool = True, lag_repr: str = "thruster", time_slices: int = 0) -> RolloutResult:
+                want_lag: bool = True, lag_repr: str = "thruster", time_slices: int = 0,
+                gen: Optional[InputGenerator] = None, steps: Optional[int] = None, gen_state=None,
+                gen_state_out: Optional[torch.Tensor] = None, health: bool = False,
+                min_abs_cos: Optional[torch.Tensor] = None, min_abs_cos_accumulate: bool = False,
+                singular_eps: float = 0.0) -> RolloutResult:
         """Open-loop rollout of N vehicles (`simulate_physics` batched).
 
         x0 [N,NX]; U is one of
@@ -243,15 +286,27 @@ class Engine:
         With u_layout="auto" a 3-D U is "tnc" and a 2-D U is "shared".  For "const" pass U=(tensor [N,NU], steps).
         stride > 0 stores the state after every stride-th step into traj [T//stride, N, NX].
 
-        Thruster model: lag_repr="thruster" exchanges the per-thruster lag states [N,24] (the reference's hidden
-        state); lag_repr="projected" exchanges the allocation-projected states [N,18] (see include/brov.h) — same
-        dynamics, fewer operations, the natural carry between the chunks of a long rollout.  With want_lag=False no
-        lag state is returned and the kernels use the projected form internally.
+        gen=InputGenerator(...), steps=T: the inputs are generated inside the kernel (U is not used); gen_state
+        [N,NU] is the AR(1) state to continue from (None = zeros), the state after the call comes back as
+        result.gen_state (written into gen_state_out if given; may be the same tensor).
+
+        Thruster model: lag_repr="thruster" (default) exchanges the per-thruster lag states [N,24] — the reference's
+        hidden state `ThrusterLag._x`; lag_repr="projected" exchanges the allocation-projected states [N,18] (see
+        include/brov.h) — what the kernels integrate, the cheapest carry between the chunks of a long rollout.
+
+        health=True returns int64 [2] counts (non-finite final states, vehicles that came within singular_eps of
+        theta = +-pi/2); min_abs_cos [N] (in/out with min_abs_cos_accumulate) is the per-vehicle running minimum of
+        |cos theta|.
         """
         x0 = self.tensor(x0)
         self._check_rows(x0, self.nx, "x0")
         n = x0.shape[0]
-        if u_layout == "const":
+        Ut = None
+        if gen is not None:
+            if steps is None:
+                raise ValueError("generated inputs need steps=")
+            steps, st, sn = int(steps), 0, 0
+        elif u_layout == "const":
             Ut, steps = U
             Ut = self.tensor(Ut)
             self._check_rows(Ut, self.nu, "U")
@@ -281,6 +336,8 @@ class Engine:
             lag_in = self.tensor(lag0).reshape(n, nlag)
         if nlag and want_lag and lag_out is None:
             lag_out = torch.empty((n, nlag), device=self.device, dtype=self.tdtype)
+        if nlag and lag_out is not None:
+            self._check_lag_inout(lag_out, n, nlag)
         traj = traj_out
         if stride and traj is None:
             nsnap = (step0 + steps) // stride - step0 // stride
@@ -289,7 +346,8 @@ class Engine:
         d.struct_size = C.sizeof(L.RolloutDesc)
         d.integrator = integ
         d.n, d.steps, d.dt = n, steps, float(dt)
-        d.x0_dev, d.xT_dev, d.u_dev = x0.data_ptr(), xT.data_ptr(), Ut.data_ptr()
+        d.x0_dev, d.xT_dev = x0.data_ptr(), xT.data_ptr()
+        d.u_dev = Ut.data_ptr() if Ut is not None else None
         d.u_stride_t, d.u_stride_n = st, sn
         d.lag_in_dev = lag_in.data_ptr() if lag_in is not None else None
         d.lag_out_dev = lag_out.data_ptr() if (nlag and lag_out is not None) else None
@@ -299,15 +357,52 @@ class Engine:
         d.snap_base = int(step0) // max(int(stride), 1)
         d.lag_in_repr = d.lag_out_repr = L.LAG_PROJECTED if proj else L.LAG_THRUSTER
         d.time_slices = int(time_slices)  # 0 = automatic temporal tiling (bit-identical results for every value)
+        gs_in = gs_out = None
+        if gen is not None:
+            if gen_state is not None:
+                gs_in = self.tensor(gen_state).reshape(n, self.nu)
+            gs_out = gen_state_out if gen_state_out is not None else torch.empty((n, self.nu), device=self.device, dtype=self.tdtype)
+            self._check_lag_inout(gs_out, n, self.nu)
+            gen.fill(d.gen, self.nu, gs_in.data_ptr() if gs_in is not None else None, gs_out.data_ptr())
+        hc = None
+        if health:
+            hc = torch.zeros(2, device=self.device, dtype=torch.int64)
+            d.health_dev = hc.data_ptr()
+        if min_abs_cos is not None:
+            self._check_lag_inout(min_abs_cos, n, 1)
+            d.min_abs_cos_dev = min_abs_cos.data_ptr()
+            d.min_abs_cos_accumulate = int(bool(min_abs_cos_accumulate))
+        d.singular_eps = float(singular_eps)
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_rollout(self._h, C.byref(d), self._stream()))
-        return RolloutResult(xT=xT, lag=lag_out if (nlag and want_lag) else None, traj=traj if stride else None)
+        return RolloutResult(xT=xT, lag=lag_out if (nlag and want_lag) else None, traj=traj if stride else None,
+                             gen_state=gs_out, health=hc, min_abs_cos=min_abs_cos)
+
+    def generate_inputs(self, gen: InputGenerator, steps: int, step0: int = 0, first: int = 0, vstride: int = 1,
+                        n_sel: int = 1, state_in=None):
+        """The command signal the kernels generate, as an array: (U [steps, n_sel, NU], state_out [n_sel, NU]) for the
+        vehicles first, first + vstride, ... and steps step0 .. step0 + steps - 1 (brov_generate_inputs).  Feeding U to
+        `rollout` reproduces the generated-input rollout of those vehicles bit for bit; a CPU reference consumes the
+        same numbers."""
+        out = torch.empty((int(steps), int(n_sel), self.nu), device=self.device, dtype=self.tdtype)
+        so = torch.empty((int(n_sel), self.nu), device=self.device, dtype=self.tdtype)
+        si = self.tensor(state_in).reshape(n_sel, self.nu) if state_in is not None else None
+        d = L.GenInputsDesc()
+        d.struct_size = C.sizeof(L.GenInputsDesc)
+        d.dtype, d.nu, d.device = self._code, self.nu, self.device_index
+        d.first, d.vstride, d.n_sel = int(first), int(vstride), int(n_sel)
+        d.step0, d.steps = int(step0), int(steps)
+        gen.fill(d.gen, self.nu, si.data_ptr() if si is not None else None, so.data_ptr())
+        d.out_dev = out.data_ptr()
+        with torch.cuda.device(self.device):
+            L.check(L.lib.brov_generate_inputs(C.byref(d), self._stream()))
+        return out, so
 
     def project_lag(self, lag24) -> torch.Tensor:
         """Per-thruster lag states [N,8,3] -> allocation-projected states [N,18] (Z[c][k] = sum_i alloc[c][i] lag[i][k])."""
-        kp = np.zeros((6, 8))
-        L.check(L.lib.brov_default_allocation(L.dptr(kp), None, None))
-        A = self.tensor(kp)
+        if self._alloc is None:
+            raise ValueError("project_lag applies to the thruster model")
+        A = self.tensor(self._alloc)     # the allocation the kernels use (set_allocation keeps it current)
         return torch.einsum("ci,nik->nck", A, self.tensor(lag24).reshape(-1, 8, 3)).reshape(-1, 18).contiguous()
 
     def step(self, x, u, lag=None, dt: float = 0.02, integrator: str = "rk4") -> RolloutResult:
@@ -322,6 +417,7 @@ class Engine:
         lag_t = None
         if self.nlag and lag is not None:
             lag_t = self.tensor(lag).reshape(n, self.nlag)
+            self._check_lag_inout(lag_t, n, self.nlag)
         out = torch.empty_like(x)
         with torch.cuda.device(self.device):
             L.check(L.lib.brov_step(self._h, INTEGRATORS[integrator], n, x.data_ptr(), u.data_ptr(), float(dt),
@@ -336,12 +432,16 @@ class Engine:
 
     def multistep_se(self, X, U, horizons: Sequence[int], dt: float = 0.02, integrator: str = "rk4",
                      lag0=None, n_windows: Optional[int] = None, lag_mode: str = "reset", window0: int = 0,
-                     row0: int = 0):
+                     row0: int = 0, se_out: Optional[torch.Tensor] = None, health_out: Optional[torch.Tensor] = None,
+                     singular_eps: float = 0.0):
         """Sum of squared endpoint errors per horizon over sliding windows of one recorded series.
         Returns (se [MAX_H] float64 device tensor, counts list).  See brov_multistep_se in include/brov.h.
         lag_mode="carry" (thruster model, one horizon): the reference's literal semantics — the lag state left by
         windows 0..k-1 is what window k starts from.  window0 / row0: global indices of the first local window / row
-        when X, U are a shard of a longer series."""
+        when X, U are a shard of a longer series.
+        se_out: float64 [MAX_H] device tensor to write into (e.g. a slice of a reduction buffer); health_out: int64 [2]
+        device tensor receiving the number of windows with a non-finite endpoint error / that came within
+        singular_eps of theta = +-pi/2."""
         X = self.tensor(X)
         U = self.tensor(U)
         self._check_rows(X, self.nx, "X")
@@ -360,7 +460,12 @@ class Engine:
         nbytes = L.lib.brov_se_workspace_bytes(nwin)
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        se = torch.zeros(L.MAX_H, dtype=torch.float64, device=self.device)
+        if se_out is None:
+            se = torch.zeros(L.MAX_H, dtype=torch.float64, device=self.device)
+        else:
+            se = se_out
+            if se.dtype != torch.float64 or se.device != self.device or not se.is_contiguous() or se.numel() < L.MAX_H:
+                raise ValueError(f"se_out must be a contiguous float64 tensor with {L.MAX_H} elements on {self.device}")
         counts = (C.c_longlong * L.MAX_H)()
         d = L.SeDesc()
         d.struct_size = C.sizeof(L.SeDesc)
@@ -380,6 +485,11 @@ class Engine:
         d.workspace_bytes = nbytes
         d.lag_carry = int(carry)
         d.window0, d.row0 = (int(window0), int(row0)) if carry else (0, 0)
+        if health_out is not None:
+            if health_out.dtype != torch.int64 or health_out.device != self.device or health_out.numel() < 2:
+                raise ValueError("health_out must be an int64 tensor with 2 elements on the engine's device")
+            d.health_dev = health_out.data_ptr()
+            d.singular_eps = float(singular_eps)
         if not carry and off:
             raise ValueError("window0 != row0 needs lag_mode='carry'")
         with torch.cuda.device(self.device):
@@ -407,26 +517,36 @@ class Engine:
         return out[hs[0]] if single else [out[h] for h in hs]
 
     # ------------------------------------------------------------------ host-buffer API (end-to-end path)
-    def rollout_host(self, x0: np.ndarray, U: np.ndarray, dt: float = 0.02, integrator: str = "rk4",
+    def rollout_host(self, x0: np.ndarray, U: Optional[np.ndarray] = None, dt: float = 0.02, integrator: str = "rk4",
                      lag0: Optional[np.ndarray] = None, stride: int = 0, chunk_steps: int = 0,
                      out_xT: Optional[np.ndarray] = None, out_traj: Optional[np.ndarray] = None,
-                     out_lag: Optional[np.ndarray] = None, lag_repr: str = "thruster", want_lag: bool = True):
+                     out_lag: Optional[np.ndarray] = None, lag_repr: str = "thruster", want_lag: bool = True,
+                     gen: Optional[InputGenerator] = None, steps: Optional[int] = None,
+                     gen_state: Optional[np.ndarray] = None, out_gen_state: Optional[np.ndarray] = None,
+                     health: Optional[np.ndarray] = None):
         """Rollout with every array in HOST memory (numpy, engine dtype, C-contiguous; pinned memory overlaps the
         copies).  Inputs stream to the device in time chunks, double buffered against the kernels.
-        U [T,N,NU] or [T,NU] (shared).  Returns (xT, lag or None, traj or None) as numpy arrays."""
+        U [T,N,NU] or [T,NU] (shared) — or gen=InputGenerator(...), steps=T: the inputs are generated on the device
+        and only x0 / lag / the AR(1) state cross PCIe.  health: uint64 [2] array receiving the counts of vehicles with
+        a non-finite final state / that came near theta = +-pi/2.  Returns (xT, lag or None, traj or None)."""
         def host(a, what):
             if not isinstance(a, np.ndarray) or a.dtype != self.ndtype or not a.flags.c_contiguous:
                 raise ValueError(f"{what} must be a C-contiguous numpy array of dtype {np.dtype(self.ndtype)}")
             return a
         x0 = host(x0, "x0")
-        U = host(U, "U")
         n = x0.shape[0]
         if x0.shape != (n, self.nx):
             raise ValueError(f"x0 must be [N, {self.nx}]")
-        shared = U.ndim == 2
-        if (shared and U.shape[1] != self.nu) or (not shared and U.shape[1:] != (n, self.nu)):
-            raise ValueError("U must be [T, N, NU] or [T, NU]")
-        steps = U.shape[0]
+        if gen is not None:
+            if steps is None:
+                raise ValueError("generated inputs need steps=")
+            steps, shared = int(steps), False
+        else:
+            U = host(U, "U")
+            shared = U.ndim == 2
+            if (shared and U.shape[1] != self.nu) or (not shared and U.shape[1:] != (n, self.nu)):
+                raise ValueError("U must be [T, N, NU] or [T, NU]")
+            steps = U.shape[0]
         xT = out_xT if out_xT is not None else np.empty_like(x0)
         proj = lag_repr == "projected" and self.model == "thruster8"
         nlag = 18 if proj else self.nlag
@@ -440,7 +560,8 @@ class Engine:
         d.struct_size = C.sizeof(L.RolloutHostDesc)
         d.integrator = INTEGRATORS[integrator]
         d.n, d.steps, d.dt = n, steps, float(dt)
-        d.x0_host, d.xT_host, d.u_host = x0.ctypes.data, host(xT, "out_xT").ctypes.data, U.ctypes.data
+        d.x0_host, d.xT_host = x0.ctypes.data, host(xT, "out_xT").ctypes.data
+        d.u_host = U.ctypes.data if gen is None else None
         d.u_shared = int(shared)
         d.lag_in_host = host(lag0, "lag0").ctypes.data if (nlag and lag0 is not None) else None
         d.lag_out_host = lag_out.ctypes.data if lag_out is not None else None
@@ -448,6 +569,13 @@ class Engine:
         d.stride = max(int(stride), 1)
         d.chunk_steps = int(chunk_steps)
         d.lag_in_repr = d.lag_out_repr = L.LAG_PROJECTED if proj else L.LAG_THRUSTER
+        if gen is not None:
+            gen.fill(d.gen, self.nu, host(gen_state, "gen_state").ctypes.data if gen_state is not None else None,
+                     host(out_gen_state, "out_gen_state").ctypes.data if out_gen_state is not None else None)
+        if health is not None:
+            if health.dtype != np.uint64 or health.size < 2 or not health.flags.c_contiguous:
+                raise ValueError("health must be a C-contiguous uint64 array with 2 elements")
+            d.health_host = health.ctypes.data_as(C.POINTER(C.c_ulonglong))
         L.check(L.lib.brov_rollout_host(self._h, C.byref(d)))
         return xT, lag_out, traj
 

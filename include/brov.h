@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BROV_ABI_VERSION 6
+#define BROV_ABI_VERSION 7
 
 enum { BROV_THRUSTER8_LAG3 = 0, BROV_WRENCH_EULER12 = 1, BROV_WRENCH_QUAT13 = 2,
        /* double-integrator comparison model of the reference's evaluation tables (kinematics + a learned linear map
@@ -149,14 +149,43 @@ int brov_thruster_wrench_host(brov_engine_t* e, long long n, const void* u_host,
  * With an RK4 step the thruster lag advances four times per step (once per stage) as in the reference.
  * Lag representation.  The eight thruster lags are copies of one linear filter, so the six allocation-projected
  * combinations Z_c = sum_i alloc[c][i] lag_i obey the same recurrence driven by (alloc F)_c and yield the identical
- * wrench with 18 instead of 24 hidden values and ~150 fewer operations per RK4 step.  The kernels run on Z whenever
- * the caller does not ask for per-thruster states back: lag_out_dev == NULL, or lag_out_repr == BROV_LAG_PROJECTED
- * (then lag_out is [n][6][3], a valid lag_in with lag_in_repr = BROV_LAG_PROJECTED for the next chunk).  Per-thruster
- * states cannot be recovered from Z: lag_in_repr = PROJECTED with lag_out_repr = THRUSTER and a lag_out buffer is an
- * error.  Results differ between the two representations only by rounding (1e-16 relative).
+ * wrench with 18 instead of 24 hidden values and ~150 fewer operations per RK4 step.  Every rollout integrates in that
+ * form.  lag_out_repr = BROV_LAG_PROJECTED returns Z ([n][6][3], a valid lag_in with lag_in_repr = BROV_LAG_PROJECTED
+ * for the next chunk, and the cheapest carry).  lag_out_repr = BROV_LAG_THRUSTER (the default, the reference's hidden
+ * state ThrusterLag._x, fossen/BlueROV2.py:503-510) is produced by a short second kernel: each thruster's lag is a
+ * stable linear filter of that thruster's input alone, so its state after the call is fixed — to below one ulp — by
+ * the last brov_se_carry_steps(e, dt, integrator) inputs of the call (or by lag_in and all inputs of a shorter call);
+ * one thread per (vehicle, thruster) replays them.  A projected lag_in with a per-thruster lag_out is therefore only
+ * accepted when the call is at least that many steps long.
  * traj (optional): state after global step g = step0+k+1 is stored when g % stride == 0, as snapshot
  * s = g/stride - 1 at traj[(s - snap_base)][n][NX].  Chunked rollouts pass xT/lag_out of one call as x0/lag_in of
- * the next and advance step0. */
+ * the next and advance step0.
+ *
+ * Generated inputs (gen.enable != 0): the input of every step is produced inside the kernel instead of being read
+ * from u_dev — the reference's smooth random command signal (training/train_sim_brov2_koopmanEDMDc.py:161-164,180)
+ *     s_k = clip(rho s_{k-1} + sigma N(0,1), -clip, clip),   u_k[j] = scale[j] s_k[j],   s_{-1} = state_in (or 0)
+ * with N(0,1) from the counter-based generator Philox4x32-10 keyed on `seed` at counter (vehicle0 + i, step0 + k):
+ * chunked, sliced and sharded rollouts see the same stream, nothing is read from HBM per step.  The AR(1) state
+ * ([n][NU], in units of u) is the only thing carried (state_in_dev / state_out_dev).  brov_generate_inputs
+ * materialises the same signal for a subset of vehicles so that a CPU reference can consume identical inputs.
+ *
+ * Health accounting (optional): health_dev (unsigned long long[2], dev) receives the number of vehicles whose final
+ * state holds a non-finite value and the number whose |cos theta| came below singular_eps at the start of some step
+ * — the singularity of the Euler-angle kinematics, where the reference clamps cos theta (fossen/BlueROV2.py:52-56) and
+ * amplifies rounding differences without bound.  min_abs_cos_dev ([n], engine scalar type) holds the running minimum
+ * of |cos theta| per vehicle: with min_abs_cos_accumulate != 0 the incoming values are kept (chunked rollouts),
+ * otherwise the call starts from 1.  Quaternion and double-integrator models report 1 / zero counts. */
+typedef struct brov_input_gen {
+    int32_t enable;
+    int32_t reserved;
+    uint64_t seed;
+    long long vehicle0;         /* global index of local vehicle 0: key of the random stream (sharded ensembles) */
+    double rho, sigma, clip;    /* reference: 0.98, 0.02, 1.0 */
+    double scale[8];            /* per input channel; the reference drives all thrusters with scale 1 */
+    const void* state_in_dev;   /* [n][NU] engine scalar type, or NULL = zeros */
+    void* state_out_dev;        /* [n][NU] or NULL (may alias state_in_dev) */
+} brov_input_gen;
+
 typedef struct brov_rollout_desc {
     uint32_t struct_size;       /* = sizeof(brov_rollout_desc) */
     int32_t integrator;
@@ -165,10 +194,10 @@ typedef struct brov_rollout_desc {
     double dt;
     const void* x0_dev;         /* [n][NX] */
     void* xT_dev;               /* [n][NX], may alias x0_dev */
-    const void* u_dev;
+    const void* u_dev;          /* ignored with generated inputs */
     long long u_stride_t, u_stride_n;
     const void* lag_in_dev;     /* [n][NLAG] or NULL = zeros */
-    void* lag_out_dev;          /* [n][NLAG] or NULL */
+    void* lag_out_dev;          /* [n][NLAG] or NULL (may alias lag_in_dev when the representations agree) */
     void* traj_dev;             /* or NULL */
     long long stride;           /* >= 1 when traj_dev != NULL */
     long long step0;
@@ -179,11 +208,31 @@ typedef struct brov_rollout_desc {
      * the steps of this call into Q slices per block of vehicles.  Vehicles are independent, but B vehicle blocks on S
      * resident slots cost ceil(B/S) rounds of the full step count; slicing makes it ceil(B*Q/S) rounds of steps/Q
      * (cfg2: 512 blocks on 296 slots, Q = 4 -> 7 rounds of 25 steps instead of 2 rounds of 100).  Slices of one
-     * vehicle block hand their state over through xT / lag_out, so lag_out must be given for models with lag state. */
+     * vehicle block hand their state over through xT and engine-owned scratch. */
     int32_t time_slices;
-    int32_t reserved0;
+    int32_t min_abs_cos_accumulate;
+    void* health_dev;           /* unsigned long long[2] or NULL */
+    void* min_abs_cos_dev;      /* [n] or NULL */
+    double singular_eps;        /* 0 = 1e-3 */
+    brov_input_gen gen;
 } brov_rollout_desc;
 int brov_rollout(brov_engine_t* e, const brov_rollout_desc* d, void* stream);
+
+/* The generated command signal as an array: out [steps][n_sel][nu] holds the inputs of steps step0 .. step0+steps-1
+ * for the selected vehicles first, first + vstride, ..., first + (n_sel-1) vstride (local indices; the stream key is
+ * gen.vehicle0 + index).  gen.state_in_dev / state_out_dev are [n_sel][nu] arrays indexed by selected vehicle.  Same
+ * device code as the rollout kernels: a rollout fed with `out` reproduces the generated-input rollout bit for bit. */
+typedef struct brov_gen_inputs_desc {
+    uint32_t struct_size;
+    int32_t dtype;              /* BROV_F64 / BROV_F32 */
+    int32_t nu;                 /* 8 or 6 */
+    int32_t device;
+    long long first, vstride, n_sel;
+    long long step0, steps;
+    brov_input_gen gen;
+    void* out_dev;
+} brov_gen_inputs_desc;
+int brov_generate_inputs(const brov_gen_inputs_desc* d, void* stream);
 /* One integrator step with one input row per vehicle (u [n][NU]) — the body of the reference's simulate_physics loop
  * as a call; lag_inout [n][NLAG] or NULL (zero lag, nothing written).  x_out may alias x. */
 int brov_step(brov_engine_t* e, int integrator, long long n, const void* x_dev, const void* u_dev, double dt,
@@ -227,6 +276,10 @@ typedef struct brov_se_desc {
     int32_t reserved;
     long long window0;
     long long row0;
+    /* optional health accounting as in brov_rollout_desc: windows whose endpoint error is not finite / that came within
+     * singular_eps of the Euler-angle singularity (unsigned long long[2], dev; zeroed by the call) */
+    void* health_dev;
+    double singular_eps;        /* 0 = 1e-3 */
 } brov_se_desc;
 /* Number of integrator steps of history a carried-lag window replays for this dt / integrator (also the number of
  * rows a shard must hold before its first window, plus one). */
@@ -333,7 +386,9 @@ int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d, void* str
 /* Host-buffer rollout: the same operation as brov_rollout with every array in HOST memory (pinned memory gives
  * asynchronous copies).  The engine streams the inputs to the device in time chunks on a copy stream, double
  * buffered against the rollout kernels, and copies snapshots and final state back; it returns after everything has
- * landed in the host arrays.  u_host is time-major [steps][n][NU] (u_shared = 0) or [steps][NU] (u_shared = 1). */
+ * landed in the host arrays.  u_host is time-major [steps][n][NU] (u_shared = 0) or [steps][NU] (u_shared = 1).
+ * Chunks carry the allocation-projected lag on the device; per-thruster states (lag_out_repr = BROV_LAG_THRUSTER) are
+ * rebuilt from the chunks that cover the last brov_se_carry_steps steps. */
 typedef struct brov_rollout_host_desc {
     uint32_t struct_size;
     int32_t integrator;
@@ -352,6 +407,11 @@ typedef struct brov_rollout_host_desc {
     long long chunk_steps;      /* 0 = choose (about 256 MiB of inputs per chunk) */
     int32_t lag_in_repr;        /* BROV_LAG_*: layout of lag_in_host / lag_out_host (thruster model only) */
     int32_t lag_out_repr;
+    /* generated inputs (gen.enable): u_host is ignored, nothing but x0 / lag / the AR(1) state crosses PCIe;
+     * gen.state_in_dev / state_out_dev are HOST pointers here ([n][NU] or NULL) */
+    brov_input_gen gen;
+    unsigned long long* health_host;   /* [2] or NULL: non-finite / near-singular vehicle counts of the whole call */
+    double singular_eps;               /* 0 = 1e-3 */
 } brov_rollout_host_desc;
 int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc* d);
 

@@ -174,10 +174,13 @@ static void make_model(model_t* M, int model, const double* phys, const double* 
 
 /* Rollout of n vehicles.  phys: [37] shared or [n][37] per vehicle (per_vehicle != 0).  U: time-major [T][n][nu]
  * (u_shared = 0) or [T][nu].  lag: [n][24] in/out (thruster model; may be NULL = zero, discarded).
- * traj: [T/stride][n][nx] or NULL.  Ad, Bd, r, e: lag discretisation and thruster geometry (thruster model). */
+ * traj: [T/stride][n][nx] or NULL.  Ad, Bd, r, e: lag discretisation and thruster geometry (thruster model).
+ * min_abs_cos: [n] in/out or NULL — running minimum of |cos theta| over the states the steps START from (Euler-angle
+ * models): the distance to the singularity of euler_kinematics_matrix (fossen/BlueROV2.py:43-62). */
 int brov_oracle_rollout(int model, int euler, long long n, long long T, double dt, const double* phys, int per_vehicle,
                         const double* Ad, const double* Bd, const double* r, const double* e, double* x,
-                        const double* U, int u_shared, double* lag, double* traj, long long stride) {
+                        const double* U, int u_shared, double* lag, double* traj, long long stride,
+                        double* min_abs_cos) {
     const int nx = model == 2 ? 13 : 12, nu = model == 0 ? 8 : 6;
 #pragma omp parallel for schedule(static)
     for (long long i = 0; i < n; ++i) {
@@ -186,14 +189,17 @@ int brov_oracle_rollout(int model, int euler, long long n, long long T, double d
         double xs[13], ls[24];
         memcpy(xs, x + i * nx, sizeof(double) * nx);
         if (lag) memcpy(ls, lag + 24 * i, sizeof(ls)); else memset(ls, 0, sizeof(ls));
+        double mc = min_abs_cos ? min_abs_cos[i] : 1.0;
         for (long long k = 0; k < T; ++k) {
             const double* u = u_shared ? U + k * nu : U + (k * n + i) * nu;
+            if (min_abs_cos && model != 2) { const double c = fabs(cos(xs[4])); if (c < mc) mc = c; }
             step(&M, euler, dt, xs, u, ls);
             if (traj && stride > 0 && (k + 1) % stride == 0)
                 memcpy(traj + (((k + 1) / stride - 1) * n + i) * nx, xs, sizeof(double) * nx);
         }
         memcpy(x + i * nx, xs, sizeof(double) * nx);
         if (lag) memcpy(lag + 24 * i, ls, sizeof(ls));
+        if (min_abs_cos) min_abs_cos[i] = mc;
     }
     return 0;
 }

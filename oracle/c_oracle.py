@@ -51,7 +51,7 @@ def lib(fma: bool = False):
 def _bind(L):
     if True:
         dp, ll, i, d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
-        L.brov_oracle_rollout.argtypes = [i, i, ll, ll, d, dp, i, dp, dp, dp, dp, dp, dp, i, dp, dp, ll]
+        L.brov_oracle_rollout.argtypes = [i, i, ll, ll, d, dp, i, dp, dp, dp, dp, dp, dp, i, dp, dp, ll, dp]
         L.brov_oracle_rollout.restype = i
         L.brov_oracle_multistep_se.argtypes = [i, i, ll, ll, d, dp, dp, dp, dp, dp, dp, dp]
         L.brov_oracle_multistep_se.restype = d
@@ -99,9 +99,11 @@ def _model_consts(kind, dt):
 
 
 def rollout(kind: str, integ: str, dt: float, x0, U, params: dict | None = None, lag0=None, stride: int = 0,
-            fma: bool = False):
+            fma: bool = False, min_abs_cos=None):
     """Same contract as fossen_np.rollout: x0 [N,nx]; U [T,N,nu] or [T,nu]; returns (snaps [S,N,nx], xT, lagT).
-    fma=True runs the FMA-contracted build of the same code (a second valid rounding, for conditioning studies)."""
+    fma=True runs the FMA-contracted build of the same code (a second valid rounding, for conditioning studies).
+    min_abs_cos: float64 [N] array updated in place with the running minimum of |cos theta| over the states the steps
+    start from (initialise it to 1)."""
     L = lib(fma)
     x = np.array(x0, float, ndmin=2, order="C")
     N, nx = x.shape
@@ -117,9 +119,11 @@ def rollout(kind: str, integ: str, dt: float, x0, U, params: dict | None = None,
         lag = np.zeros((N, 24)) if lag0 is None else np.array(lag0, float).reshape(N, 24).copy()
     S = T // stride if stride else 0
     traj = np.zeros((S, N, nx)) if S else None
+    if min_abs_cos is not None:
+        assert min_abs_cos.dtype == np.float64 and min_abs_cos.shape == (N,) and min_abs_cos.flags.c_contiguous
     rc = L.brov_oracle_rollout(MODEL_ID[kind], int(integ == "euler"), N, T, float(dt), _ptr(phys), int(per), _ptr(Ad),
                                _ptr(Bd), _ptr(r), _ptr(e), _ptr(x), _ptr(U), shared, _ptr(lag), _ptr(traj),
-                               int(stride))
+                               int(stride), _ptr(min_abs_cos))
     assert rc == 0
     return (traj if S else np.zeros((0, N, nx))), x, (lag.reshape(N, 8, 3) if lag is not None else None)
 

@@ -1,5 +1,7 @@
-"""Randomised parity sweep: random model / integrator / ensemble size / horizon / snapshot stride / input layout /
-chunking / time slicing / initial lag, GPU engine against the plain-C oracle.  Usage: fuzz_parity.py [cases] [seed]"""
+"""Randomised parity sweep: random model / integrator / ensemble size / horizon / snapshot stride / input layout
+(per-vehicle series through the TMA ring, shared series, constant rows, inputs generated in the kernel) / chunking /
+time slicing / initial lag / lag representation (per-thruster states rebuilt by the epilogue, or the projected carry),
+GPU engine against the plain-C oracle.  Usage: fuzz_parity.py [cases] [seed]"""
 import os
 import sys
 
@@ -30,7 +32,7 @@ for case in range(cases):
     n = int(rng.choice([1, 2, 31, 32, 33, 127, 128, 129, int(rng.integers(1, 3000))]))
     T = int(rng.integers(1, 80))
     stride = int(rng.choice([0, 1, 2, 3, 7, T]))
-    layout = rng.choice(["tnc", "shared", "const"])
+    layout = rng.choice(["tnc", "shared", "const", "gen"])
     nx, nu = (13 if model == "quat13" else 12), (8 if model == "thruster8" else 6)
     x0 = rng.uniform(-0.5, 0.5, (n, nx))
     x0[:, -3:] *= 0.3                                  # body rates up to 0.15 rad/s
@@ -42,7 +44,13 @@ for case in range(cases):
     # forces up to 8 N, moments up to 0.3 N m: a persistent larger torque tumbles the vehicle through the Euler-angle
     # singularity, where the reference itself amplifies a rounding-level perturbation by many orders of magnitude
     amp = np.full(8, 0.5) if nu == 8 else np.array([8.0, 8.0, 8.0, 0.3, 0.3, 0.3])
-    if layout == "tnc":
+    gen = None
+    if layout == "gen":     # the command signal generated inside the kernel; the oracle consumes its materialised form
+        gen = B.InputGenerator(seed=int(rng.integers(1 << 62)), sigma=float(rng.choice([0.02, 0.1])), scale=list(amp),
+                               vehicle0=int(rng.integers(1 << 40)))
+        e_ = engines.get((model, dtype)) or engines.setdefault((model, dtype), B.Engine(model, dtype))
+        U = e_.generate_inputs(gen, steps=T, n_sel=n)[0].cpu().numpy().astype(np.float64)
+    elif layout == "tnc":
         U = rng.uniform(-1, 1, (T, n, nu)) * amp
     elif layout == "shared":
         U = rng.uniform(-1, 1, (T, nu)) * amp
@@ -68,24 +76,32 @@ for case in range(cases):
     e = engines.get(key) or engines.setdefault(key, B.Engine(model, dtype))
     Ug = (Ur, T) if layout == "const" else Ur
     slices = int(rng.choice([0, 1, 2, 3]))
+    repr_ = str(rng.choice(["thruster", "projected"])) if model == "thruster8" else "thruster"
+    lag_in = None if lag0r is None else lag0r.reshape(n, 24)
+    if repr_ == "projected" and lag_in is not None:
+        lag_in = e.project_lag(lag_in)
+    kw = dict(dt=DT, integrator=integ, stride=stride, time_slices=slices, lag_repr=repr_)
     if rng.random() < 0.5 and T >= 2 and layout != "const":
         cut = int(rng.integers(1, T))            # two chunked calls carrying state, lag and the global step index
-        r1 = e.rollout(x0r, Ur[:cut], dt=DT, integrator=integ, lag0=None if lag0r is None else lag0r.reshape(n, 24),
-                       stride=stride, u_layout=layout, time_slices=slices)
-        r2 = e.rollout(r1.xT, Ur[cut:], dt=DT, integrator=integ, lag0=r1.lag, stride=stride, u_layout=layout, step0=cut,
-                       time_slices=slices)
+        if gen is not None:
+            r1 = e.rollout(x0r, gen=gen, steps=cut, lag0=lag_in, **kw)
+            r2 = e.rollout(r1.xT, gen=gen, steps=T - cut, lag0=r1.lag, step0=cut, gen_state=r1.gen_state, **kw)
+        else:
+            r1 = e.rollout(x0r, Ur[:cut], lag0=lag_in, u_layout=layout, **kw)
+            r2 = e.rollout(r1.xT, Ur[cut:], lag0=r1.lag, u_layout=layout, step0=cut, **kw)
         gx, gl = r2.xT, r2.lag
         gt = torch.cat([t for t in (r1.traj, r2.traj) if t is not None]) if stride else None
     else:
-        r = e.rollout(x0r, Ug, dt=DT, integrator=integ, lag0=None if lag0r is None else lag0r.reshape(n, 24),
-                      stride=stride, u_layout=layout, time_slices=slices)
+        r = (e.rollout(x0r, gen=gen, steps=T, lag0=lag_in, **kw) if gen is not None
+             else e.rollout(x0r, Ug, lag0=lag_in, u_layout=layout, **kw))
         gx, gl, gt = r.xT, r.lag, r.traj
     err = normwise(gx.cpu().numpy().astype(np.float64)[good], xT[good])
     if stride:
         assert gt.shape[0] == snaps.shape[0], (case, gt.shape, snaps.shape)
         err = max(err, normwise(gt.cpu().numpy().astype(np.float64)[:, good], snaps[:, good]))
     if model == "thruster8":
-        err = max(err, normwise(gl.cpu().numpy().astype(np.float64).reshape(n, 8, 3), lagT))
+        lag_want = lagT if repr_ == "thruster" else np.einsum("ci,nik->nck", B.default_allocation()[0], lagT)
+        err = max(err, normwise(gl.cpu().numpy().astype(np.float64).reshape(lag_want.shape), lag_want))
     tol = 1e-10 if dtype == "f64" else 1e-4
     if err >= tol:   # breakdown for the report
         ex = np.max(np.abs(gx.cpu().numpy().astype(np.float64) - xT), axis=1)
@@ -96,14 +112,14 @@ for case in range(cases):
             et = np.max(np.abs(gt.cpu().numpy().astype(np.float64) - snaps), axis=(0, 2))
             print("  traj err of that vehicle", et[iv], " worst traj vehicle", int(np.argmax(np.where(good, et, 0))), et[good].max())
         if model == "thruster8":
-            print("  lag err", normwise(gl.cpu().numpy().astype(np.float64).reshape(n, 8, 3), lagT))
+            print("  lag err", normwise(gl.cpu().numpy().astype(np.float64).reshape(lag_want.shape), lag_want), repr_)
     worst[dtype] = max(worst[dtype], err)
     status = "ok" if err < tol else "FAIL"
     skipped += int((~good).sum())
     total += n
     if status == "FAIL" or case % 25 == 0:
         print(f"case {case:4d} {model:9s} {integ:5s} {dtype} n={n:5d} T={T:3d} stride={stride:2d} {layout:6s} slices={slices} "
-              f"lag0={'y' if lag0 is not None else 'n'} err={err:.2e} {status}", flush=True)
+              f"lag0={'y' if lag0 is not None else 'n'} {repr_[:4]} err={err:.2e} {status}", flush=True)
     assert err < tol, "parity failure"
 print(f"fuzz_parity: {cases} cases OK ({total} vehicles, {skipped} ill-conditioned ones excluded); "
       f"worst normwise error fp64 {worst['f64']:.2e}, fp32 {worst['f32']:.2e}")

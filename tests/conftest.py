@@ -19,6 +19,12 @@ def golden():
     return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")))
 
 
+@pytest.fixture(scope="session")
+def golden_r2():
+    """Round-2 outputs of the unmodified reference (tests/golden/make_golden_r2.py): cos(theta) clamp, lag tails."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_r2.npz")))
+
+
 def normwise(a, b):
     """Parity metric of SURVEY 7 / BASELINE.md 3: ||a-b||_inf / max(||b||_inf, 1)."""
     a = np.asarray(a, float)

@@ -33,9 +33,12 @@ def test_every_declared_symbol_is_exported(L):
     assert declared == set(L._PROTOS), declared ^ set(L._PROTOS)
     assert L.lib.brov_abi_version() == L.ABI_VERSION
     # struct layouts match the header's field order and sizes (LP64)
-    assert C.sizeof(L.RolloutDesc) == 4 + 4 + 8 * 14 + 4 + 4 + 4 + 4
-    assert C.sizeof(L.SeDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 * 4 + 4 + 8 * 4 + 4 + 4 + 8 + 8
-    assert C.sizeof(L.RolloutHostDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 + 8 * 5 + 4 + 4
+    gen = 4 + 4 + 8 + 8 + 8 * 3 + 8 * 8 + 8 + 8
+    assert C.sizeof(L.InputGen) == gen
+    assert C.sizeof(L.RolloutDesc) == 4 + 4 + 8 * 14 + 4 + 4 + 4 + 4 + 8 * 3 + gen
+    assert C.sizeof(L.GenInputsDesc) == 4 * 4 + 8 * 5 + gen + 8
+    assert C.sizeof(L.SeDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 * 4 + 4 + 8 * 4 + 4 + 4 + 8 + 8 + 8 + 8
+    assert C.sizeof(L.RolloutHostDesc) == 4 + 4 + 8 * 3 + 8 * 3 + 4 + 4 + 8 * 5 + 4 + 4 + gen + 8 + 8
     assert C.sizeof(L.PincWeights) == 4 * 4 + 5 * 8 + 5 * 8 + 4 * 4 + 4 * 8 + 4 * 8
     assert C.sizeof(L.PincRolloutDesc) == 4 + 4 + 8 * 11
     assert C.sizeof(L.PincSeDesc) == 4 + 4 + 4 * 4 + 8 * 5 + 4 + 4 + 8 * 3

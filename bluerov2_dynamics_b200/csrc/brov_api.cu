@@ -588,12 +588,12 @@ static int fill_gen(const brov_input_gen& g, int nu, InputGen<T>* out) {
         return fail(BROV_EINVAL, "input generator: need 0 <= rho <= 1, sigma >= 0, clip > 0");
     if (g.vehicle0 < 0) return fail(BROV_EINVAL, "input generator: vehicle0 < 0");
     out->on = 1;
-    out->rho = (T)g.rho;
+    out->rho = (float)g.rho;
     for (int j = 0; j < 8; ++j) {
         const double sc = j < nu ? g.scale[j] : 0.0;
         if (!(sc >= 0.0) || !std::isfinite(sc)) return fail(BROV_EINVAL, "input generator: scale[%d] must be finite and >= 0", j);
-        out->sigma[j] = (T)(g.sigma * sc);
-        out->clip[j] = (T)(std::isfinite(g.clip) ? g.clip * sc : g.clip);
+        out->sigma[j] = (float)(g.sigma * sc);
+        out->clip[j] = (float)(std::isfinite(g.clip) ? g.clip * sc : g.clip);
     }
     out->vehicle0 = (unsigned long long)g.vehicle0;
     out->k0 = (uint32_t)(g.seed & 0xffffffffu);
@@ -608,6 +608,8 @@ static int fill_gen(const brov_input_gen& g, int nu, InputGen<T>* out) {
 struct Lag24 {
     const void* in;
     void* out;
+    bool partial;   // the caller chains several calls over the filter's memory itself (brov_rollout_host): starting a
+                    // short call from zeros is intended
 };
 
 template <typename T>
@@ -644,7 +646,7 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
     long long depth = 0;
     if (want_thr_out) {
         if ((rc = carry_depth(e, d->dt, nsub, &depth))) return rc;
-        if (d->lag_in_dev && d->lag_in_repr == BROV_LAG_PROJECTED && !l24.in && d->steps < depth)
+        if (d->lag_in_dev && d->lag_in_repr == BROV_LAG_PROJECTED && !l24.in && !l24.partial && d->steps < depth)
             return fail(BROV_EINVAL, "per-thruster lag states cannot be recovered from an allocation-projected lag_in in a call of fewer than %lld steps", depth);
     }
 
@@ -742,7 +744,7 @@ static int check_rollout_common(brov_engine* e, int integrator, long long n, lon
 
 // public semantics of lag_in / lag_out -> the kernel call plus the per-thruster epilogue
 static int rollout_dev(brov_engine* e, const brov_rollout_desc* d, cudaStream_t st) {
-    Lag24 l24 = {nullptr, nullptr};
+    Lag24 l24 = {nullptr, nullptr, false};
     if (e->model == BROV_THRUSTER8_LAG3) {
         if (d->lag_out_dev && d->lag_out_repr == BROV_LAG_THRUSTER) l24.out = d->lag_out_dev;
         if (d->lag_in_dev && d->lag_in_repr == BROV_LAG_THRUSTER) l24.in = d->lag_in_dev;
@@ -1120,7 +1122,7 @@ extern "C" int brov_rollout_host(brov_engine_t* e, const brov_rollout_host_desc*
             r.singular_eps = d->singular_eps;
         }
         // per-thruster states: rebuilt by the chunks that cover the last `depth` steps of the call
-        Lag24 l24 = {nullptr, nullptr};
+        Lag24 l24 = {nullptr, nullptr, true};
         if (want24 && done + len > d->steps - depth) {
             l24.out = h.d_lag24;
             l24.in = (tail_started || (done == 0 && in24)) ? h.d_lag24 : nullptr;

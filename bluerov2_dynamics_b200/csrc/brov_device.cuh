@@ -113,6 +113,17 @@ __device__ __forceinline__ double rcp_(double a) {
     return r;
 }
 
+// 1/a without the range guard, for operands known to be normal and far from the ends of the exponent range (clamped
+// cosines >= 1e-7, quaternion norms >= 1e-12): no branch in the step
+__device__ __forceinline__ float rcp_nr(float a) { return rcp_(a); }
+__device__ __forceinline__ double rcp_nr(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    r = fma(r, fma(-a, r, 1.0), r);
+    r = fma(r, fma(-a, r, 1.0), r);
+    return r;
+}
+
 // sin & cos.  fp32: 3-term Cody-Waite reduction by pi/2 (FMA keeps the products exact) + minimax polynomials on
 // [-pi/4, pi/4] (Cephes sinf/cosf coefficients); |error| <= ~1.5 ulp.  No slow path, no local memory; domain
 // |a| < 2^30 rad (a float that large has an ulp of 64 rad anyway).
@@ -210,7 +221,9 @@ template <typename T> __device__ __forceinline__ T thrust_poly(const Consts<T>& 
 // nu_dot = Minv (tau - C(nu) nu - D(nu_r) nu_r - g); g from (sin th, cos th sin phi, cos th cos phi).
 // Every axis is ONE chain of fused multiply-adds onto tau_i: the Coriolis terms (closed form of C_RB + C_A times nu,
 // fossen/BlueROV2.py:280-325), the restoring terms (:340-355) and the damping term (:327-338) are accumulated with
-// their signs instead of being formed as separate vectors and subtracted (47 instead of 62 operations).
+// their signs instead of being formed as separate vectors and subtracted (47 instead of 62 operations; measured
+// against the separate-vector form, profiles/r02h_tune_variants.txt: fp32 thruster rollout 3.02 against 3.07 ms,
+// fp64 4.51 against 4.48 ms per 1000 steps — kept for both).
 template <typename T, class P>
 __device__ __forceinline__ void nu_dot(const T* __restrict__ nu, const T* __restrict__ nur, const T* __restrict__ tau,
                                        T sth, T cs, T cc, const P& p, T* __restrict__ out) {
@@ -317,7 +330,8 @@ __device__ __forceinline__ void rhs_euler12(const T* __restrict__ x, const Trig<
     {
         T ct = cth;
         if (abs_(ct) < T(1e-7)) ct = (ct > T(0)) ? T(1e-7) : ((ct < T(0)) ? T(-1e-7) : T(0));
-        T ic = rcp_(ct);
+        // |ct| >= 1e-7, or exactly +0 (sign(0) = 0), where the reference divides by zero: 1 / +0 = +inf
+        const T ic = (ct == T(0)) ? T(INFINITY) : rcp_nr(ct);
         T sq = sphi * nu[4] + cphi * nu[5];
         T psd = sq * ic;
         xd[5] = psd;
@@ -349,7 +363,7 @@ __device__ __forceinline__ void rhs_quat13(const T* __restrict__ x, const T* __r
         T n2 = qw * qw + qx * qx + qy * qy + qz * qz;
         T n = sqrt_(n2);
         if (n < T(1e-12)) { qw = T(1); qx = qy = qz = T(0); }
-        else { T in = rcp_(n); qw *= in; qx *= in; qy *= in; qz *= in; }
+        else { T in = rcp_nr(n); qw *= in; qx *= in; qy *= in; qz *= in; }
     }
     const T* nu = x + 7;
     T R00 = T(1) - T(2) * (qy * qy + qz * qz), R01 = T(2) * (qx * qy - qz * qw), R02 = T(2) * (qx * qz + qy * qw);
@@ -376,7 +390,7 @@ __device__ __forceinline__ void rhs_quat13(const T* __restrict__ x, const T* __r
 template <typename T> __device__ __forceinline__ void quat_renorm(T* q) {
     T n = sqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     if (n < T(1e-12)) { q[0] = T(1); q[1] = q[2] = q[3] = T(0); }
-    else { T in = rcp_(n); q[0] *= in; q[1] *= in; q[2] *= in; q[3] *= in; }
+    else { T in = rcp_nr(n); q[0] *= in; q[1] *= in; q[2] *= in; q[3] *= in; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -541,6 +555,132 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// counter-based input generator: the reference's "random thrust" command signal
+//     u_k = clip(0.98 u_{k-1} + 0.02 N(0,1), -1, 1)        training/train_sim_brov2_koopmanEDMDc.py:161-164,180
+// generated inside the kernels instead of being streamed from HBM.  The normal deviates of (vehicle, step) come from
+// Philox4x32-10 (Salmon et al., SC'11) keyed on the seed with the counter (vehicle lo, vehicle hi, step lo,
+// step hi << 1 | block): any step of any vehicle can be regenerated independently, chunked / sliced / sharded rollouts
+// see the identical stream.  The AR(1) state is the only thing carried (NU values per vehicle).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BROV_PHILOX_ROUNDS = 10;   // the standard safety margin; 7 rounds measured 4 % faster in fp32 only
+// rounds [r0, r1) of Philox4x32 on the counter block c[4]; the round keys are key + r * Weyl constants
+__device__ __forceinline__ void philox_rounds(uint32_t* __restrict__ c, uint32_t k0, uint32_t k1, int r0, int r1) {
+#pragma unroll
+    for (int r = r0; r < r1; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        c[0] = hi1 ^ c[1] ^ (k0 + (uint32_t)r * 0x9E3779B9u);
+        c[1] = lo1;
+        c[2] = hi0 ^ c[3] ^ (k1 + (uint32_t)r * 0xBB67AE85u);
+        c[3] = lo0;
+    }
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t* __restrict__ out) {
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    philox_rounds(out, k0, k1, 0, BROV_PHILOX_ROUNDS);
+}
+
+// two N(0,1) deviates from two 32-bit words: Box-Muller on 23-bit uniforms, fast-math transcendentals (MUFU).
+// u1 in (0, 1), u2 in [0, 1): n0 = sqrt(-2 ln u1) cos(2 pi u2), n1 = sqrt(-2 ln u1) sin(2 pi u2); |n| < 5.7.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* __restrict__ n0, float* __restrict__ n1) {
+    const float f1 = __uint_as_float(0x3f800000u | (a >> 9));            // [1, 2)
+    const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
+    const float u1 = f1 - 0.99999994f;                                    // (0, 1]: never 0
+    const float th = fmaf(f2, 6.2831855f, -6.2831855f);                   // 2 pi (f2 - 1)
+    const float r = sqrtf(-1.3862944f * __log2f(u1));                     // sqrt(-2 ln u1), ln = ln2 * log2
+    float s, c;
+    __sincosf(th, &s, &c);
+    *n0 = r * c;
+    *n1 = r * s;
+}
+
+// The AR(1) recursion runs in float32 whatever the engine's scalar type: the command signal is a sequence of
+// float32-representable numbers (half the registers in the fp64 kernels, and fp32 and fp64 engines fed the same seed
+// integrate the IDENTICAL inputs); the state arrays in memory have the engine's scalar type and convert exactly.
+template <typename T> struct InputGen {
+    float rho;
+    float sigma[8];       // sigma * scale_j
+    float clip[8];        // clip * scale_j
+    unsigned long long vehicle0;   // global index of local vehicle 0
+    uint32_t k0, k1;      // seed
+    const T* state_in;    // [n][NU] or nullptr (zeros)
+    T* state_out;         // [n][NU] or nullptr
+    int on;
+};
+
+// the 8 standard-normal deviates of (vehicle, step): depends on the counters only, never on the signal's state, so the
+// kernels draw the deviates of step k+1 while step k integrates (integer / MUFU work under the FP pipes' latency)
+template <typename T>
+__device__ __forceinline__ void gen_normals(const InputGen<T>& g, unsigned long long veh, long long step,
+                                            float* __restrict__ n) {
+    const uint32_t v0 = (uint32_t)veh, v1 = (uint32_t)(veh >> 32);
+    const uint32_t s0 = (uint32_t)step, s1 = (uint32_t)((unsigned long long)step >> 32) << 1;
+    uint32_t w[8];
+    philox4x32_10(v0, v1, s0, s1, g.k0, g.k1, w);
+    philox4x32_10(v0, v1, s0, s1 | 1u, g.k0, g.k1, w + 4);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) box_muller(w[j], w[j + 1], &n[j], &n[j + 1]);
+}
+// s <- clip(rho s + sigma n, -clip, clip)
+template <typename T, int NU>
+__device__ __forceinline__ void gen_apply(const InputGen<T>& g, const float* __restrict__ n, float* __restrict__ s) {
+#pragma unroll
+    for (int j = 0; j < NU; ++j) s[j] = fminf(fmaxf(fmaf(g.rho, s[j], g.sigma[j] * n[j]), -g.clip[j]), g.clip[j]);
+}
+// advance the AR(1) input state s[NU] of global vehicle `veh` to global step `step`
+template <typename T, int NU>
+__device__ __forceinline__ void gen_advance(const InputGen<T>& g, unsigned long long veh, long long step,
+                                            float* __restrict__ s) {
+    float n[8];
+    gen_normals<T>(g, veh, step, n);
+    gen_apply<T, NU>(g, n, s);
+}
+
+// The deviates of the NEXT step, drawn in slices between the stages of the current step (integrate_step calls
+// work(0..3)): the Philox rounds are dependent integer multiplies and the Box-Muller transform is MUFU work — placed in
+// one lump at the top of the step they stall a warp that has only one other warp to hide behind (fp64: +30 % per step
+// measured, r02f); spread through the step they issue into the latency gaps of the FP pipes.
+template <typename T> struct GenSide {
+    const InputGen<T>& g;
+    uint32_t c[8];        // two counter blocks in flight
+    float n[8];           // finished deviates
+    __device__ __forceinline__ GenSide(const InputGen<T>& g_) : g(g_) {}
+    __device__ __forceinline__ void start(unsigned long long veh, long long step) {
+        c[0] = c[4] = (uint32_t)veh;
+        c[1] = c[5] = (uint32_t)(veh >> 32);
+        c[2] = c[6] = (uint32_t)step;
+        c[3] = (uint32_t)((unsigned long long)step >> 32) << 1;
+        c[7] = c[3] | 1u;
+    }
+    __device__ __forceinline__ void rounds(int r0, int r1) {
+        philox_rounds(c, g.k0, g.k1, r0, r1);
+        philox_rounds(c + 4, g.k0, g.k1, r0, r1);
+    }
+    __device__ __forceinline__ void finish() {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) box_muller(c[j], c[j + 1], &n[j], &n[j + 1]);
+    }
+    // slice s of 4 (RK4: one per stage); `all`: everything at once (Euler step)
+    __device__ __forceinline__ void work(int s) {
+        constexpr int R = BROV_PHILOX_ROUNDS;
+        // one counter block after the other (4 live words instead of 8): 5.37 against 5.65 ms per 1000 fp64 steps
+        // with both blocks in flight (profiles/r02k_tune_variants.txt)
+        if (s == 0) philox_rounds(c, g.k0, g.k1, 0, R / 2);
+        else if (s == 1) philox_rounds(c, g.k0, g.k1, R / 2, R);
+        else if (s == 2) philox_rounds(c + 4, g.k0, g.k1, 0, R / 2);
+        else { philox_rounds(c + 4, g.k0, g.k1, R / 2, R); finish(); }
+    }
+    __device__ __forceinline__ void all() { rounds(0, BROV_PHILOX_ROUNDS); finish(); }
+};
+struct NoSide {
+    __device__ __forceinline__ NoSide() {}
+    template <class G> __device__ __forceinline__ explicit NoSide(const G&) {}
+    __device__ __forceinline__ void work(int) {}
+    __device__ __forceinline__ void all() {}
+};
+
+// ---------------------------------------------------------------------------------------------------------------
 // one integrator step of one vehicle (the body of simulate_physics' loop: RK4 training/train_tank_brov2_rk4.py:386-394,
 // Euler training/train_tank_brov2_full_comparison.py:462-465, quaternion re-normalisation
 // training/train_tank_brov2_wrench_quat.py:262-263)
@@ -550,9 +690,10 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
 //   abs_cth |cos theta| of the state the step starts from (Euler-angle Fossen models; 1 otherwise): how close the
 //           vehicle is to the singularity of the Euler-rate kinematics (fossen/BlueROV2.py:43-62)
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODEL, int INTEG, bool LAG1, class P>
+//   side    work to interleave with the step (GenSide: the next step's input deviates; NoSide: nothing)
+template <typename T, int MODEL, int INTEG, bool LAG1, class P, class SIDE>
 __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x, T* __restrict__ lag,
-                                               const T* __restrict__ u, T& abs_cth) {
+                                               const T* __restrict__ u, T& abs_cth, SIDE& side) {
     constexpr int NX = ModelDim<MODEL>::NX;
     constexpr int NL = LAG1 ? 6 : 1;  // continuous auxiliary states integrated with x
     constexpr bool LAGW = true;
@@ -578,6 +719,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
     abs_cth = (EULER_ANGLES && !ModelDim<MODEL>::DI) ? abs_(tr0.cth) : T(1);
     if constexpr (INTEG == INTEG_EULER) {
         model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, 0, x, tr0, lag, Fu, k, kl);
+        side.all();
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt * k[i];
         if constexpr (LAG1) {
@@ -593,6 +735,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, 0, x, tr0, lag, Fu, k, kl);
 #pragma unroll
         for (int s = 1; s <= 3; ++s) {
+            side.work(s - 1);
             const T w = (s == 1) ? T(1) : T(2);   // weight of the stage just evaluated
             const T h = (s == 3) ? dt : hdt;      // offset of the next stage
 #pragma unroll
@@ -614,6 +757,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
             }
             model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, s, xs, trs, LAG1 ? ls : lag, Fu, k, kl);
         }
+        side.work(3);
         const T dt6 = dt * T(1.0 / 6.0);
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt6 * (acc[i] + k[i]);
@@ -624,75 +768,6 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
     }
     if constexpr (MODEL == MODEL_THRUSTER8) lag_advance<T, LAGW>(c, lag, Fu);
     if constexpr (ModelDim<MODEL>::QUAT) quat_renorm<T>(x + 3);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// counter-based input generator: the reference's "random thrust" command signal
-//     u_k = clip(0.98 u_{k-1} + 0.02 N(0,1), -1, 1)        training/train_sim_brov2_koopmanEDMDc.py:161-164,180
-// generated inside the kernels instead of being streamed from HBM.  The normal deviates of (vehicle, step) come from
-// Philox4x32-10 (Salmon et al., SC'11) keyed on the seed with the counter (vehicle lo, vehicle hi, step lo,
-// step hi << 1 | block): any step of any vehicle can be regenerated independently, chunked / sliced / sharded rollouts
-// see the identical stream.  The AR(1) state is the only thing carried (NU values per vehicle).
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t* __restrict__ out) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// two N(0,1) deviates from two 32-bit words: Box-Muller on 23-bit uniforms, fast-math transcendentals (MUFU).
-// u1 in (0, 1), u2 in [0, 1): n0 = sqrt(-2 ln u1) cos(2 pi u2), n1 = sqrt(-2 ln u1) sin(2 pi u2); |n| < 5.7.
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* __restrict__ n0, float* __restrict__ n1) {
-    const float f1 = __uint_as_float(0x3f800000u | (a >> 9));            // [1, 2)
-    const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
-    const float u1 = f1 - 0.99999994f;                                    // (0, 1]: never 0
-    const float th = fmaf(f2, 6.2831855f, -6.2831855f);                   // 2 pi (f2 - 1)
-    const float r = sqrtf(-1.3862944f * __log2f(u1));                     // sqrt(-2 ln u1), ln = ln2 * log2
-    float s, c;
-    __sincosf(th, &s, &c);
-    *n0 = r * c;
-    *n1 = r * s;
-}
-
-template <typename T> struct InputGen {
-    T rho;
-    T sigma[8];           // sigma * scale_j
-    T clip[8];            // clip * scale_j
-    unsigned long long vehicle0;   // global index of local vehicle 0
-    uint32_t k0, k1;      // seed
-    const T* state_in;    // [n][NU] or nullptr (zeros)
-    T* state_out;         // [n][NU] or nullptr
-    int on;
-};
-
-// advance the AR(1) input state s[NU] of global vehicle `veh` to global step `step`: s <- clip(rho s + sigma n)
-template <typename T, int NU>
-__device__ __forceinline__ void gen_advance(const InputGen<T>& g, unsigned long long veh, long long step,
-                                            T* __restrict__ s) {
-    const uint32_t v0 = (uint32_t)veh, v1 = (uint32_t)(veh >> 32);
-    const uint32_t s0 = (uint32_t)step, s1 = (uint32_t)((unsigned long long)step >> 32) << 1;
-    uint32_t w[8];
-    philox4x32_10(v0, v1, s0, s1, g.k0, g.k1, w);
-    philox4x32_10(v0, v1, s0, s1 | 1u, g.k0, g.k1, w + 4);
-    float n[8];
-#pragma unroll
-    for (int j = 0; j < 8; j += 2) box_muller(w[j], w[j + 1], &n[j], &n[j + 1]);
-#pragma unroll
-    for (int j = 0; j < NU; ++j) {
-        T v = g.rho * s[j] + g.sigma[j] * T(n[j]);
-        v = v > g.clip[j] ? g.clip[j] : v;
-        s[j] = v < -g.clip[j] ? -g.clip[j] : v;
-    }
 }
 
 }  // namespace brov

@@ -27,20 +27,23 @@ constexpr int TAIL_BLOCK = 256;
 //   fp64: 128-thread blocks, no register cap (~250 registers, 8 warps per SM), lag state and RK4 accumulator in
 //         registers, next-step inputs prefetched, constant block in shared memory.
 constexpr int ROLLOUT_BLOCK = 128;
-#ifndef BROV_F32_MAXREG
-#define BROV_F32_MAXREG 128
-#endif
-#ifndef BROV_F32_PV_MAXREG
-#define BROV_F32_PV_MAXREG 168    // Monte-Carlo fp32 kernels keep the per-vehicle coefficients in registers
-#endif
-#ifndef BROV_F32_PV_REGS
-#define BROV_F32_PV_REGS 1
-#endif
-template <typename T, bool PV> struct MaxReg {
-    static constexpr int N = sizeof(T) == 8 ? 255 : (PV && BROV_F32_PV_REGS ? BROV_F32_PV_MAXREG : BROV_F32_MAXREG);
+// Register caps.  fp32: 128 (16 warps per SM) for every kernel, the Monte-Carlo ones included (per-vehicle
+// coefficients in registers: 2.90 ms per 100 steps of 1,048,576 vehicles at 128, 2.99 at 168, 3.07 with the table in
+// shared memory; profiles/r02d_tune_variants.txt).  fp64: none — the wrench-input kernels do fit 168 registers with
+// the prefetch path, but 12 instead of 8 warps per SM bought 2 % (wrench12) / 6 % (quat13) and cost the Monte-Carlo
+// kernel 30 % in spills (profiles/r02i_tune_variants.txt): they are bound by dependent-issue latency inside a stage,
+// not by the number of warps.
+template <typename T> struct MaxReg { static constexpr int N = sizeof(T) == 8 ? 255 : 128; };
+// Which streamed-input path a kernel is built with (measured on B200, profiles/r02f / r02g_tune_variants.txt; ms per 100 RK4
+// steps, 65,536 fp64 / 1,048,576 fp32 vehicles, TMA ring vs register prefetch): wrench12 fp64 0.386 / 0.432, quat13 fp64
+// 0.369 / 0.424, Monte-Carlo fp32 2.94 / 3.07 (wrench12) and 3.15 / 3.51 (quat13) — the ring wins where the step
+// leaves registers for the compiler to schedule with; thruster8 fp64 0.551 / 0.485 and fp32 3.36 / 3.03, wrench12
+// fp32 2.48 / 2.40 — the barrier at the top of the loop costs more than the prefetch registers.
+template <typename T, int MODEL, bool PV> struct UseTma {
+    static constexpr bool V = sizeof(T) == 8 ? MODEL != MODEL_THRUSTER8 : PV;
 };
 // where the per-vehicle coefficient table lives during a launch: fp32 registers, fp64 shared memory [36][BLOCK]
-template <typename T, bool PV> struct PvInRegs { static constexpr bool V = PV && sizeof(T) == 4 && BROV_F32_PV_REGS; };
+template <typename T, bool PV> struct PvInRegs { static constexpr bool V = PV && sizeof(T) == 4; };
 
 // per-launch health accounting (optional): vehicles whose final state is not finite, vehicles that came within eps of
 // the Euler-angle singularity theta = +-pi/2 (fossen/BlueROV2.py:43-62 clamps cos theta there)
@@ -146,49 +149,54 @@ __device__ __forceinline__ void load_u(const T* __restrict__ p, bool vec, T* __r
 // registers one step ahead) costing the wrench fp64 kernel 20 % of its cycles in long-scoreboard stalls because the
 // loads shared a scoreboard with the first shared-memory constant load of the step.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int U_STAGES = 4;   // steps in flight per warp
+constexpr int U_STAGES = 4;   // steps in flight per warp (2 measured the same: the ring is never the bottleneck)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_init_fence() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 // arm the barrier with the byte count, then start the bulk copy that completes on it (bytes % 16 == 0, 16 B aligned)
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+// No "memory" clobbers on the ring's instructions: the ring is only ever touched through volatile asm (these and
+// load_u_smem), which the compiler keeps in program order among themselves; a clobber would also pin every ordinary
+// shared-memory load of the step — the fp64 constant block — behind the wait at the top of the loop, and the r02e
+// capture showed exactly that as short-scoreboard stalls all over the step (5.11 against 4.51 ms per 1000 steps).
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar));
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
     uint32_t ok;
     do {
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok)
-                     : "r"(addr), "r"(parity)
-                     : "memory");
+                     : "r"(addr), "r"(parity));
     } while (!ok);
 }
-// this lane's input row out of a ring slot (rows are NU scalars, row stride = NU)
+// warp barrier WITHOUT compiler memory-fence semantics (__syncwarp() has them and would keep the step's constant
+// loads from moving across the top of the loop): all the ring needs is that every lane has executed its reads of a
+// slot — volatile asm, in program order before this — when lane 0 hands the slot back to the TMA engine
+__device__ __forceinline__ void warp_sync_nofence() { asm volatile("bar.warp.sync 0xffffffff;"); }
+// this lane's input row out of a ring slot; `row` is a 32-bit shared-window address (one register, no generic
+// pointer arithmetic in the step loop)
 template <typename T, int NU>
-__device__ __forceinline__ void load_u_smem(const T* __restrict__ row, T* __restrict__ u) {
-    if constexpr (sizeof(T) * NU % 16 == 0) {
-        using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-        constexpr int VEC = 16 / sizeof(T);
+__device__ __forceinline__ void load_u_smem(uint32_t row, T* __restrict__ u) {
+    if constexpr (sizeof(T) == 8) {
 #pragma unroll
-        for (int j = 0; j < NU / VEC; ++j) {
-            V v = reinterpret_cast<const V*>(row)[j];
-            if constexpr (sizeof(T) == 4) { u[4 * j] = v.x; u[4 * j + 1] = v.y; u[4 * j + 2] = v.z; u[4 * j + 3] = v.w; }
-            else { u[2 * j] = v.x; u[2 * j + 1] = v.y; }
-        }
+        for (int j = 0; j < NU / 2; ++j)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(u[2 * j]), "=d"(u[2 * j + 1]) : "r"(row + 16 * j));
+    } else if constexpr (NU % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NU / 4; ++j)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(u[4 * j]), "=f"(u[4 * j + 1]), "=f"(u[4 * j + 2]), "=f"(u[4 * j + 3]) : "r"(row + 16 * j));
     } else {   // fp32, 6 inputs: 24-byte rows
-        const float2* q = reinterpret_cast<const float2*>(row);
 #pragma unroll
-        for (int j = 0; j < NU / 2; ++j) { float2 v = q[j]; u[2 * j] = v.x; u[2 * j + 1] = v.y; }
+        for (int j = 0; j < NU / 2; ++j)
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[2 * j]), "=f"(u[2 * j + 1]) : "r"(row + 8 * j));
     }
 }
 
@@ -268,7 +276,7 @@ __device__ __forceinline__ void count_health(const Health& h, bool bad, bool nea
 
 // GEN: the inputs are generated in the kernel (gen_advance) instead of being read from a.U
 template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__((MaxReg<T, PV>::N))
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__(MaxReg<T>::N)
 rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     constexpr int BLOCK = ROLLOUT_BLOCK;
     constexpr int NX = ModelDim<MODEL>::NX;
@@ -355,8 +363,8 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     T lag[NL];
     if (slice > 0) load_lag<T, MODEL, LAG1>(a.c, a.lag_out, true, i, lag);
     else load_lag<T, MODEL, LAG1>(a.c, a.lag_in, a.lag_in_w != 0, i, lag);
-    T mc = T(1);   // running min of |cos theta|
-    if (a.mincos && (slice > 0 || !a.mincos_init)) mc = __ldcg(a.mincos + i);
+    float mc = 1.0f;   // running min of |cos theta| (float: a health metric, and one register in the fp64 kernels)
+    if (a.mincos && (slice > 0 || !a.mincos_init)) mc = (float)__ldcg(a.mincos + i);
 
     const int nsteps = k_end - k_begin;
     const long long warp_v0 = (long long)vb * BLOCK + warp * 32;
@@ -364,70 +372,98 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const int warp_n = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem));   // live vehicles of this warp
     const int n_valid = warp_n * NX;
 
-    // Inputs.  Generated: u is the AR(1) state of the command signal, advanced in registers.  Streamed, per-vehicle
-    // time-major layout: the warp's rows of step k are one contiguous block, fetched U_STAGES - 1 steps ahead by the
-    // TMA engine into the warp's shared-memory ring.  Other layouts (one series shared by all vehicles, one constant
-    // row per vehicle, unaligned buffers): plain loads, which hit L1 after the first touch.
+    // Inputs of the step, one of three sources:
+    //  GEN       generated in the kernel: gs is the AR(1) state of the command signal, the deviates of the next step
+    //            are drawn between the stages of the current one (GenSide);
+    //  TMA ring  per-vehicle time-major series, 16-byte aligned: the warp's rows of step k are one contiguous block,
+    //            fetched U_STAGES - 1 steps ahead by the TMA engine into the warp's shared-memory ring (kernels
+    //            chosen by UseTma; unaligned / shared / constant layouts fall back to plain loads, L1 hits);
+    //  prefetch  every layout, next step's row loaded into registers one step ahead (the other kernels).
     T u[NU];
+    constexpr bool TMA = !GEN && UseTma<T, MODEL, PV>::V;
+    constexpr bool PREFETCH = !GEN && !TMA;
     constexpr uint32_t ROW_BYTES = NU * sizeof(T);
-    __shared__ __align__(8) uint64_t u_bar[BLOCK / 32][U_STAGES];
-    T* ring = tiles + (a.traj ? BLOCK * NX : 0) + warp * (U_STAGES * 32 * NU);
+    constexpr uint32_t SLOT_BYTES = 32 * ROW_BYTES;
+    __shared__ __align__(8) uint64_t u_bar[TMA ? BLOCK / 32 : 1][U_STAGES];
+    const uint32_t ring = smem_u32(tiles + (a.traj ? BLOCK * NX : 0) + warp * (U_STAGES * 32 * NU));   // shared-window address
+    const uint32_t bars = smem_u32(&u_bar[TMA ? warp : 0][0]);
     const uint32_t warp_bytes = (uint32_t)warp_n * ROW_BYTES;
-    const bool tma = !GEN && a.u_tma && warp_n > 0 && (warp_bytes % 16u) == 0;   // uniform per warp
+    const bool tma = TMA && a.u_tma && warp_n > 0 && (warp_bytes % 16u) == 0;   // uniform per warp
     const T* up = a.U + i * a.u_stride_n + (long long)k_begin * a.u_stride_t;
     const T* wsrc = a.U + warp_v0 * NU + (long long)k_begin * a.u_stride_t;     // row of the warp's first vehicle
-    const T* myrow = ring + (lane < warp_n ? lane : (warp_n > 0 ? warp_n - 1 : 0)) * NU;
+    const uint32_t myrow = ring + (uint32_t)(lane < warp_n ? lane : (warp_n > 0 ? warp_n - 1 : 0)) * ROW_BYTES;
     const bool uvec = a.u_vec != 0;
+    const bool stream = a.u_stride_n != 0;  // per-vehicle inputs are read exactly once: evict-first
+    float gs[GEN ? NU : 1];
     if constexpr (GEN) {
         const T* ssrc = slice > 0 ? a.gen.state_out : a.gen.state_in;
 #pragma unroll
-        for (int j = 0; j < NU; ++j) u[j] = ssrc ? __ldcg(ssrc + i * NU + j) : T(0);
-    } else if (tma) {
-        if (lane == 0) {
+        for (int j = 0; j < NU; ++j) gs[j] = ssrc ? (float)__ldcg(ssrc + i * NU + j) : 0.0f;
+    } else if constexpr (TMA) {
+        if (tma) {
+            if (lane == 0) {
 #pragma unroll
-            for (int s = 0; s < U_STAGES; ++s) mbar_init(&u_bar[warp][s], 1);
-            mbar_init_fence();
+                for (int s = 0; s < U_STAGES; ++s) mbar_init(bars + 8 * s, 1);
+                mbar_init_fence();
 #pragma unroll
-            for (int s = 0; s < U_STAGES - 1; ++s)
-                if (s < nsteps) tma_load_1d(ring + s * 32 * NU, wsrc + (long long)s * a.u_stride_t, warp_bytes, &u_bar[warp][s]);
+                for (int s = 0; s < U_STAGES - 1; ++s)
+                    if (s < nsteps) tma_load_1d(ring + s * SLOT_BYTES, wsrc + (long long)s * a.u_stride_t, warp_bytes, bars + 8 * s);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+    } else if (nsteps > 0) {
+        if (stream) load_u<T, NU, true>(up, uvec, u); else load_u<T, NU, false>(up, uvec, u);
     }
 
     const long long gstep0 = a.step0 + k_begin;
     const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)i;
     int countdown = a.traj ? (int)(a.stride - (gstep0 % a.stride)) : 0x7fffffff;
     long long snap = a.traj ? (gstep0 / a.stride - a.snap_base) : 0;
+    typename std::conditional<GEN, GenSide<T>, NoSide>::type side{a.gen};
+    if constexpr (GEN) { side.start(veh, gstep0); side.all(); }
 
     for (int k = 0; k < nsteps; ++k) {
+        T un[PREFETCH ? NU : 1];
         if constexpr (GEN) {
             if (a.gen_snap && k_begin + k == a.gen_snap_step && live) {
 #pragma unroll
-                for (int j = 0; j < NU; ++j) a.gen_snap[i * NU + j] = u[j];
+                for (int j = 0; j < NU; ++j) a.gen_snap[i * NU + j] = T(gs[j]);
             }
-            gen_advance<T, NU>(a.gen, veh, gstep0 + k, u);
-        } else if (tma) {
-            // refill the slot read one step ago (all lanes are past those reads: they sit before the previous step)
-            const int kn = k + U_STAGES - 1;
-            __syncwarp();
-            if (lane == 0 && kn < nsteps)
-                tma_load_1d(ring + (kn % U_STAGES) * 32 * NU, wsrc + (long long)kn * a.u_stride_t, warp_bytes,
-                            &u_bar[warp][kn % U_STAGES]);
-            mbar_wait(&u_bar[warp][k % U_STAGES], (uint32_t)(k / U_STAGES) & 1u);
-            load_u_smem<T, NU>(myrow + (k % U_STAGES) * 32 * NU, u);
+            gen_apply<T, NU>(a.gen, side.n, gs);
+            side.start(veh, gstep0 + k + 1);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) u[j] = T(gs[j]);
+        } else if constexpr (TMA) {
+            if (tma) {
+                // refill the slot read one step ago (every lane has executed those reads: they precede the last step)
+                const int kn = k + U_STAGES - 1;
+                warp_sync_nofence();
+                if (lane == 0 && kn < nsteps)
+                    tma_load_1d(ring + (kn % U_STAGES) * SLOT_BYTES, wsrc + (long long)kn * a.u_stride_t, warp_bytes,
+                                bars + 8 * (kn % U_STAGES));
+                mbar_wait(bars + 8 * (k % U_STAGES), (uint32_t)(k / U_STAGES) & 1u);
+                load_u_smem<T, NU>(myrow + (k % U_STAGES) * SLOT_BYTES, u);
+            } else {
+                load_u<T, NU, false>(up + (long long)k * a.u_stride_t, uvec, u);
+            }
         } else {
-            load_u<T, NU, false>(up + (long long)k * a.u_stride_t, uvec, u);
+            const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
+            if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
         }
 
         T acth;
-        integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth);
-        mc = acth < mc ? acth : mc;
+        integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth, side);
+        mc = fminf(mc, (float)acth);
 
         if (--countdown == 0) {
             countdown = a.stride;
             T* dst = a.traj + (snap * a.n + warp_v0) * NX;
             snapshot_warp<T, NX>(tiles + warp * 32 * NX, x, dst, n_valid, a.traj_vec != 0, lane);
             ++snap;
+        }
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) u[j] = un[j];
         }
     }
 
@@ -438,11 +474,11 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
 #pragma unroll
             for (int j = 0; j < NL; ++j) a.lag_out[i * NL + j] = lag[j];
         }
-        if (a.mincos) a.mincos[i] = mc;
+        if (a.mincos) a.mincos[i] = T(mc);
         if constexpr (GEN) {
             if (a.gen.state_out) {
 #pragma unroll
-                for (int j = 0; j < NU; ++j) a.gen.state_out[i * NU + j] = u[j];
+                for (int j = 0; j < NU; ++j) a.gen.state_out[i * NU + j] = T(gs[j]);
             }
         }
     }
@@ -501,17 +537,18 @@ template <typename T>
 __global__ void __launch_bounds__(RHS_BLOCK) lag_tail_gen_kernel(const __grid_constant__ LagTailArgs<T> a) {
     const long long i = (long long)blockIdx.x * RHS_BLOCK + threadIdx.x;
     if (i >= a.n) return;
-    T lag[24], s[8];
+    T lag[24];
+    float s[8];
 #pragma unroll
     for (int j = 0; j < 24; ++j) lag[j] = a.lag_in ? a.lag_in[i * 24 + j] : T(0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = a.gen_state ? a.gen_state[i * 8 + j] : T(0);
+    for (int j = 0; j < 8; ++j) s[j] = a.gen_state ? (float)a.gen_state[i * 8 + j] : 0.0f;
     const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)i;
     for (int k = a.first; k < a.steps; ++k) {
         gen_advance<T, 8>(a.gen, veh, a.step0 + k, s);
         T F[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(s[j]);
+        for (int j = 0; j < 8; ++j) F[j] = thrust_poly<T>(T(s[j]));
         lag_advance<T, false>(a.c, lag, F);
     }
 #pragma unroll
@@ -536,17 +573,17 @@ __global__ void __launch_bounds__(RHS_BLOCK) gen_inputs_kernel(const __grid_cons
     const long long j = (long long)blockIdx.x * RHS_BLOCK + threadIdx.x;
     if (j >= a.n_sel) return;
     const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)(a.first + j * a.vstride);
-    T s[NU];
+    float s[NU];
 #pragma unroll
-    for (int q = 0; q < NU; ++q) s[q] = a.gen.state_in ? a.gen.state_in[j * NU + q] : T(0);
+    for (int q = 0; q < NU; ++q) s[q] = a.gen.state_in ? (float)a.gen.state_in[j * NU + q] : 0.0f;
     for (int k = 0; k < a.steps; ++k) {
         gen_advance<T, NU>(a.gen, veh, a.step0 + k, s);
 #pragma unroll
-        for (int q = 0; q < NU; ++q) a.out[((long long)k * a.n_sel + j) * NU + q] = s[q];
+        for (int q = 0; q < NU; ++q) a.out[((long long)k * a.n_sel + j) * NU + q] = T(s[q]);
     }
     if (a.gen.state_out) {
 #pragma unroll
-        for (int q = 0; q < NU; ++q) a.gen.state_out[j * NU + q] = s[q];
+        for (int q = 0; q < NU; ++q) a.gen.state_out[j * NU + q] = T(s[q]);
     }
 }
 
@@ -685,7 +722,7 @@ __global__ void __launch_bounds__(RHS_BLOCK) thruster_series_kernel(const __grid
 // multi-horizon endpoint squared error over sliding windows
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODEL, int INTEG>
-__global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__((MaxReg<T, false>::N))
+__global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__(MaxReg<T>::N)
 se_kernel(const __grid_constant__ SeArgs<T> a) {
     constexpr int BLOCK = ROLLOUT_BLOCK;
     constexpr int NX = ModelDim<MODEL>::NX;
@@ -740,7 +777,8 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
         T u[NU];
         load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
         T acth;
-        integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth);
+        NoSide side;
+        integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth, side);
         mc = acth < mc ? acth : mc;
 #pragma unroll
         for (int h = 0; h < MAX_H; ++h) {

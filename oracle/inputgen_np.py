@@ -67,16 +67,18 @@ def normals(seed: int, vehicles, steps):
 
 def command_signal(seed: int, vehicles, step0: int, steps: int, nu: int = 8, rho=0.98, sigma=0.02, clip=1.0, scale=None,
                    state0=None, dtype=np.float64):
-    """U [steps, len(vehicles), nu] and the AR(1) state after the last step, in the engine's arithmetic order:
-    s <- clip(rho s + (sigma scale_j) n, -(clip scale_j), clip scale_j), evaluated in `dtype`."""
+    """U [steps, len(vehicles), nu] and the AR(1) state after the last step.  As in the engine the recursion
+    s <- clip(rho s + (sigma scale_j) n, -(clip scale_j), clip scale_j) runs in float32 whatever the engine's scalar
+    type (the signal is a sequence of float32-representable numbers); the result is returned as `dtype`."""
     veh = np.asarray(vehicles)
-    n = normals(seed, veh, np.arange(step0, step0 + steps))[..., :nu].astype(dtype)
+    f = np.float32
+    n = normals(seed, veh, np.arange(step0, step0 + steps))[..., :nu]
     sc = np.ones(nu) if scale is None else np.asarray(scale, float)
-    sg, cl = (sigma * sc).astype(dtype), (clip * sc).astype(dtype)
-    s = np.zeros((len(veh), nu), dtype) if state0 is None else np.array(state0, dtype)
-    U = np.zeros((steps, len(veh), nu), dtype)
-    r = dtype(rho)
+    sg, cl = (sigma * sc).astype(f), (clip * sc).astype(f)
+    s = np.zeros((len(veh), nu), f) if state0 is None else np.array(state0, f)
+    U = np.zeros((steps, len(veh), nu), f)
+    r = f(rho)
     for k in range(steps):
-        s = np.clip(r * s + sg * n[k], -cl, cl).astype(dtype)
+        s = np.clip(r * s + sg * n[k], -cl, cl).astype(f)     # the device fuses the multiply-add: equal to ~1 ulp
         U[k] = s
-    return U, s
+    return U.astype(dtype), s.astype(dtype)

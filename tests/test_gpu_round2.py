@@ -196,15 +196,21 @@ def test_generated_inputs_rollout(B, dtype, tol, kind, nu):
     assert torch.equal(a.gen_state, s_end)
     if a.lag is not None:
         assert torch.equal(a.lag, b.lag)          # per-thruster lag from the regenerated tail == from the array
-    # chunks carry (x, lag, generator state); slices and an unaligned number of chunks change nothing
+    # chunks carry (x, the kernel's own lag, generator state); slices and a ragged number of chunks change nothing
     x, lag, gs = e.tensor(x0), None, None
     for c0 in range(0, T, 37):
         m = min(37, T - c0)
-        r = e.rollout(x, gen=gen, steps=m, step0=c0, dt=DT, lag0=lag, gen_state=gs, time_slices=2 if m > 16 else 1)
+        r = e.rollout(x, gen=gen, steps=m, step0=c0, dt=DT, lag0=lag, gen_state=gs, time_slices=2 if m > 16 else 1,
+                      lag_repr="projected")
         x, lag, gs = r.xT, r.lag, r.gen_state
     assert torch.equal(x, a.xT) and torch.equal(gs, a.gen_state)
-    if lag is not None:
-        assert normwise(cpu(lag), cpu(a.lag)) < (1e-13 if dtype == "f64" else 1e-5)
+    if a.lag is not None:   # ... and with the per-thruster carry (re-projected at every chunk start) to rounding
+        x, lag, gs = e.tensor(x0), None, None
+        for c0 in range(0, T, 37):
+            r = e.rollout(x, gen=gen, steps=min(37, T - c0), step0=c0, dt=DT, lag0=lag, gen_state=gs)
+            x, lag, gs = r.xT, r.lag, r.gen_state
+        rt = 1e-13 if dtype == "f64" else 2e-5
+        assert normwise(cpu(x), cpu(a.xT)) < rt and normwise(cpu(lag), cpu(a.lag)) < rt
     for q in (1, 3, 5):
         r = e.rollout(x0, gen=gen, steps=T, dt=DT, stride=10, time_slices=q)
         assert torch.equal(r.xT, a.xT) and torch.equal(r.traj, a.traj) and torch.equal(r.gen_state, a.gen_state), q
@@ -238,7 +244,7 @@ def test_health_counters_and_min_abs_cos(B):
     mco = np.ones(n)
     CO.rollout("thruster8", "rk4", DT, x0, U, min_abs_cos=mco)
     ok = mco > 0.02                                 # away from the singularity both trajectories agree
-    assert np.max(np.abs(cpu(mc)[ok] - mco[ok])) < 1e-9
+    assert np.max(np.abs(cpu(mc)[ok] - mco[ok])) < 2e-7     # the engine keeps this health metric in float32
     hc = r.health.cpu().numpy()
     assert hc[0] == 0 and abs(int(hc[1]) - int((mco < 0.05).sum())) <= 2 and hc[1] > 0
     # chunked accumulation and time slices give the same per-vehicle minima
@@ -260,12 +266,14 @@ def test_health_counters_and_min_abs_cos(B):
     # evaluator: windows near the singularity are reported next to the squared errors
     X = np.zeros((300, 12)); X[:, 4] = np.linspace(1.50, 1.64, 300)
     hv = torch.zeros(2, device="cuda", dtype=torch.int64)
+    e.multistep_se(X, O.smooth_inputs(rng, 300, 8), [1], dt=DT, health_out=hv, singular_eps=0.01)
+    want = int((np.abs(np.cos(X[:299, 4])) < 0.01).sum())      # H = 1: only the window starts are evaluated
+    assert hv[0] == 0 and abs(int(hv[1]) - want) <= 1 and hv[1] > 0
     e.multistep_se(X, O.smooth_inputs(rng, 300, 8), [1, 5], dt=DT, health_out=hv, singular_eps=0.01)
-    want = int((np.abs(np.cos(X[:299, 4])) < 0.01).sum())
-    assert hv[0] == 0 and abs(int(hv[1]) - want) <= 6 and hv[1] > 0
+    assert hv[0] == 0 and int(hv[1]) >= want                   # longer windows drift into the band as well
 
 
-@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 1e-5)])
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 5e-5)])
 def test_cos_theta_clamp_against_reference(B, golden_r2, dtype, tol):
     """The reference clamps |cos theta| < 1e-7 to 1e-7 sign(cos theta) (fossen/BlueROV2.py:52-56): right-hand sides and
     one Euler step on and next to theta = +-pi/2, both signs of the tiny cosine, against the unmodified reference."""
@@ -273,15 +281,25 @@ def test_cos_theta_clamp_against_reference(B, golden_r2, dtype, tol):
 
     def rel(a, b):
         return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
-    rows = slice(0, 8) if dtype == "f64" else [0, 1, 6, 7]     # float32 cannot represent pi/2 +- 5e-8
-    e = B.Engine("thruster8", dtype)
-    assert rel(cpu(e.rhs(g["clamp_x"], g["clamp_u8"], dt=DT))[rows], g["clamp_xdot_thr"][rows]) < tol
-    r = e.rollout(g["clamp_x"], g["clamp_u8"][None], dt=DT, integrator="euler", health=True, singular_eps=1e-6)
-    assert rel(cpu(r.xT)[rows], g["clamp_euler_thr"][rows]) < tol
-    w = B.Engine("wrench12", dtype)
-    assert rel(cpu(w.rhs(g["clamp_x"], g["clamp_tau"]))[rows], g["clamp_xdot_wrench"][rows]) < tol
-    rw = w.rollout(g["clamp_x"], g["clamp_tau"][None], dt=DT, integrator="euler")
-    assert rel(cpu(rw.xT)[rows], g["clamp_euler_wrench"][rows]) < tol
+    e, w = B.Engine("thruster8", dtype), B.Engine("wrench12", dtype)
+    x, u8, tau = g["clamp_x"], g["clamp_u8"], g["clamp_tau"]
+    want = {k: g[k] for k in ("clamp_xdot_thr", "clamp_euler_thr", "clamp_xdot_wrench", "clamp_euler_wrench")}
+    if dtype == "f32":
+        # float32 cannot hold pi/2 +- 5e-8: the rounded angles land on the other side of the singularity, so the fp32
+        # engine is compared with the oracle (pinned to the same golden rows in tests/test_oracle_r2_golden.py)
+        # evaluated at the float32-rounded states, where both see the same tiny cosines
+        x, u8, tau = (a.astype(np.float32).astype(np.float64) for a in (x, u8, tau))
+        m = O.Model("thruster8", DT)
+        want["clamp_xdot_thr"] = m.f(x, u8, m.zero_lag(len(x)))[0]
+        want["clamp_euler_thr"] = x + DT * want["clamp_xdot_thr"]
+        want["clamp_xdot_wrench"] = O.rhs_wrench12(x, tau, O.default_params())
+        want["clamp_euler_wrench"] = x + DT * want["clamp_xdot_wrench"]
+    assert rel(cpu(e.rhs(x, u8, dt=DT)), want["clamp_xdot_thr"]) < tol
+    r = e.rollout(x, u8[None], dt=DT, integrator="euler", health=True, singular_eps=1e-6)
+    assert rel(cpu(r.xT), want["clamp_euler_thr"]) < tol
+    assert rel(cpu(w.rhs(x, tau)), want["clamp_xdot_wrench"]) < tol
+    rw = w.rollout(x, tau[None], dt=DT, integrator="euler")
+    assert rel(cpu(rw.xT), want["clamp_euler_wrench"]) < tol
     if dtype == "f64":
         assert r.health.tolist() == [0, 7]          # every clamped row is reported, the control row is not
     # host helper (sign(0) = 0 is only reachable through the helper: no double has cos exactly 0)
@@ -393,7 +411,7 @@ def test_bench_call_every_vehicle_against_c_oracle(B, total_steps):
     # the engine's own singularity accounting agrees with the oracle's wherever the trajectories agree
     hc = r.health.cpu().numpy()
     good = err <= TOL64
-    assert np.max(np.abs(cpu(mc)[good] - mco[good])) < 1e-8 and hc[0] == 0
+    assert np.max(np.abs(cpu(mc)[good] - mco[good])) < 2e-7 and hc[0] == 0     # float32 health metric
     assert abs(int(hc[1]) - int((mco < EPS_COS).sum())) <= len(bad) + 2
     near = mco[bad] < EPS_COS
     rest = bad[~near]

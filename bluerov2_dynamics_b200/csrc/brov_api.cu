@@ -912,11 +912,23 @@ static int se_impl(brov_engine* e, const brov_se_desc* d, cudaStream_t st) {
     a.partial = (double*)d->workspace_dev;
     a.rows = (int)d->rows; a.nwin = (int)d->n_windows; a.nH = d->n_horizons;
     for (int h = 0; h < MAX_H; ++h) a.H[h] = h < d->n_horizons ? d->horizons[h] : 0x7fffffff;
-    a.carry_steps = 0; a.win0 = d->window0; a.row0 = d->row0;
+    a.carry_steps = 0; a.wpt = 1; a.win0 = d->window0; a.row0 = d->row0;
     if (d->lag_carry && e->model == BROV_THRUSTER8_LAG3) {
         long long m = 0;
         if ((rc = carry_depth(e, d->dt, d->integrator == BROV_RK4 ? 4 : 1, &m))) return rc;
         a.carry_steps = (int)m;
+        // windows per thread: the replay (m steps) is paid once per wpt windows of H steps each; more windows per
+        // thread mean fewer threads — pick the count that minimises rounds x steps per thread
+        {
+            const long long H = d->horizons[0];
+            const double slots = 2.0 * e->num_sms * ROLLOUT_BLOCK * (e->dtype == BROV_F32 ? 2.0 : 1.0);
+            double best = 1e300;
+            for (int w = 1; w <= 64; w *= 2) {
+                const double threads = std::ceil((double)d->n_windows / w);
+                const double cost = std::ceil(threads / slots) * (double)(w * H + m);
+                if (cost < best * 0.97) { best = cost; a.wpt = w; }
+            }
+        }
         // the replay of window0's history reads input rows back to window (window0 * H - m) / H: they must be local
         const long long H = d->horizons[0];
         const long long first_hist = d->window0 * H - m;

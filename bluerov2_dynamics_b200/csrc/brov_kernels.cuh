@@ -105,6 +105,10 @@ template <typename T> struct SeArgs {
     // holds after windows 0..k-1 (SURVEY trap T3).  The lag is a stable linear filter, so only the last carry_steps
     // integrator steps of that history are distinguishable from zero in floating point; each thread replays them.
     int carry_steps;      // 0 = off
+    // windows per thread.  Carried-lag mode: a thread that scores consecutive windows hands its lag from one to the
+    // next for free (the end of window k IS the start of window k+1 for the shared model object) and pays the replay
+    // once per wpt windows instead of once per window (49 replayed steps against H = 1 or 10 of its own).
+    int wpt;
     long long win0;       // global index of local window 0
     long long row0;       // global index of local row 0 of X / U
     Health health;        // windows with a non-finite endpoint error / that came within eps of the singularity
@@ -732,70 +736,83 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     constexpr int NL = LR::N;
     __shared__ double red[BLOCK / 32][MAX_H];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long gk = (long long)blockIdx.x * BLOCK + tid;
-    const bool live = gk < a.nwin;
-    const long long k = live ? gk : 0;
-    const long long kr = k + (a.win0 - a.row0);  // local row of the window's start (rows before it: carry history)
+    // a thread scores a.wpt consecutive windows (1 except in carried-lag mode, see SeArgs::wpt)
+    const long long gk = ((long long)blockIdx.x * BLOCK + tid) * a.wpt;
     ParamsConst<T> p;
     p.kp = a.c.kp;
-
-    T x[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + kr * NX + j);
-    T lag[NL];
-    load_lag<T, MODEL, false>(a.c, a.lag0, false, k, lag);
     const bool uvec = ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && (sizeof(T) * NU % 16 == 0);
-    if constexpr (MODEL == MODEL_THRUSTER8) {
-        if (a.carry_steps > 0 && live) {
-            // history of the shared model object: windows w = 0..kg-1, each feeding U[w..w+H-1]; replay its tail
-            const long long H0 = a.H[0];
-            const long long total = (a.win0 + k) * H0;
-            const long long m = total < a.carry_steps ? total : a.carry_steps;
-            for (long long s = total - m; s < total; ++s) {
-                const long long w = s / H0;
-                const long long row = w + (s - w * H0) - a.row0;
-                T u[NU], F[8], TF[6];
-                load_u<T, NU, false>(a.U + row * NU, uvec, u);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(u[i]);
-                allocate_wrench<T>(a.c, F, TF);
-                lag_advance<T, true>(a.c, lag, TF);
-            }
-        }
-    }
-
+    const int hmax = a.H[a.nH - 1];
     double se[MAX_H];
 #pragma unroll
     for (int h = 0; h < MAX_H; ++h) se[h] = 0.0;
-    const int hmax = a.H[a.nH - 1];
-    // window k may run j steps while row k + j exists
-    long long room = (long long)a.rows - 1 - kr;
-    const int nsteps = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
-    T mc = T(1);
-    bool bad = false;
-    for (int j = 0; j < nsteps; ++j) {
-        T u[NU];
-        load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
-        T acth;
-        NoSide side;
-        integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth, side);
-        mc = acth < mc ? acth : mc;
+    int n_bad = 0, n_sing = 0;
+    T lag[NL];
+    for (int c = 0; c < a.wpt; ++c) {
+        const long long k = gk + c;
+        if (k >= a.nwin) break;
+        const long long kr = k + (a.win0 - a.row0);  // local row of the window's start (rows before it: carry history)
+        T x[NX];
 #pragma unroll
-        for (int h = 0; h < MAX_H; ++h) {
-            if (h < a.nH && j + 1 == a.H[h]) {
-                const T* tgt = a.X + (kr + j + 1) * NX;
-                double s = 0.0;
+        for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + kr * NX + j);
+        if (c == 0) {
+            load_lag<T, MODEL, false>(a.c, a.lag0, false, k, lag);
+            if constexpr (MODEL == MODEL_THRUSTER8) {
+                if (a.carry_steps > 0) {
+                    // history of the shared model object: windows w = 0..kg-1, each feeding U[w..w+H-1]; replay its tail
+                    const long long H0 = a.H[0];
+                    const long long total = (a.win0 + k) * H0;
+                    const long long m = total < a.carry_steps ? total : a.carry_steps;
+                    for (long long s = total - m; s < total; ++s) {
+                        const long long w = s / H0;
+                        const long long row = w + (s - w * H0) - a.row0;
+                        T u[NU], F[8], TF[6];
+                        load_u<T, NU, false>(a.U + row * NU, uvec, u);
 #pragma unroll
-                for (int q = 0; q < NX; ++q) {
-                    double e = (double)x[q] - (double)__ldg(tgt + q);
-                    s += e * e;
+                        for (int i = 0; i < 8; ++i) F[i] = thrust_poly<T>(u[i]);
+                        allocate_wrench<T>(a.c, F, TF);
+                        lag_advance<T, true>(a.c, lag, TF);
+                    }
                 }
-                se[h] = s;
-                bad |= !(s <= 1.7976931348623157e308);
+            }
+        }   // c > 0: the lag this thread's previous window ended with IS the state the shared object hands to this one
+
+        // window k may run j steps while row k + j exists
+        long long room = (long long)a.rows - 1 - kr;
+        const int nsteps = (int)(room < hmax ? (room < 0 ? 0 : room) : hmax);
+        T mc = T(1);
+        bool bad = false;
+        for (int j = 0; j < nsteps; ++j) {
+            T u[NU];
+            load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
+            T acth;
+            NoSide side;
+            integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth, side);
+            mc = acth < mc ? acth : mc;
+#pragma unroll
+            for (int h = 0; h < MAX_H; ++h) {
+                if (h < a.nH && j + 1 == a.H[h]) {
+                    const T* tgt = a.X + (kr + j + 1) * NX;
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NX; ++q) {
+                        double e = (double)x[q] - (double)__ldg(tgt + q);
+                        s += e * e;
+                    }
+                    se[h] += s;
+                    bad |= !(s <= 1.7976931348623157e308);
+                }
             }
         }
+        n_bad += bad ? 1 : 0;
+        n_sing += ((double)mc < a.health.eps) ? 1 : 0;
     }
-    if (a.health.counters) count_health(a.health, live && bad, live && ((double)mc < a.health.eps), lane);
+    if (a.health.counters) {
+        const int tb = __reduce_add_sync(0xffffffffu, n_bad), ts = __reduce_add_sync(0xffffffffu, n_sing);
+        if (lane == 0) {
+            if (tb) atomicAdd(a.health.counters + 0, (unsigned long long)tb);
+            if (ts) atomicAdd(a.health.counters + 1, (unsigned long long)ts);
+        }
+    }
 #pragma unroll
     for (int h = 0; h < MAX_H; ++h) {
         double v = se[h];

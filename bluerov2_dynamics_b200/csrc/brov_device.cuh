@@ -588,7 +588,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float* __rest
     const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
     const float u1 = f1 - 0.99999994f;                                    // (0, 1]: never 0
     const float th = fmaf(f2, 6.2831855f, -6.2831855f);                   // 2 pi (f2 - 1)
-    const float r = sqrtf(-1.3862944f * __log2f(u1));                     // sqrt(-2 ln u1), ln = ln2 * log2
+    float r;                                                              // sqrt(-2 ln u1), ln = ln2 * log2
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862944f * __log2f(u1)));
     float s, c;
     __sincosf(th, &s, &c);
     *n0 = r * c;
@@ -637,45 +638,51 @@ __device__ __forceinline__ void gen_advance(const InputGen<T>& g, unsigned long 
     gen_apply<T, NU>(g, n, s);
 }
 
-// The deviates of the NEXT step, drawn in slices between the stages of the current step (integrate_step calls
-// work(0..3)): the Philox rounds are dependent integer multiplies and the Box-Muller transform is MUFU work — placed in
-// one lump at the top of the step they stall a warp that has only one other warp to hide behind (fp64: +30 % per step
-// measured, r02f); spread through the step they issue into the latency gaps of the FP pipes.
-template <typename T> struct GenSide {
+// The command signal of the NEXT step, produced in slices between the stages of the current step (integrate_step
+// calls work(0..3)): the Philox rounds are dependent integer multiplies and the Box-Muller transform is MUFU work —
+// placed in one lump at the top of the step they stall a warp that has only one other warp to hide behind (fp64: +30 %
+// per step measured, r02f); spread through the step they issue into the latency gaps of the FP pipes.  One counter
+// block (4 words -> 4 deviates -> 4 channels) at a time; the AR(1) state gs[] is advanced in place as soon as a block
+// is done — the current step converted it to inputs before its first stage and does not look at it again.
+template <typename T, int NU> struct GenSide {
     const InputGen<T>& g;
-    uint32_t c[8];        // two counter blocks in flight
-    float n[8];           // finished deviates
-    __device__ __forceinline__ GenSide(const InputGen<T>& g_) : g(g_) {}
-    __device__ __forceinline__ void start(unsigned long long veh, long long step) {
-        c[0] = c[4] = (uint32_t)veh;
-        c[1] = c[5] = (uint32_t)(veh >> 32);
-        c[2] = c[6] = (uint32_t)step;
-        c[3] = (uint32_t)((unsigned long long)step >> 32) << 1;
-        c[7] = c[3] | 1u;
+    float* gs;            // AR(1) state, NU channels: on entry to a step the state that step uses
+    uint32_t c[4];        // counter block in flight
+    uint32_t v0, v1, s0, s1;
+    bool advance;         // false on the last step of a launch: the state handed on is the last one USED
+    __device__ __forceinline__ GenSide(const InputGen<T>& g_, float* gs_) : g(g_), gs(gs_), advance(true) {}
+    __device__ __forceinline__ void start(unsigned long long veh, long long step, bool adv) {
+        v0 = (uint32_t)veh; v1 = (uint32_t)(veh >> 32);
+        s0 = (uint32_t)step; s1 = (uint32_t)((unsigned long long)step >> 32) << 1;
+        advance = adv;
     }
-    __device__ __forceinline__ void rounds(int r0, int r1) {
-        philox_rounds(c, g.k0, g.k1, r0, r1);
-        philox_rounds(c + 4, g.k0, g.k1, r0, r1);
-    }
-    __device__ __forceinline__ void finish() {
+    __device__ __forceinline__ void block(int b) { c[0] = v0; c[1] = v1; c[2] = s0; c[3] = s1 | (uint32_t)b; }
+    __device__ __forceinline__ void finish(int b) {
+        float n[4];
+        box_muller(c[0], c[1], &n[0], &n[1]);
+        box_muller(c[2], c[3], &n[2], &n[3]);
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) box_muller(c[j], c[j + 1], &n[j], &n[j + 1]);
+        for (int j = 0; j < 4; ++j) {
+            const int q = 4 * b + j;
+            if (q < NU) {
+                const float v = fminf(fmaxf(fmaf(g.rho, gs[q], g.sigma[q] * n[j]), -g.clip[q]), g.clip[q]);
+                gs[q] = advance ? v : gs[q];
+            }
+        }
     }
-    // slice s of 4 (RK4: one per stage); `all`: everything at once (Euler step)
+    // slice s of 4 (RK4: one per stage); all(): everything at once (Euler step, prologue)
     __device__ __forceinline__ void work(int s) {
         constexpr int R = BROV_PHILOX_ROUNDS;
-        // one counter block after the other (4 live words instead of 8): 5.37 against 5.65 ms per 1000 fp64 steps
-        // with both blocks in flight (profiles/r02k_tune_variants.txt)
-        if (s == 0) philox_rounds(c, g.k0, g.k1, 0, R / 2);
-        else if (s == 1) philox_rounds(c, g.k0, g.k1, R / 2, R);
-        else if (s == 2) philox_rounds(c + 4, g.k0, g.k1, 0, R / 2);
-        else { philox_rounds(c + 4, g.k0, g.k1, R / 2, R); finish(); }
+        if (s == 0) { block(0); philox_rounds(c, g.k0, g.k1, 0, R / 2); }
+        else if (s == 1) { philox_rounds(c, g.k0, g.k1, R / 2, R); finish(0); }
+        else if (s == 2) { block(1); philox_rounds(c, g.k0, g.k1, 0, R / 2); }
+        else { philox_rounds(c, g.k0, g.k1, R / 2, R); finish(1); }
     }
-    __device__ __forceinline__ void all() { rounds(0, BROV_PHILOX_ROUNDS); finish(); }
+    __device__ __forceinline__ void all() { work(0); work(1); work(2); work(3); }
 };
 struct NoSide {
     __device__ __forceinline__ NoSide() {}
-    template <class G> __device__ __forceinline__ explicit NoSide(const G&) {}
+    template <class G> __device__ __forceinline__ NoSide(const G&, float*) {}
     __device__ __forceinline__ void work(int) {}
     __device__ __forceinline__ void all() {}
 };

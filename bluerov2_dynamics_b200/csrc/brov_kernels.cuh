@@ -423,20 +423,25 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const unsigned long long veh = a.gen.vehicle0 + (unsigned long long)i;
     int countdown = a.traj ? (int)(a.stride - (gstep0 % a.stride)) : 0x7fffffff;
     long long snap = a.traj ? (gstep0 / a.stride - a.snap_base) : 0;
-    typename std::conditional<GEN, GenSide<T>, NoSide>::type side{a.gen};
-    if constexpr (GEN) { side.start(veh, gstep0); side.all(); }
+    // generated inputs: gs enters every step as the state that step uses; the prologue advances the state handed in
+    // (the one before the first step) once, the steps advance it for their successors (GenSide)
+    float gs_dummy[1];
+    typename std::conditional<GEN, GenSide<T, NU>, NoSide>::type side{a.gen, GEN ? gs : gs_dummy};
+    if constexpr (GEN) {
+        if (nsteps > 0) { side.start(veh, gstep0, true); side.all(); }
+    }
 
     for (int k = 0; k < nsteps; ++k) {
         T un[PREFETCH ? NU : 1];
         if constexpr (GEN) {
-            if (a.gen_snap && k_begin + k == a.gen_snap_step && live) {
+            // the state BEFORE step gen_snap_step is the one this step uses when it is that step's predecessor
+            if (a.gen_snap && k_begin + k + 1 == a.gen_snap_step && live) {
 #pragma unroll
                 for (int j = 0; j < NU; ++j) a.gen_snap[i * NU + j] = T(gs[j]);
             }
-            gen_apply<T, NU>(a.gen, side.n, gs);
-            side.start(veh, gstep0 + k + 1);
 #pragma unroll
             for (int j = 0; j < NU; ++j) u[j] = T(gs[j]);
+            side.start(veh, gstep0 + k + 1, k + 1 < nsteps);
         } else if constexpr (TMA) {
             if (tma) {
                 // refill the slot read one step ago (every lane has executed those reads: they precede the last step)

@@ -36,6 +36,11 @@ class KoopmanEDMDc:
             raise RuntimeError("bluerov2_dynamics_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         if self.centers_ is None:
             raise RuntimeError("model has no centres: call fit() or set centers_ / A_ / B_")
+        if need_model and hasattr(self, "decoder_"):
+            # the reference's _lift_inverse honours a user-attached decoder_ (Koopman/koopmanEDMDc.py:238-246); the
+            # kernels decode with the first n lifted coordinates only — refuse rather than score a different model
+            raise NotImplementedError("a user-attached decoder_ is not supported by the B200 kernels (they decode with "
+                                      "the first state_dim lifted coordinates, as the reference does without decoder_)")
         n, k = self.state_dim, int(np.shape(self.centers_)[0])
         d = n + k
         if self.A_ is None or self.B_ is None:

@@ -74,6 +74,10 @@ class BlueROV2(FossenModelBase):
         z = V * V
         return V * (8.9 + z * (176.0 + z * (-404.1 + z * (389.9 - 140.3 * z))))
 
+    def _thruster_force_from_input(self, V, i, dt):
+        """Static T200 curve, then ONE step of thruster i's lag (stateful), fossen/BlueROV2.py:245-263."""
+        return float(self.thruster_lags[i].step(self._old_thruster_force_from_input(V), dt))
+
     # --- hidden lag state <-> device ---------------------------------------------------------------------------
     def _lag_tensor(self, eng):
         flat = np.concatenate([np.asarray(l._x, float).reshape(3) for l in self.thruster_lags])

@@ -76,6 +76,39 @@ class FossenModelBase:
             eng._pushed = p
         return eng
 
+    # --- the reference's private term helpers, for callers that poke at them (fossen/BlueROV2.py:280-355 and the twins
+    # in BlueROV2_thrust.py:150-230, BlueROV2_wrench.py:228-319).  Host numpy on the live attributes: they are not on
+    # the accelerated path (the kernels evaluate C(nu) nu, D(nu_r) nu_r and g(eta) in closed form), they keep the
+    # attribute surface whole.
+    @staticmethod
+    def _skew(a):
+        return np.array([[0.0, -a[2], a[1]], [a[2], 0.0, -a[0]], [-a[1], a[0], 0.0]])
+
+    def _coriolis(self, nu):
+        """C(nu) = C_RB + C_A for a diagonal mass matrix and CG at the origin (Fossen 2011, eqs. 3.60 / 6.43):
+        [[0, -S(M11 v1)], [-S(M11 v1), -S(M22 v2)]] with M = M_RB + M_A."""
+        nu = np.asarray(nu, float).reshape(6)
+        m11 = np.array([self.m - self.Xu_dot, self.m - self.Yv_dot, self.m - self.Zw_dot])
+        m22 = np.array([self.Ix - self.Kp_dot, self.Iy - self.Mq_dot, self.Iz - self.Nr_dot])
+        C = np.zeros((6, 6))
+        C[0:3, 3:6] = C[3:6, 0:3] = -self._skew(m11 * nu[0:3])
+        C[3:6, 3:6] = -self._skew(m22 * nu[3:6])
+        return C
+
+    def _damping(self, nu_r):
+        """D(nu_r) = diag(-L_i - Q_i |nu_r,i|): linear + quadratic damping on the relative velocity."""
+        nu_r = np.asarray(nu_r, float).reshape(6)
+        lin = np.array([getattr(self, n) for n in _LIN])
+        quad = np.array([getattr(self, n) for n in _QUAD])
+        return np.diag(-lin - quad * np.abs(nu_r))
+
+    def _restoring(self, phi, theta, psi=0.0):
+        """g(eta) for CG at the origin and centre of buoyancy (xb, yb, zb)."""
+        sph, cph, sth, cth = np.sin(phi), np.cos(phi), np.sin(theta), np.cos(theta)
+        wb, bx, by, bz = self.W - self.B, self.xb * self.B, self.yb * self.B, self.zb * self.B
+        return np.array([wb * sth, -wb * cth * sph, -wb * cth * cph,
+                         by * cth * cph - bz * cth * sph, -bz * sth - bx * cth * cph, bx * cth * sph + by * sth])
+
     def _dynamics_one(self, x, u, nx, nu, dt, lag=None):
         """One dynamics() call through the host-buffer entry point (brov_rhs_host); `lag` is a numpy [1,24] array that
         is advanced in place."""

@@ -126,7 +126,7 @@ class PincModel:
 
     @classmethod
     def from_checkpoint(cls, path, device: Optional[int] = None) -> "PincModel":
-        return cls(torch.load(path, map_location="cpu"), device)
+        return cls(torch.load(path, map_location="cpu", weights_only=True), device)   # a plain state_dict of tensors
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -55,3 +55,25 @@ def test_endpoint_rmse_against_live_reference():
         want = R.multistep_rmse_endpoint_physics(X, U, H, DT)
         got = O.multistep_se(m, "rk4", X, U, [H], lag_mode="carry")[H][2]
         assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), (H, got, want)
+
+
+def test_mirror_private_helpers_against_live_reference():
+    """_coriolis / _damping / _restoring of the model mirrors (host numpy, attribute surface only) against the
+    reference's own methods (fossen/BlueROV2.py:280-355), including after an attribute edit."""
+    import bluerov2_dynamics_b200.fossen._base as Bm
+    R = RL.load()
+
+    class M(Bm.FossenModelBase):
+        pass
+    m = M()
+    m._init_constants(1000.0, None)
+    ref = R.BlueROV2()
+    rng = np.random.default_rng(5)
+    for obj in (m, ref):
+        obj.Xu_dot, obj.Nr_abs, obj.zb = -7.5, -2.0, -0.02
+    for _ in range(5):
+        nu = rng.normal(size=6)
+        assert np.array_equal(m._coriolis(nu), ref._coriolis(nu)) or np.allclose(m._coriolis(nu), ref._coriolis(nu), rtol=1e-15)
+        assert np.allclose(m._damping(nu), ref._damping(nu), rtol=1e-15)
+        a = rng.uniform(-1, 1, 3)
+        assert np.allclose(m._restoring(*a), ref._restoring(*a), rtol=1e-15, atol=1e-18)

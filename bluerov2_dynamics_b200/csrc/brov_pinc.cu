@@ -16,6 +16,7 @@
 // float64 on the four allocation-projected lag filters the network input needs (rows X, Y, Z, Mz of the allocation
 // matrix: 12 hidden values instead of the reference's 24), exactly one lag step per rollout step like the reference.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -513,6 +514,133 @@ __global__ void __launch_bounds__(256) pinc_finish_kernel(const double* __restri
     }
 }
 
+#include "brov_pinc_tc.cuh"
+
+// PINcNet.forward on the tensor cores: persistent CTAs of two 128-thread tiles, one input row per thread and tile
+__global__ void __launch_bounds__(TC_TILES * TC_M, 1) pinc_forward_tc_kernel(const float* __restrict__ wtc, const float4 beta4,
+                                                                             const float* __restrict__ Zin,
+                                                                             float* __restrict__ out, long long n) {
+    extern __shared__ __align__(1024) float smf[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bars[TC_TILES];
+    TcCtx c;
+    tc_setup(c, smf, wtc, &tmem_slot, bars);
+    const float beta[4] = {beta4.x, beta4.y, beta4.z, beta4.w};
+    const long long ntiles = (n + TC_M - 1) / TC_M;
+    for (long long tile = (long long)blockIdx.x * TC_TILES + c.half; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
+        const long long gi = tile * TC_M + c.row;
+        const long long i = gi < n ? gi : n - 1;
+        float z[NIN], xn[9];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
+        pinc_forward_tc(c, beta, z, xn);
+        if (gi < n) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
+        }
+    }
+    tc_teardown(c, &tmem_slot);
+}
+
+// multistep_rmse_endpoint_pinc on the tensor cores: one window per thread, 128 windows per tile, persistent CTAs
+__global__ void __launch_bounds__(TC_TILES * TC_M, 1) pinc_se_tc_kernel(const __grid_constant__ PincSeArgs a,
+                                                                        const float* __restrict__ wtc) {
+    extern __shared__ __align__(1024) float smf[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t bars[TC_TILES];
+    __shared__ double red[TC_TILES * TC_M / 32][BROV_MAX_H];
+    TcCtx c;
+    tc_setup(c, smf, wtc, &tmem_slot, bars);
+    double se[BROV_MAX_H];
+#pragma unroll
+    for (int h = 0; h < BROV_MAX_H; ++h) se[h] = 0.0;
+    const int hmax = a.H[a.nH - 1];
+    const long long ntiles = (a.nwin + TC_M - 1) / TC_M;
+    // the CTA's two tiles walk the tile list independently (tile-wide barriers only inside the loop)
+    for (long long tile = (long long)blockIdx.x * TC_TILES + c.half; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
+        const long long gk = tile * TC_M + c.row;
+        const bool live = gk < a.nwin;
+        const long long k = live ? gk : a.nwin - 1;     // dead slots shadow the last window and score nothing
+        const long long kr = k + (a.win0 - a.row0);
+        const long long room = a.rows - 1 - kr;
+        const int nst = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
+        float z[NIN], xn[9];
+        double Z[12];
+        {
+            double x12[12];
+#pragma unroll
+            for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr * 12 + j);
+            x12_to_9(x12, z);
+        }
+        z[13] = (float)a.m.dt;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
+        if (a.carry_steps > 0 && live) {
+            const long long H0 = a.H[0];
+            const long long total = (a.win0 + k) * H0;
+            const long long m = total < a.carry_steps ? total : a.carry_steps;
+            if (a.carry_lag0 && total <= a.carry_steps) {
+                double l24[24];
+#pragma unroll
+                for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
+                project4(a.m, l24, Z);
+            }
+            for (long long s = total - m; s < total; ++s) {
+                const long long ww = s / H0;
+                const long long row = ww + (s - ww * H0) - a.row0;
+                double u8[8], u4[4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
+                thruster_map4(a.m, u8, Z, u4);
+            }
+        }
+        for (int j = 0; j < hmax; ++j) {     // uniform trip count: the forward pass holds block-wide barriers
+            // a window that has run out of rows keeps stepping on its last valid input row; its results are ignored
+            const long long row = kr + (j < nst ? j : (nst > 0 ? nst - 1 : 0));
+            double u8[8], u4[4];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) u8[q] = __ldg(a.U + row * 8 + q);
+            thruster_map4(a.m, u8, Z, u4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[9 + q] = (float)u4[q];
+            pinc_forward_tc(c, a.p.beta, z, xn);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) z[q] = xn[q];
+#pragma unroll
+            for (int h = 0; h < BROV_MAX_H; ++h) {
+                if (h < a.nH && j + 1 == a.H[h] && j < nst) {
+                    double x12[12];
+                    x9_to_12(xn, x12);
+                    const double* tgt = a.X + (kr + j + 1) * 12;
+                    double s = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) {
+                        const double e = x12[q] - __ldg(tgt + q);
+                        s += e * e;
+                    }
+                    se[h] += s;
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int h = 0; h < BROV_MAX_H; ++h) {
+        double v = se[h];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) red[warp][h] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < BROV_MAX_H) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < TC_TILES * TC_M / 32; ++w) v += red[w][threadIdx.x];
+        a.partial[(long long)blockIdx.x * BROV_MAX_H + threadIdx.x] = v;
+    }
+    tc_teardown(c, &tmem_slot);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -520,6 +648,9 @@ __global__ void __launch_bounds__(256) pinc_finish_kernel(const double* __restri
 // ---------------------------------------------------------------------------------------------------------------
 struct brov_pinc {
     int device;
+    int num_sms;
+    bool use_tc;     // dense layers on the tensor cores (default; BROV_PINC_TC=0 selects the CUDA-core kernels)
+    float* wtc;      // tensor-core blob (TC_NW floats): hi / lo TF32 parts of every layer in UMMA core-matrix layout
     float* w;        // packed blob on the device
     float beta[4];
     ThrMap m;
@@ -534,6 +665,8 @@ static int pinc_attrs(brov_pinc* h) {
     BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES2));
     BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_se_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES2));
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+    BROV_CUDA_TRY(cudaFuncSetAttribute(pinc_se_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
     h->attr_set = true;
     return BROV_OK;
 }
@@ -576,12 +709,50 @@ extern "C" int brov_pinc_create(int device, const brov_pinc_weights* wts, brov_p
     for (int j = 0; j < 9; ++j) blob[OFF_B4 + j] = wts->b[4][j];
     memset(h, 0, sizeof(*h));
     h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    {
+        const char* env = getenv("BROV_PINC_TC");
+        h->use_tc = !(env && env[0] == '0');
+    }
     for (int l = 0; l < 4; ++l) h->beta[l] = wts->beta[l];
+    // tensor-core blob: every weight split into two TF32 numbers (round to nearest), W[n][k] at tc_off(rows, n, k)
+    float* tcb = new (std::nothrow) float[TC_NW];
+    if (!tcb) { delete[] blob; delete h; return brov::fail_msg(BROV_ENOMEM, "out of host memory"); }
+    memset(tcb, 0, TC_NW * sizeof(float));
+    auto rna = [](float x) {
+        uint32_t b;
+        memcpy(&b, &x, 4);
+        if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0x1000u) & 0xffffe000u;
+        float r;
+        memcpy(&r, &b, 4);
+        return r;
+    };
+    auto put = [&](int hi_off, int lo_off, int rows, int n, int k, float w) {
+        const float hi = rna(w);
+        tcb[hi_off + tc_off(rows, n, k)] = hi;
+        tcb[lo_off + tc_off(rows, n, k)] = rna(w - hi);
+    };
+    for (int n = 0; n < HID; ++n) for (int k = 0; k < NIN; ++k) put(TC_L0_HI, TC_L0_LO, HID, n, k, wts->W[0][n * NIN + k]);
+    for (int l = 1; l <= 3; ++l)
+        for (int n = 0; n < HID; ++n) for (int k = 0; k < HID; ++k)
+            put(TC_L1 + (l - 1) * 8192, TC_L1 + (l - 1) * 8192 + 4096, HID, n, k, wts->W[l][n * HID + k]);
+    for (int n = 0; n < 9; ++n) for (int k = 0; k < HID; ++k) put(TC_L4_HI, TC_L4_LO, 16, n, k, wts->W[4][n * HID + k]);
+    for (int l = 0; l < 4; ++l)
+        for (int j = 0; j < HID; ++j) {
+            tcb[TC_PAR + l * 192 + j] = wts->b[l][j];
+            tcb[TC_PAR + l * 192 + 64 + j] = wts->ln_w[l][j];
+            tcb[TC_PAR + l * 192 + 128 + j] = wts->ln_b[l][j];
+        }
+    for (int j = 0; j < 9; ++j) tcb[TC_PAR + 4 * 192 + j] = wts->b[4][j];
     cudaError_t e = cudaMalloc(&h->w, NW * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->w, blob, NW * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->wtc, TC_NW * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->wtc, tcb, TC_NW * sizeof(float), cudaMemcpyHostToDevice);
     delete[] blob;
+    delete[] tcb;
     if (e != cudaSuccess) {
         cudaFree(h->w);
+        cudaFree(h->wtc);
         delete h;
         return brov::fail_msg(BROV_ECUDA, "brov_pinc_create: %s", cudaGetErrorString(e));
     }
@@ -593,6 +764,7 @@ extern "C" void brov_pinc_destroy(brov_pinc_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->w);
+    cudaFree(h->wtc);
     cudaFree(h->partial);
     delete h;
 }
@@ -626,7 +798,14 @@ extern "C" int brov_pinc_forward(brov_pinc_t* h, const float* z_dev, float* out_
     PincParams p;
     p.w = h->w;
     memcpy(p.beta, h->beta, sizeof(p.beta));
-    pinc_forward_kernel<<<(unsigned)((n + PB - 1) / PB), PB, SMEM_BYTES, (cudaStream_t)stream>>>(p, z_dev, out_dev, n);
+    if (h->use_tc) {
+        const long long ctas = ((n + TC_M - 1) / TC_M + TC_TILES - 1) / TC_TILES;
+        const unsigned grid = (unsigned)(ctas < h->num_sms ? ctas : h->num_sms);
+        pinc_forward_tc_kernel<<<grid, TC_TILES * TC_M, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
+            h->wtc, make_float4(h->beta[0], h->beta[1], h->beta[2], h->beta[3]), z_dev, out_dev, n);
+    } else {
+        pinc_forward_kernel<<<(unsigned)((n + PB - 1) / PB), PB, SMEM_BYTES, (cudaStream_t)stream>>>(p, z_dev, out_dev, n);
+    }
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;
 }
@@ -687,7 +866,9 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     }
     int rc = pinc_attrs(h);
     if (rc) return rc;
-    const size_t nblocks = (size_t)((d->n_windows + NWIN * PB2 - 1) / (NWIN * PB2));
+    const size_t tiles = ((size_t)((d->n_windows + TC_M - 1) / TC_M) + TC_TILES - 1) / TC_TILES;   // CTAs of TC_TILES tiles
+    const size_t nblocks = h->use_tc ? (tiles < (size_t)h->num_sms ? tiles : (size_t)h->num_sms)
+                                     : (size_t)((d->n_windows + NWIN * PB2 - 1) / (NWIN * PB2));
     if (nblocks * BROV_MAX_H > h->cap_partial) {
         cudaFree(h->partial);
         h->partial = nullptr; h->cap_partial = 0;
@@ -703,7 +884,8 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     for (int q = 0; q < BROV_MAX_H; ++q) a.H[q] = q < d->n_horizons ? d->horizons[q] : 0x7fffffff;
     a.carry_steps = d->carry_steps; a.win0 = d->window0; a.row0 = d->row0;
     a.carry_lag0 = (const double*)d->carry_lag0_dev;
-    pinc_se_kernel<<<(unsigned)nblocks, PB2, SMEM_BYTES2, st>>>(a);
+    if (h->use_tc) pinc_se_tc_kernel<<<(unsigned)nblocks, TC_TILES * TC_M, TC_SMEM_BYTES, st>>>(a, h->wtc);
+    else pinc_se_kernel<<<(unsigned)nblocks, PB2, SMEM_BYTES2, st>>>(a);
     pinc_finish_kernel<<<1, 256, 0, st>>>(h->partial, (int)nblocks, d->se_out_dev);
     BROV_CUDA_TRY(cudaGetLastError());
     return BROV_OK;

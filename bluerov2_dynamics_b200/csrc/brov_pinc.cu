@@ -516,109 +516,134 @@ __global__ void __launch_bounds__(256) pinc_finish_kernel(const double* __restri
 
 #include "brov_pinc_tc.cuh"
 
-// PINcNet.forward on the tensor cores: persistent CTAs of two 128-thread tiles, one input row per thread and tile
-__global__ void __launch_bounds__(TC_TILES * TC_M, 1) pinc_forward_tc_kernel(const float* __restrict__ wtc, const float4 beta4,
-                                                                             const float* __restrict__ Zin,
-                                                                             float* __restrict__ out, long long n) {
+// PINcNet.forward on the tensor cores: persistent CTAs of two tiles, 128 input rows per tile, two threads per row
+__global__ void __launch_bounds__(TC_THREADS, 1) pinc_forward_tc_kernel(const float* __restrict__ wtc, const __grid_constant__ TcAct act,
+                                                                         const float* __restrict__ Zin,
+                                                                         float* __restrict__ out, long long n) {
     extern __shared__ __align__(1024) float smf[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[TC_TILES];
+    __shared__ float2 xch[TC_TILES * 2 * TC_M];
     TcCtx c;
-    tc_setup(c, smf, wtc, &tmem_slot, bars);
-    const float beta[4] = {beta4.x, beta4.y, beta4.z, beta4.w};
+    tc_setup(c, smf, wtc, &tmem_slot, bars, xch);
     const long long ntiles = (n + TC_M - 1) / TC_M;
-    for (long long tile = (long long)blockIdx.x * TC_TILES + c.half; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
+    for (long long tile = (long long)blockIdx.x * TC_TILES + c.tile; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
         const long long gi = tile * TC_M + c.row;
         const long long i = gi < n ? gi : n - 1;
         float z[NIN], xn[9];
+        if (c.part == 0) {
 #pragma unroll
-        for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
-        pinc_forward_tc(c, beta, z, xn);
-        if (gi < n) {
+            for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
+            tc_put_state(c, z, z[13]);
+            tc_put_thrust(c, z + 9);
+        }
+        pinc_net_tc(c, act);
+        tc_layer_wait(c);
+        if (c.part == 0) {
+            tc_residual(c, z, xn);
+            if (gi < n) {
 #pragma unroll
-            for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
+                for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
+            }
         }
     }
     tc_teardown(c, &tmem_slot);
 }
 
-// multistep_rmse_endpoint_pinc on the tensor cores: one window per thread, 128 windows per tile, persistent CTAs
-__global__ void __launch_bounds__(TC_TILES * TC_M, 1) pinc_se_tc_kernel(const __grid_constant__ PincSeArgs a,
-                                                                        const float* __restrict__ wtc) {
+// multistep_rmse_endpoint_pinc on the tensor cores: a tile = 128 consecutive windows stepped together through the
+// longest horizon.  The row's leader thread carries the network state and scores the endpoints; its helper carries
+// the projected lag states and evaluates the thruster map of the next step under the output layer's MMAs.
+__global__ void __launch_bounds__(TC_THREADS, 1) pinc_se_tc_kernel(const __grid_constant__ PincSeArgs a,
+                                                                    const float* __restrict__ wtc,
+                                                                    const __grid_constant__ TcAct act) {
     extern __shared__ __align__(1024) float smf[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[TC_TILES];
-    __shared__ double red[TC_TILES * TC_M / 32][BROV_MAX_H];
+    __shared__ float2 xch[TC_TILES * 2 * TC_M];
+    __shared__ double red[TC_THREADS / 32][BROV_MAX_H];
     TcCtx c;
-    tc_setup(c, smf, wtc, &tmem_slot, bars);
+    tc_setup(c, smf, wtc, &tmem_slot, bars, xch);
     double se[BROV_MAX_H];
 #pragma unroll
     for (int h = 0; h < BROV_MAX_H; ++h) se[h] = 0.0;
     const int hmax = a.H[a.nH - 1];
+    const float dtf = (float)a.m.dt;
     const long long ntiles = (a.nwin + TC_M - 1) / TC_M;
     // the CTA's two tiles walk the tile list independently (tile-wide barriers only inside the loop)
-    for (long long tile = (long long)blockIdx.x * TC_TILES + c.half; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
+    for (long long tile = (long long)blockIdx.x * TC_TILES + c.tile; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
         const long long gk = tile * TC_M + c.row;
         const bool live = gk < a.nwin;
         const long long k = live ? gk : a.nwin - 1;     // dead slots shadow the last window and score nothing
         const long long kr = k + (a.win0 - a.row0);
         const long long room = a.rows - 1 - kr;
         const int nst = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
-        float z[NIN], xn[9];
+        float z[9];
         double Z[12];
-        {
-            double x12[12];
-#pragma unroll
-            for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr * 12 + j);
-            x12_to_9(x12, z);
-        }
-        z[13] = (float)a.m.dt;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
-        if (a.carry_steps > 0 && live) {
-            const long long H0 = a.H[0];
-            const long long total = (a.win0 + k) * H0;
-            const long long m = total < a.carry_steps ? total : a.carry_steps;
-            if (a.carry_lag0 && total <= a.carry_steps) {
-                double l24[24];
-#pragma unroll
-                for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
-                project4(a.m, l24, Z);
-            }
-            for (long long s = total - m; s < total; ++s) {
-                const long long ww = s / H0;
-                const long long row = ww + (s - ww * H0) - a.row0;
-                double u8[8], u4[4];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
-                thruster_map4(a.m, u8, Z, u4);
-            }
-        }
-        for (int j = 0; j < hmax; ++j) {     // uniform trip count: the forward pass holds block-wide barriers
-            // a window that has run out of rows keeps stepping on its last valid input row; its results are ignored
+        float u4f[4];
+        // a window that has run out of rows keeps stepping on its last valid input row; its results are ignored
+        auto thrust = [&](int j) {
             const long long row = kr + (j < nst ? j : (nst > 0 ? nst - 1 : 0));
             double u8[8], u4[4];
 #pragma unroll
             for (int q = 0; q < 8; ++q) u8[q] = __ldg(a.U + row * 8 + q);
             thruster_map4(a.m, u8, Z, u4);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) z[9 + q] = (float)u4[q];
-            pinc_forward_tc(c, a.p.beta, z, xn);
+            for (int q = 0; q < 4; ++q) u4f[q] = (float)u4[q];
+        };
+        if (c.part == 0) {
+            double x12[12];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) z[q] = xn[q];
+            for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr * 12 + j);
+            x12_to_9(x12, z);
+        } else {
 #pragma unroll
-            for (int h = 0; h < BROV_MAX_H; ++h) {
-                if (h < a.nH && j + 1 == a.H[h] && j < nst) {
-                    double x12[12];
-                    x9_to_12(xn, x12);
-                    const double* tgt = a.X + (kr + j + 1) * 12;
-                    double s = 0.0;
+            for (int j = 0; j < 12; ++j) Z[j] = 0.0;
+            if (a.carry_steps > 0 && live) {
+                const long long H0 = a.H[0];
+                const long long total = (a.win0 + k) * H0;
+                const long long m = total < a.carry_steps ? total : a.carry_steps;
+                if (a.carry_lag0 && total <= a.carry_steps) {
+                    double l24[24];
 #pragma unroll
-                    for (int q = 0; q < 12; ++q) {
-                        const double e = x12[q] - __ldg(tgt + q);
-                        s += e * e;
+                    for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
+                    project4(a.m, l24, Z);
+                }
+                for (long long s = total - m; s < total; ++s) {
+                    const long long ww = s / H0;
+                    const long long row = ww + (s - ww * H0) - a.row0;
+                    double u8[8], u4[4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
+                    thruster_map4(a.m, u8, Z, u4);
+                }
+            }
+            thrust(0);
+        }
+        for (int j = 0; j < hmax; ++j) {     // uniform trip count: the network holds tile-wide barriers
+            if (c.part == 0) tc_put_state(c, z, dtf);
+            else tc_put_thrust(c, u4f);
+            pinc_net_tc(c, act);
+            if (c.part == 1 && j + 1 < hmax) thrust(j + 1);       // under the output layer's MMAs
+            tc_layer_wait(c);
+            if (c.part == 0) {
+                float xn[9];
+                tc_residual(c, z, xn);
+#pragma unroll
+                for (int q = 0; q < 9; ++q) z[q] = xn[q];
+#pragma unroll
+                for (int h = 0; h < BROV_MAX_H; ++h) {
+                    if (h < a.nH && j + 1 == a.H[h] && j < nst) {
+                        double x12[12];
+                        x9_to_12(xn, x12);
+                        const double* tgt = a.X + (kr + j + 1) * 12;
+                        double s = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) {
+                            const double e = x12[q] - __ldg(tgt + q);
+                            s += e * e;
+                        }
+                        se[h] += s;
                     }
-                    se[h] += s;
                 }
             }
         }
@@ -635,7 +660,7 @@ __global__ void __launch_bounds__(TC_TILES * TC_M, 1) pinc_se_tc_kernel(const __
     if (threadIdx.x < BROV_MAX_H) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < TC_TILES * TC_M / 32; ++w) v += red[w][threadIdx.x];
+        for (int w = 0; w < TC_THREADS / 32; ++w) v += red[w][threadIdx.x];
         a.partial[(long long)blockIdx.x * BROV_MAX_H + threadIdx.x] = v;
     }
     tc_teardown(c, &tmem_slot);
@@ -650,6 +675,7 @@ struct brov_pinc {
     int device;
     int num_sms;
     bool use_tc;     // dense layers on the tensor cores (default; BROV_PINC_TC=0 selects the CUDA-core kernels)
+    TcAct act;       // folded activation / LayerNorm scalars of the tensor-core path
     float* wtc;      // tensor-core blob (TC_NW floats): hi / lo TF32 parts of every layer in UMMA core-matrix layout
     float* w;        // packed blob on the device
     float beta[4];
@@ -727,23 +753,42 @@ extern "C" int brov_pinc_create(int device, const brov_pinc_weights* wts, brov_p
         memcpy(&r, &b, 4);
         return r;
     };
-    auto put = [&](int hi_off, int lo_off, int rows, int n, int k, float w) {
-        const float hi = rna(w);
+    // x (double) -> two TF32 numbers, x = hi + lo to 2^-22 relative
+    auto put = [&](int hi_off, int lo_off, int rows, int n, int k, double w) {
+        const float hi = rna((float)w);
         tcb[hi_off + tc_off(rows, n, k)] = hi;
-        tcb[lo_off + tc_off(rows, n, k)] = rna(w - hi);
+        tcb[lo_off + tc_off(rows, n, k)] = rna((float)(w - (double)hi));
     };
-    for (int n = 0; n < HID; ++n) for (int k = 0; k < NIN; ++k) put(TC_L0_HI, TC_L0_LO, HID, n, k, wts->W[0][n * NIN + k]);
-    for (int l = 1; l <= 3; ++l)
-        for (int n = 0; n < HID; ++n) for (int k = 0; k < HID; ++k)
-            put(TC_L1 + (l - 1) * 8192, TC_L1 + (l - 1) * 8192 + 4096, HID, n, k, wts->W[l][n * HID + k]);
-    for (int n = 0; n < 9; ++n) for (int k = 0; k < HID; ++k) put(TC_L4_HI, TC_L4_LO, 16, n, k, wts->W[4][n * HID + k]);
-    for (int l = 0; l < 4; ++l)
-        for (int j = 0; j < HID; ++j) {
-            tcb[TC_PAR + l * 192 + j] = wts->b[l][j];
-            tcb[TC_PAR + l * 192 + 64 + j] = wts->ln_w[l][j];
-            tcb[TC_PAR + l * 192 + 128 + j] = wts->ln_b[l][j];
+    // Folds (double precision): LayerNorm l's affine into layer l + 1 (W' = W diag(ln_w), b' = b + W ln_b); the
+    // activation's input scale beta log2(e) into the hidden layers' biases; its output scale ln 2 / (beta + 1e-12) into
+    // LayerNorm's epsilon (see brov_pinc_tc.cuh).
+    const double LOG2E = 1.4426950408889634, LN2 = 0.6931471805599453;
+    for (int l = 0; l < 4; ++l) {
+        const double kappa = LN2 / ((double)wts->beta[l] + 1e-12);
+        h->act.sc[l] = (float)((double)wts->beta[l] * LOG2E);
+        h->act.eps[l] = (float)(1e-5 / (kappa * kappa));
+        h->act.sg[l] = kappa < 0.0 ? -1.0f : 1.0f;
+    }
+    for (int l = 0; l <= 4; ++l) {
+        const int K = l == 0 ? NIN : HID, N = l == 4 ? 9 : HID;
+        const int hi_off = l == 0 ? TC_L0_HI : (l == 4 ? TC_L4_HI : TC_L1 + (l - 1) * 8192);
+        const int lo_off = l == 0 ? TC_L0_LO : (l == 4 ? TC_L4_LO : TC_L1 + (l - 1) * 8192 + 4096);
+        const int rows = l == 4 ? 16 : HID;
+        for (int n = 0; n < N; ++n) {
+            double bias = wts->b[l][n];
+            if (l == 0) {
+                for (int k = 0; k < 16; ++k)       // layer 0's K axis in the order the kernels store it (tc_kmap0)
+                    if (tc_kmap0(k) >= 0) put(hi_off, lo_off, rows, n, k, wts->W[0][n * NIN + tc_kmap0(k)]);
+            } else {
+                for (int k = 0; k < K; ++k) {
+                    const double w = wts->W[l][n * K + k];
+                    put(hi_off, lo_off, rows, n, k, w * (double)wts->ln_w[l - 1][k]);
+                    bias += w * (double)wts->ln_b[l - 1][k];
+                }
+            }
+            tcb[TC_PAR + l * 64 + n] = (float)(l < 4 ? bias * (double)wts->beta[l] * LOG2E : bias);
         }
-    for (int j = 0; j < 9; ++j) tcb[TC_PAR + 4 * 192 + j] = wts->b[4][j];
+    }
     cudaError_t e = cudaMalloc(&h->w, NW * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(h->w, blob, NW * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&h->wtc, TC_NW * sizeof(float));
@@ -801,8 +846,8 @@ extern "C" int brov_pinc_forward(brov_pinc_t* h, const float* z_dev, float* out_
     if (h->use_tc) {
         const long long ctas = ((n + TC_M - 1) / TC_M + TC_TILES - 1) / TC_TILES;
         const unsigned grid = (unsigned)(ctas < h->num_sms ? ctas : h->num_sms);
-        pinc_forward_tc_kernel<<<grid, TC_TILES * TC_M, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
-            h->wtc, make_float4(h->beta[0], h->beta[1], h->beta[2], h->beta[3]), z_dev, out_dev, n);
+        pinc_forward_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
+            h->wtc, h->act, z_dev, out_dev, n);
     } else {
         pinc_forward_kernel<<<(unsigned)((n + PB - 1) / PB), PB, SMEM_BYTES, (cudaStream_t)stream>>>(p, z_dev, out_dev, n);
     }
@@ -884,7 +929,7 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     for (int q = 0; q < BROV_MAX_H; ++q) a.H[q] = q < d->n_horizons ? d->horizons[q] : 0x7fffffff;
     a.carry_steps = d->carry_steps; a.win0 = d->window0; a.row0 = d->row0;
     a.carry_lag0 = (const double*)d->carry_lag0_dev;
-    if (h->use_tc) pinc_se_tc_kernel<<<(unsigned)nblocks, TC_TILES * TC_M, TC_SMEM_BYTES, st>>>(a, h->wtc);
+    if (h->use_tc) pinc_se_tc_kernel<<<(unsigned)nblocks, TC_THREADS, TC_SMEM_BYTES, st>>>(a, h->wtc, h->act);
     else pinc_se_kernel<<<(unsigned)nblocks, PB2, SMEM_BYTES2, st>>>(a);
     pinc_finish_kernel<<<1, 256, 0, st>>>(h->partial, (int)nblocks, d->se_out_dev);
     BROV_CUDA_TRY(cudaGetLastError());

@@ -1,5 +1,6 @@
 """Times the PINc evaluator (1,000,100-row series, H = 1/10/100, every window) on the tensor-core path and — with
-BROV_PINC_TC=0 in the environment — on the CUDA-core path.  Usage: python profiles/pinc_timing.py"""
+BROV_PINC_TC=0 in the environment — on the CUDA-core path.  Usage: python profiles/pinc_timing.py [H]  (one horizon
+only, e.g. 10, for a short run under ncu)"""
 import os
 import sys
 import time
@@ -18,7 +19,10 @@ U = torch.rand((T, 8), device=dev, dtype=torch.float64, generator=g) * 0.8 - 0.4
 X = 0.5 * torch.randn((T, 12), device=dev, dtype=torch.float64, generator=g)
 cg = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_cmp.npz"))
 M = P.PincModel({kk[len("pinc_sd_"):]: cg[kk] for kk in cg.files if kk.startswith("pinc_sd_")})
-for hs in ([1, 10, 100], [100], [10]):
+out = M(cg["pinc_dataset_zin"][:64]).cpu().numpy().astype(np.float64)
+ref = cg["pinc_forward"]
+print(f"forward vs the reference's torch network: normwise {np.max(np.abs(out - ref)) / max(np.max(np.abs(ref)), 1.0):.2e}", flush=True)
+for hs in ([[int(sys.argv[1])]] if len(sys.argv) > 1 else ([1, 10, 100], [100], [10])):
     se, cnt = M.multistep_se(X, U, hs, dt, "reset")
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

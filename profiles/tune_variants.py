@@ -78,8 +78,10 @@ case("thr_f64_tma_1000", "thruster8", "f64", N64, 1000, "tma")
 case("thr_f64_gen_1000", "thruster8", "f64", N64, 1000, "gen")
 case("thr_f64_tma_1000_lag24", "thruster8", "f64", N64, 1000, "tma", lag_repr="thruster")
 case("w12_f64_tma_100", "wrench12", "f64", N64, 100, "tma")
+case("w12_f64_tma_1000", "wrench12", "f64", N64, 1000, "tma")
 case("w12_f64_gen_1000", "wrench12", "f64", N64, 1000, "gen")
 case("q13_f64_tma_100", "quat13", "f64", N64, 100, "tma")
+case("q13_f64_tma_1000", "quat13", "f64", N64, 1000, "tma")
 case("w12_f64_mc_100", "wrench12", "f64", N64, 100, "tma", mc=True)
 case("thr_f32_tma_100_s10", "thruster8", "f32", N32, 100, "tma", stride=10)
 case("thr_f32_gen_100_s10", "thruster8", "f32", N32, 100, "gen", stride=10)

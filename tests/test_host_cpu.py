@@ -44,6 +44,32 @@ def test_every_declared_symbol_is_exported(L):
     assert C.sizeof(L.PincSeDesc) == 4 + 4 + 4 * 4 + 8 * 5 + 4 + 4 + 8 * 3
 
 
+def test_header_compiles_as_c_and_layouts_match_the_ctypes_mirrors(L, tmp_path):
+    """include/brov.h is plain C: gcc compiles it, and sizeof / offsetof of every descriptor a binding has to mirror
+    agree with the ctypes structures of _lib.py (the binding INTEGRATION.md shows)."""
+    pairs = [("brov_input_gen", L.InputGen), ("brov_rollout_desc", L.RolloutDesc),
+             ("brov_gen_inputs_desc", L.GenInputsDesc), ("brov_se_desc", L.SeDesc),
+             ("brov_rollout_host_desc", L.RolloutHostDesc), ("brov_pinc_weights", L.PincWeights),
+             ("brov_pinc_rollout_desc", L.PincRolloutDesc), ("brov_pinc_se_desc", L.PincSeDesc)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "brov.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("abi %d\\n", BROV_ABI_VERSION);', "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(got["abi"]) == L.ABI_VERSION
+    for cname, ct in pairs:
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+
+
 def test_constants_match_reference(L, golden):
     from bluerov2_dynamics_b200.engine import default_allocation, default_physical, derive_params, lag_discretize
     ph = default_physical()

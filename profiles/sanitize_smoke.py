@@ -1,5 +1,6 @@
 """Small-size pass over every kernel of libbrov.so, meant to run under compute-sanitizer on a B200:
 
+    python profiles/sanitize_smoke.py                      (plain: ragged-size pass over every kernel)
     compute-sanitizer --tool memcheck  python profiles/sanitize_smoke.py
     compute-sanitizer --tool racecheck python profiles/sanitize_smoke.py
 
@@ -34,6 +35,21 @@ for dtype in ("f64", "f32"):
             r2 = e.rollout(x0, U[:, 0], dt=dt, integrator=integ, stride=0, u_layout="shared")
             e.rollout(x0, U, dt=dt, integrator=integ, stride=3, time_slices=3)
             assert torch.isfinite(r.xT).all() and torch.isfinite(r2.xT).all()
+        if not e.is_di:   # round-2 paths: generated commands, projected lag carry, health counters, materialised stream
+            gen = B.InputGenerator(seed=7, sigma=0.05, scale=None if nu == 8 else [8, 8, 8, 0.3, 0.3, 0.3], vehicle0=11)
+            mc = torch.empty(n, device="cuda", dtype=e.tdtype)
+            r1 = e.rollout(x0, gen=gen, steps=T, dt=dt, stride=4, health=True, min_abs_cos=mc,
+                           lag_repr="projected" if model == "thruster8" else "thruster")
+            r2 = e.rollout(r1.xT, gen=gen, steps=60, step0=T, dt=dt, lag0=r1.lag, gen_state=r1.gen_state, health=True,
+                           min_abs_cos=mc, min_abs_cos_accumulate=True, time_slices=2,
+                           lag_repr="projected" if model == "thruster8" else "thruster")
+            assert torch.isfinite(r2.xT).all() and int(r2.health[0]) == 0
+            e.generate_inputs(gen, steps=T, first=5, n_sel=17)
+            e.rollout_host(np.ascontiguousarray(x0.astype(e.ndtype)), gen=gen, steps=41, dt=dt, chunk_steps=16, health=np.zeros(2, np.uint64))
+            if model == "thruster8":   # per-thruster lag epilogue: shorter and longer than the filter memory
+                e.rollout(x0, gen=gen, steps=5, dt=dt, lag0=np.full((n, 24), 0.01))
+                e.rollout(x0, gen=gen, steps=70, dt=dt, lag0=np.full((n, 24), 0.01))
+                e.rollout(x0, np.tile(U, (4, 1, 1)), dt=dt, lag0=np.full((n, 24), 0.01))
         e.rhs(x0, U[0])
         e.step(x0, U[0], dt=dt, integrator="euler")
         if model != "thruster8":
@@ -81,5 +97,10 @@ M(cg["pinc_dataset_zin"][:77])
 M.rollout(np.tile(g["rmse_X12"][:3], (150, 1))[:401], np.tile(g["rmse_U8"][:17, None, :], (1, 401, 1)), dt, stride=4)
 P.multistep_rmse_endpoint_pinc(g["rmse_X12"], g["rmse_U8"], [1, 10, 100], dt, M, lag_mode="reset")
 P.multistep_rmse_endpoint_pinc(g["rmse_X12"], g["rmse_U8"], 10, dt, M)
+# tensor-core evaluator: more windows than one CTA's two tiles, ragged last tile, both lag modes
+Xl, Ul = np.tile(g["rmse_X12"], (6, 1)), np.tile(g["rmse_U8"], (6, 1))
+P.multistep_rmse_endpoint_pinc(Xl, Ul, [1, 10, 100], dt, M, lag_mode="reset")
+P.multistep_rmse_endpoint_pinc(Xl, Ul, 10, dt, M)
+M(np.tile(cg["pinc_dataset_zin"], (8, 1))[:700])
 torch.cuda.synchronize()
 print("sanitize_smoke OK")

@@ -373,7 +373,9 @@ def run_e2e_legs(torch, dist, B, cfg, leg, steps, warmup, world, windows):
                api="Engine.rollout_host -> brov_rollout_host (C ABI), pinned host buffers, 250 RK4 steps per call in 10 "
                    "sub-chunks double-buffered on a copy stream")
     reset()
-    gchunk = leg["chunk"]
+    # ONE call = the whole job of configs[1]: 10,000 RK4 steps of every vehicle (one launch, the library's default for
+    # generated commands); x0 / lag / generator state go up once per call and come back once
+    gchunk = 10 * leg["chunk"]
     health = np.zeros(2, np.uint64)
     sec = wall(lambda k: eng.rollout_host(xh, gen=gen, steps=gchunk, dt=DT, integrator="rk4", lag0=lagh, out_xT=xh,
                                           out_lag=lagh, lag_repr="projected", gen_state=gsh, out_gen_state=gsh, health=health),

@@ -455,13 +455,17 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
             } else {
                 load_u<T, NU, false>(up + (long long)k * a.u_stride_t, uvec, u);
             }
-        } else {
-            const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
-            if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un);
         }
 
         T acth;
-        integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth, side);
+        if constexpr (PREFETCH) {   // the next step's row is requested between stages 2 and 3 (LateSide)
+            const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
+            auto pf = [&]() { if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un); };
+            LateSide<decltype(pf)> late{pf, 1};
+            integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth, late);
+        } else {
+            integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth, side);
+        }
         mc = fminf(mc, (float)acth);
 
         if (--countdown == 0) {

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 # name -> list of -D defines.  The knobs measured in round 2 (input path per kernel, register caps, nu_dot form, ring
 # depth, Philox rounds, per-vehicle table placement) are decided and gone from the sources; their timings are kept in
-# profiles/r02[d-k]_tune_variants.txt.  Add a knob to the sources and an entry here to measure the next one.
+# profiles/r02[d-t]_tune_variants.txt.  Add a knob to the sources and an entry here to measure the next one.
 VARIANTS = {}
 VDIR = os.path.join(ROOT, "bluerov2_dynamics_b200", "variants")
 

@@ -81,7 +81,8 @@ class ShardedEvaluator:
     """Multi-step endpoint squared error of ONE recorded series on `world` GPUs, as a replayable step.
 
     Each rank owns a contiguous block of windows (plus the halo rows they read); one evaluation is
-    `se_kernel -> se_finish_kernel -> all-reduce` of a 6-double vector [se_H0..se_H3, n_nonfinite, n_near_singular].
+    `se_kernel -> se_finish_kernel -> all-reduce` of a 6-double vector [se_H0..se_H3, n_nonfinite, n_near_singular]
+    (lag_mode="carry": one se_kernel pass per horizon, concurrent on forked streams, ONE all-reduce).
     The whole chain is captured ONCE in a CUDA graph (the NCCL all-reduce included) and replayed: at 125,000 windows per
     GPU the kernels take ~0.85 ms, so the ~0.2 ms of per-call host work (descriptor packing, three launches, a clone
     and an eager all-reduce) of the round-1 loop was a fifth of the step.  `use_graph=False` keeps the eager chain
@@ -95,48 +96,78 @@ class ShardedEvaluator:
         T = len(X)
         self.T, self.nx = T, X.shape[1]
         self.carry = lag_mode == "carry" and engine.model == "thruster8"
+        dev = engine.device
+        from . import _lib as L
+        # passes: (horizons, first local row, n_rows, n_windows, window0, row0).  reset: ONE pass scores every horizon
+        # (H = 1 and 10 are prefixes of the H = 100 rollout).  carry: the lag history a window inherits depends on the
+        # horizon (the reference runs one evaluation per horizon on one shared model object), so one pass per horizon
+        # — launched longest first on separate streams inside the same graph, so that the short passes fill the tail
+        # of the long one instead of each paying its own partial last wave.
         if self.carry:
-            if len(self.hs) != 1:
-                raise ValueError("lag_mode='carry' scores one horizon per evaluator")
             depth = engine.carry_steps(dt, integrator)
-            lo, hi, self.nloc, self.win0 = window_shard_carry(T, self.hs[0], rank, world, depth)
-            self.row0 = lo
+            shards = [window_shard_carry(T, h, rank, world, depth) for h in self.hs]
+            lo = min((s[0] for s in shards if s[2] > 0), default=0)
+            hi = max((s[1] for s in shards if s[2] > 0), default=0)
+            self.passes = [([h], s[0] - lo, s[1] - s[0], s[2], s[3], s[0]) for h, s in zip(self.hs, shards)]
+            self.passes.sort(key=lambda p: -p[0][0])
         else:
-            lo, hi, self.nloc = window_shard(T, self.hs, rank, world)
-            self.win0 = self.row0 = 0
+            lo, hi, nloc = window_shard(T, self.hs, rank, world)
+            self.passes = [(self.hs, 0, hi - lo, nloc, 0, 0)]
+        self.nloc = sum(p[3] for p in self.passes)
         self.X = engine.tensor(X[lo:hi]).contiguous()
         self.U = engine.tensor(U[lo:hi]).contiguous()
-        self.buf = torch.zeros(8, dtype=torch.float64, device=engine.device)      # [se x4, health x2, pad x2]
-        self.hc = torch.zeros(2, dtype=torch.int64, device=engine.device)
+        self.buf = torch.zeros(8, dtype=torch.float64, device=dev)      # [se x4, health x2, pad x2]
+        npass = len(self.passes)
+        self.se = torch.zeros((npass, 8), dtype=torch.float64, device=dev)
+        self.hc = torch.zeros((npass, 2), dtype=torch.int64, device=dev)
+        self.ws = [torch.empty(int(L.lib.brov_se_workspace_bytes(max(p[3], 1))), dtype=torch.uint8, device=dev)
+                   for p in self.passes]
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(npass - 1)]
         self.graph = None
-        self._eager()                      # warm-up: allocates the engine workspace, initialises NCCL for this size
-        torch.cuda.synchronize(engine.device)
+        self._eager()                      # warm-up: initialises NCCL for this size
+        torch.cuda.synchronize(dev)
         if use_graph:
             try:
                 g = torch.cuda.CUDAGraph()
-                s = torch.cuda.Stream(device=engine.device)
-                s.wait_stream(torch.cuda.current_stream(engine.device))
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(s):
                     self._eager()
-                torch.cuda.current_stream(engine.device).wait_stream(s)
-                torch.cuda.synchronize(engine.device)
+                torch.cuda.current_stream(dev).wait_stream(s)
+                torch.cuda.synchronize(dev)
                 with torch.cuda.graph(g, stream=s):
                     self._eager()
                 self.graph = g
             except Exception as ex:        # capture of the collective not supported by this torch / NCCL pairing
                 self.graph = None
                 self.capture_error = repr(ex)
-                torch.cuda.synchronize(engine.device)
+                torch.cuda.synchronize(dev)
+
+    def _pass(self, i):
+        hs, r0, nrows, nwin, win0, row0 = self.passes[i]
+        if nwin > 0:
+            self.e.multistep_se(self.X[r0:r0 + nrows], self.U[r0:r0 + nrows], hs, dt=self.dt, integrator=self.integ,
+                                n_windows=nwin, lag_mode=self.lag_mode, window0=win0, row0=row0, se_out=self.se[i],
+                                health_out=self.hc[i], singular_eps=self.eps, workspace=self.ws[i])
+        else:
+            self.se[i].zero_()
+            self.hc[i].zero_()
 
     def _eager(self):
-        if self.nloc > 0:
-            self.e.multistep_se(self.X, self.U, self.hs, dt=self.dt, integrator=self.integ, n_windows=self.nloc,
-                                lag_mode=self.lag_mode, window0=self.win0, row0=self.row0, se_out=self.buf,
-                                health_out=self.hc, singular_eps=self.eps)
+        cur = torch.cuda.current_stream(self.e.device)
+        self._pass(0)
+        for i, s in enumerate(self.side, start=1):      # fork: the other passes on their own streams
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                self._pass(i)
+        for s in self.side:                              # join
+            cur.wait_stream(s)
+        if self.carry:
+            for i, p in enumerate(self.passes):
+                self.buf[self.hs.index(p[0][0])] = self.se[i, 0]
         else:
-            self.buf.zero_()
-            self.hc.zero_()
-        self.buf[4:6] = self.hc.to(torch.float64)
+            self.buf[:4] = self.se[0, :4]
+        self.buf[4:6] = self.hc.sum(dim=0).to(torch.float64)
         allreduce_sum_(self.buf)
 
     def run(self) -> torch.Tensor:

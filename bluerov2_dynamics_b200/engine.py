@@ -433,7 +433,7 @@ class Engine:
     def multistep_se(self, X, U, horizons: Sequence[int], dt: float = 0.02, integrator: str = "rk4",
                      lag0=None, n_windows: Optional[int] = None, lag_mode: str = "reset", window0: int = 0,
                      row0: int = 0, se_out: Optional[torch.Tensor] = None, health_out: Optional[torch.Tensor] = None,
-                     singular_eps: float = 0.0):
+                     singular_eps: float = 0.0, workspace: Optional[torch.Tensor] = None):
         """Sum of squared endpoint errors per horizon over sliding windows of one recorded series.
         Returns (se [MAX_H] float64 device tensor, counts list).  See brov_multistep_se in include/brov.h.
         lag_mode="carry" (thruster model, one horizon): the reference's literal semantics — the lag state left by
@@ -441,7 +441,9 @@ class Engine:
         when X, U are a shard of a longer series.
         se_out: float64 [MAX_H] device tensor to write into (e.g. a slice of a reduction buffer); health_out: int64 [2]
         device tensor receiving the number of windows with a non-finite endpoint error / that came within
-        singular_eps of theta = +-pi/2."""
+        singular_eps of theta = +-pi/2.
+        workspace: uint8 device tensor of at least brov_se_workspace_bytes(n_windows) for the per-block partial sums
+        (default: the engine's own, which calls on DIFFERENT streams must not share)."""
         X = self.tensor(X)
         U = self.tensor(U)
         self._check_rows(X, self.nx, "X")
@@ -458,8 +460,14 @@ class Engine:
         off = int(window0) - int(row0)
         nwin = max(rows - off - hs[0], 0) if n_windows is None else int(n_windows)
         nbytes = L.lib.brov_se_workspace_bytes(nwin)
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if workspace is not None:
+            if workspace.dtype != torch.uint8 or workspace.device != self.device or workspace.numel() < nbytes:
+                raise ValueError(f"workspace must be a uint8 tensor of at least {nbytes} bytes on {self.device}")
+            ws = workspace
+        else:
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ws = self._ws
         if se_out is None:
             se = torch.zeros(L.MAX_H, dtype=torch.float64, device=self.device)
         else:
@@ -481,7 +489,7 @@ class Engine:
             d.horizons[i] = h
         d.se_out_dev = se.data_ptr()
         d.count_out = counts
-        d.workspace_dev = self._ws.data_ptr()
+        d.workspace_dev = ws.data_ptr()
         d.workspace_bytes = nbytes
         d.lag_carry = int(carry)
         d.window0, d.row0 = (int(window0), int(row0)) if carry else (0, 0)

@@ -470,3 +470,34 @@ def test_bench_call_fp32_twin(B):
     assert bad.sum() <= MAX_EXCLUDED_FRACTION * n, int(bad.sum())
     print(f"fp32 twin: {int((~bad).sum())} of {n} vehicles within {TOL32:g} (median {np.median(err):.1e}); {int(bad.sum())} "
           f"near the singularity (max of their min |cos theta| {mco[bad].max() if bad.any() else 0:.3f})")
+
+
+# ------------------------------------------------------------------------------------------------ sharded evaluator
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_sharded_evaluator_matches_reference_golden(B, golden, use_graph):
+    """dist.ShardedEvaluator (what bench.py's rmse leg and a multi-GPU caller run): `reset` scores every horizon in one
+    pass, `carry` — the reference's literal semantics (training/train_tank_brov2_rk4.py:399-417, one model object for
+    all windows) — one pass per horizon on concurrent streams inside one captured graph.  Both against the numbers the
+    unmodified reference produced; rank r of a pretended world of 3 adds up to the same sums."""
+    from bluerov2_dynamics_b200 import dist as D
+    X, U = golden["rmse_X12"], golden["rmse_U8"]
+    HS = [int(h) for h in golden["rmse_H"]]
+    e = B.Engine("thruster8", "f64")
+    for mode, key in (("reset", "rmse_thr_rk4_reset"), ("carry", "rmse_thr_rk4_carry")):
+        ev = D.ShardedEvaluator(e, X, U, HS, DT, "rk4", 0, 1, lag_mode=mode, use_graph=use_graph)
+        assert (ev.graph is not None) == use_graph, getattr(ev, "capture_error", None)
+        for _ in range(3):          # replays give the same answer
+            ev.run()
+        torch.cuda.synchronize()
+        r, hc = ev.rmse()
+        assert np.allclose(r, golden[key], rtol=1e-10), (mode, r, golden[key])
+        assert hc == [0, 0]
+        # shards: the per-rank vectors (no process group here: the all-reduce is the identity) add up to the whole
+        tot = np.zeros(4)
+        for rank in range(3):
+            es = D.ShardedEvaluator(e, X, U, HS, DT, "rk4", rank, 3, lag_mode=mode, use_graph=False)
+            es.run()
+            tot += es.buf.cpu().numpy()[:4]
+        cnt = D.global_counts(len(X), HS)
+        rs = [float(np.sqrt(tot[i] / (cnt[i] * 12))) for i in range(len(HS))]
+        assert np.allclose(rs, golden[key], rtol=1e-10), (mode, rs)

@@ -15,6 +15,7 @@
 // activations in a private shared-memory column ([unit][thread], conflict-free).  The thruster map runs inline in
 // float64 on the four allocation-projected lag filters the network input needs (rows X, Y, Z, Mz of the allocation
 // matrix: 12 hidden values instead of the reference's 24), exactly one lag step per rollout step like the reference.
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -516,60 +517,54 @@ __global__ void __launch_bounds__(256) pinc_finish_kernel(const double* __restri
 
 #include "brov_pinc_tc.cuh"
 
-// PINcNet.forward on the tensor cores: persistent CTAs of two tiles, 128 input rows per tile, two threads per row
-__global__ void __launch_bounds__(TC_THREADS, 1) pinc_forward_tc_kernel(const float* __restrict__ wtc, const __grid_constant__ TcAct act,
+// PINcNet.forward on the tensor cores (brov_pinc_tc.cuh): persistent CTAs of three 128-row tiles, one thread per row
+__global__ void __launch_bounds__(TC_THREADS, 1) pinc_forward_tc_kernel(const float* __restrict__ wtc,
+                                                                         const __grid_constant__ TcAct act,
                                                                          const float* __restrict__ Zin,
                                                                          float* __restrict__ out, long long n) {
     extern __shared__ __align__(1024) float smf[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[TC_TILES];
-    __shared__ float2 xch[TC_TILES * 2 * TC_M];
     TcCtx c;
-    tc_setup(c, smf, wtc, &tmem_slot, bars, xch);
+    tc_setup(c, smf, wtc, &tmem_slot, bars);
     const long long ntiles = (n + TC_M - 1) / TC_M;
     for (long long tile = (long long)blockIdx.x * TC_TILES + c.tile; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
         const long long gi = tile * TC_M + c.row;
         const long long i = gi < n ? gi : n - 1;
         float z[NIN], xn[9];
-        if (c.part == 0) {
 #pragma unroll
-            for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
-            tc_put_state(c, z, z[13]);
-            tc_put_thrust(c, z + 9);
-        }
+        for (int j = 0; j < NIN; ++j) z[j] = Zin[i * NIN + j];
+        tc_put_inputs(c, z, z[13], z + 9);
         pinc_net_tc(c, act);
         tc_layer_wait(c);
-        if (c.part == 0) {
-            tc_residual(c, z, xn);
-            if (gi < n) {
+        tc_residual(c, z, xn);
+        if (gi < n) {
 #pragma unroll
-                for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
-            }
+            for (int j = 0; j < 9; ++j) out[i * 9 + j] = xn[j];
         }
     }
-    tc_teardown(c, &tmem_slot);
+    tc_teardown(&tmem_slot);
 }
 
 // multistep_rmse_endpoint_pinc on the tensor cores: a tile = 128 consecutive windows stepped together through the
-// longest horizon.  The row's leader thread carries the network state and scores the endpoints; its helper carries
-// the projected lag states and evaluates the thruster map of the next step under the output layer's MMAs.
+// longest horizon; a thread carries its window's network state and projected lag states, scores the endpoints, and
+// evaluates the fp64 thruster map of the NEXT step while the output layer's MMAs of the current one run.
 __global__ void __launch_bounds__(TC_THREADS, 1) pinc_se_tc_kernel(const __grid_constant__ PincSeArgs a,
                                                                     const float* __restrict__ wtc,
                                                                     const __grid_constant__ TcAct act) {
     extern __shared__ __align__(1024) float smf[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t bars[TC_TILES];
-    __shared__ float2 xch[TC_TILES * 2 * TC_M];
     __shared__ double red[TC_THREADS / 32][BROV_MAX_H];
     TcCtx c;
-    tc_setup(c, smf, wtc, &tmem_slot, bars, xch);
+    tc_setup(c, smf, wtc, &tmem_slot, bars);
     double se[BROV_MAX_H];
 #pragma unroll
     for (int h = 0; h < BROV_MAX_H; ++h) se[h] = 0.0;
     const int hmax = a.H[a.nH - 1];
     const float dtf = (float)a.m.dt;
     const long long ntiles = (a.nwin + TC_M - 1) / TC_M;
-    // the CTA's two tiles walk the tile list independently (tile-wide barriers only inside the loop)
+    // the CTA's three tiles walk the tile list independently (tile-wide barriers only inside the loop)
     for (long long tile = (long long)blockIdx.x * TC_TILES + c.tile; tile < ntiles; tile += (long long)gridDim.x * TC_TILES) {
         const long long gk = tile * TC_M + c.row;
         const bool live = gk < a.nwin;
@@ -577,9 +572,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinc_se_tc_kernel(const __grid_
         const long long kr = k + (a.win0 - a.row0);
         const long long room = a.rows - 1 - kr;
         const int nst = live ? (int)(room < hmax ? (room < 0 ? 0 : room) : hmax) : 0;
-        float z[9];
+        float z[9], u4f[4];
         double Z[12];
-        float u4f[4];
         // a window that has run out of rows keeps stepping on its last valid input row; its results are ignored
         auto thrust = [&](int j) {
             const long long row = kr + (j < nst ? j : (nst > 0 ? nst - 1 : 0));
@@ -590,60 +584,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinc_se_tc_kernel(const __grid_
 #pragma unroll
             for (int q = 0; q < 4; ++q) u4f[q] = (float)u4[q];
         };
-        if (c.part == 0) {
+        {
             double x12[12];
 #pragma unroll
             for (int j = 0; j < 12; ++j) x12[j] = __ldg(a.X + kr * 12 + j);
             x12_to_9(x12, z);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 12; ++j) Z[j] = 0.0;
-            if (a.carry_steps > 0 && live) {
-                const long long H0 = a.H[0];
-                const long long total = (a.win0 + k) * H0;
-                const long long m = total < a.carry_steps ? total : a.carry_steps;
-                if (a.carry_lag0 && total <= a.carry_steps) {
-                    double l24[24];
-#pragma unroll
-                    for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
-                    project4(a.m, l24, Z);
-                }
-                for (long long s = total - m; s < total; ++s) {
-                    const long long ww = s / H0;
-                    const long long row = ww + (s - ww * H0) - a.row0;
-                    double u8[8], u4[4];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
-                    thruster_map4(a.m, u8, Z, u4);
-                }
-            }
-            thrust(0);
         }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) Z[j] = 0.0;
+        if (a.carry_steps > 0 && live) {
+            const long long H0 = a.H[0];
+            const long long total = (a.win0 + k) * H0;
+            const long long m = total < a.carry_steps ? total : a.carry_steps;
+            if (a.carry_lag0 && total <= a.carry_steps) {
+                double l24[24];
+#pragma unroll
+                for (int j = 0; j < 24; ++j) l24[j] = __ldg(a.carry_lag0 + j);
+                project4(a.m, l24, Z);
+            }
+            for (long long s = total - m; s < total; ++s) {
+                const long long ww = s / H0;
+                const long long row = ww + (s - ww * H0) - a.row0;
+                double u8[8], u4[4];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) u8[j] = __ldg(a.U + row * 8 + j);
+                thruster_map4(a.m, u8, Z, u4);
+            }
+        }
+        thrust(0);
         for (int j = 0; j < hmax; ++j) {     // uniform trip count: the network holds tile-wide barriers
-            if (c.part == 0) tc_put_state(c, z, dtf);
-            else tc_put_thrust(c, u4f);
+            tc_put_inputs(c, z, dtf, u4f);
             pinc_net_tc(c, act);
-            if (c.part == 1 && j + 1 < hmax) thrust(j + 1);       // under the output layer's MMAs
+            if (j + 1 < hmax) thrust(j + 1);       // the fp64 thruster map of the next step under the output layer's MMAs
             tc_layer_wait(c);
-            if (c.part == 0) {
-                float xn[9];
-                tc_residual(c, z, xn);
+            float xn[9];
+            tc_residual(c, z, xn);
 #pragma unroll
-                for (int q = 0; q < 9; ++q) z[q] = xn[q];
+            for (int q = 0; q < 9; ++q) z[q] = xn[q];
 #pragma unroll
-                for (int h = 0; h < BROV_MAX_H; ++h) {
-                    if (h < a.nH && j + 1 == a.H[h] && j < nst) {
-                        double x12[12];
-                        x9_to_12(xn, x12);
-                        const double* tgt = a.X + (kr + j + 1) * 12;
-                        double s = 0.0;
+            for (int h = 0; h < BROV_MAX_H; ++h) {
+                if (h < a.nH && j + 1 == a.H[h] && j < nst) {
+                    double x12[12];
+                    x9_to_12(xn, x12);
+                    const double* tgt = a.X + (kr + j + 1) * 12;
+                    double s = 0.0;
 #pragma unroll
-                        for (int q = 0; q < 12; ++q) {
-                            const double e = x12[q] - __ldg(tgt + q);
-                            s += e * e;
-                        }
-                        se[h] += s;
+                    for (int q = 0; q < 12; ++q) {
+                        const double e = x12[q] - __ldg(tgt + q);
+                        s += e * e;
                     }
+                    se[h] += s;
                 }
             }
         }
@@ -663,7 +653,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) pinc_se_tc_kernel(const __grid_
         for (int w = 0; w < TC_THREADS / 32; ++w) v += red[w][threadIdx.x];
         a.partial[(long long)blockIdx.x * BROV_MAX_H + threadIdx.x] = v;
     }
-    tc_teardown(c, &tmem_slot);
+    tc_teardown(&tmem_slot);
 }
 
 }  // namespace
@@ -742,9 +732,10 @@ extern "C" int brov_pinc_create(int device, const brov_pinc_weights* wts, brov_p
     }
     for (int l = 0; l < 4; ++l) h->beta[l] = wts->beta[l];
     // tensor-core blob: every weight split into two TF32 numbers (round to nearest), W[n][k] at tc_off(rows, n, k)
-    float* tcb = new (std::nothrow) float[TC_NW];
+    float* tcb = new (std::nothrow) float[TC_NW];    // TF32 parts, biases, then FP16 copies of the high parts
     if (!tcb) { delete[] blob; delete h; return brov::fail_msg(BROV_ENOMEM, "out of host memory"); }
     memset(tcb, 0, TC_NW * sizeof(float));
+    unsigned short* tcb16 = reinterpret_cast<unsigned short*>(tcb);
     auto rna = [](float x) {
         uint32_t b;
         memcpy(&b, &x, 4);
@@ -754,10 +745,12 @@ extern "C" int brov_pinc_create(int device, const brov_pinc_weights* wts, brov_p
         return r;
     };
     // x (double) -> two TF32 numbers, x = hi + lo to 2^-22 relative
-    auto put = [&](int hi_off, int lo_off, int rows, int n, int k, double w) {
+    auto put = [&](int hi_off, int lo_off, int h16_off, int rows, int n, int k, double w) {
         const float hi = rna((float)w);
         tcb[hi_off + tc_off(rows, n, k)] = hi;
         tcb[lo_off + tc_off(rows, n, k)] = rna((float)(w - (double)hi));
+        const __half w16 = __float2half_rn((float)w);      // multiplies the activations' FP16 low parts
+        memcpy(&tcb16[2 * h16_off + tc_off16(rows, n, k)], &w16, 2);
     };
     // Folds (double precision): LayerNorm l's affine into layer l + 1 (W' = W diag(ln_w), b' = b + W ln_b); the
     // activation's input scale beta log2(e) into the hidden layers' biases; its output scale ln 2 / (beta + 1e-12) into
@@ -774,15 +767,16 @@ extern "C" int brov_pinc_create(int device, const brov_pinc_weights* wts, brov_p
         const int hi_off = l == 0 ? TC_L0_HI : (l == 4 ? TC_L4_HI : TC_L1 + (l - 1) * 8192);
         const int lo_off = l == 0 ? TC_L0_LO : (l == 4 ? TC_L4_LO : TC_L1 + (l - 1) * 8192 + 4096);
         const int rows = l == 4 ? 16 : HID;
+        const int h16_off = l == 0 ? TC_H16_L0 : (l == 4 ? TC_H16_L4 : TC_H16_L1 + (l - 1) * 2048);
         for (int n = 0; n < N; ++n) {
             double bias = wts->b[l][n];
             if (l == 0) {
                 for (int k = 0; k < 16; ++k)       // layer 0's K axis in the order the kernels store it (tc_kmap0)
-                    if (tc_kmap0(k) >= 0) put(hi_off, lo_off, rows, n, k, wts->W[0][n * NIN + tc_kmap0(k)]);
+                    if (tc_kmap0(k) >= 0) put(hi_off, lo_off, h16_off, rows, n, k, wts->W[0][n * NIN + tc_kmap0(k)]);
             } else {
                 for (int k = 0; k < K; ++k) {
                     const double w = wts->W[l][n * K + k];
-                    put(hi_off, lo_off, rows, n, k, w * (double)wts->ln_w[l - 1][k]);
+                    put(hi_off, lo_off, h16_off, rows, n, k, w * (double)wts->ln_w[l - 1][k]);
                     bias += w * (double)wts->ln_b[l - 1][k];
                 }
             }
@@ -911,7 +905,8 @@ extern "C" int brov_pinc_multistep_se(brov_pinc_t* h, const brov_pinc_se_desc* d
     }
     int rc = pinc_attrs(h);
     if (rc) return rc;
-    const size_t tiles = ((size_t)((d->n_windows + TC_M - 1) / TC_M) + TC_TILES - 1) / TC_TILES;   // CTAs of TC_TILES tiles
+    const size_t per_cta = TC_TILES;
+    const size_t tiles = ((size_t)((d->n_windows + TC_M - 1) / TC_M) + per_cta - 1) / per_cta;   // CTAs of per_cta tiles
     const size_t nblocks = h->use_tc ? (tiles < (size_t)h->num_sms ? tiles : (size_t)h->num_sms)
                                      : (size_t)((d->n_windows + NWIN * PB2 - 1) / (NWIN * PB2));
     if (nblocks * BROV_MAX_H > h->cap_partial) {

@@ -788,15 +788,20 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
         // window k may run j steps while row k + j exists
         long long room = (long long)a.rows - 1 - kr;
         const int nsteps = (int)(room < hmax ? (room < 0 ? 0 : room) : hmax);
-        T mc = T(1);
+        float mc = 1.0f;
         bool bad = false;
+        T u[NU], un[NU];
+        if (nsteps > 0) load_u<T, NU, false>(a.U + kr * NU, uvec, u);
         for (int j = 0; j < nsteps; ++j) {
-            T u[NU];
-            load_u<T, NU, false>(a.U + (kr + j) * NU, uvec, u);
+            // the next step's input row is requested between stages 2 and 3 of this one (LateSide, as in the rollout)
+            const T* nxt = a.U + (kr + (j + 1 < nsteps ? j + 1 : j)) * NU;
+            auto pf = [&]() { load_u<T, NU, false>(nxt, uvec, un); };
+            LateSide<decltype(pf)> late{pf, 1};
             T acth;
-            NoSide side;
-            integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth, side);
-            mc = acth < mc ? acth : mc;
+            integrate_step<T, MODEL, INTEG, false, decltype(p)>(a.c, p, x, lag, u, acth, late);
+#pragma unroll
+            for (int q = 0; q < NU; ++q) u[q] = un[q];
+            mc = fminf(mc, (float)acth);
 #pragma unroll
             for (int h = 0; h < MAX_H; ++h) {
                 if (h < a.nH && j + 1 == a.H[h]) {

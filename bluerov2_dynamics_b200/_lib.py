@@ -54,7 +54,7 @@ class SeDesc(C.Structure):
                 ("n_windows", C.c_longlong), ("dt", C.c_double), ("X_dev", C.c_void_p), ("U_dev", C.c_void_p),
                 ("lag0_dev", C.c_void_p), ("n_horizons", C.c_int32), ("horizons", C.c_int32 * MAX_H),
                 ("se_out_dev", C.c_void_p), ("count_out", C.POINTER(C.c_longlong)), ("workspace_dev", C.c_void_p),
-                ("workspace_bytes", C.c_size_t), ("lag_carry", C.c_int32), ("reserved", C.c_int32),
+                ("workspace_bytes", C.c_size_t), ("lag_carry", C.c_int32), ("time_slices", C.c_int32),
                 ("window0", C.c_longlong), ("row0", C.c_longlong), ("health_dev", C.c_void_p),
                 ("singular_eps", C.c_double)]
 

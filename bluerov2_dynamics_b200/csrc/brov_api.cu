@@ -898,9 +898,18 @@ extern "C" int brov_se_carry_steps(brov_engine_t* e, double dt, int integrator, 
     return carry_depth(e, dt, integrator == BROV_RK4 ? 4 : 1, steps_out);
 }
 
+static constexpr int SE_MAX_QUANTA = 4;
+static size_t se_align(size_t b) { return (b + 255) & ~(size_t)255; }
+// partial sums (per block and time slice), ticket + progress flags, and the hand-over rows of the time slices
+// (state 13 + lag 18 scalars, min |cos theta|, non-finite flag per window)
+static size_t se_partial_bytes(long long n_windows) {
+    return se_align((size_t)((n_windows + 63) / 64) * SE_MAX_QUANTA * MAX_H * sizeof(double));  // blocks down to 64 windows
+}
+static size_t se_flag_bytes(long long n_windows) { return se_align((size_t)(2 + (n_windows + 63) / 64) * sizeof(int)); }
 extern "C" size_t brov_se_workspace_bytes(long long n_windows) {
     if (n_windows < 1) n_windows = 1;
-    return (size_t)((n_windows + 63) / 64) * MAX_H * sizeof(double);  // covers blocks down to 64 windows
+    return se_partial_bytes(n_windows) + se_flag_bytes(n_windows) + se_align((size_t)n_windows * 13 * sizeof(double)) +
+           se_align((size_t)n_windows * 18 * sizeof(double)) + 2 * se_align((size_t)n_windows * 4);
 }
 
 template <typename T>
@@ -941,6 +950,34 @@ static int se_impl(brov_engine* e, const brov_se_desc* d, cudaStream_t st) {
     a.health.counters = (unsigned long long*)d->health_dev;
     a.health.eps = d->singular_eps > 0.0 ? d->singular_eps : 1e-3;
     if (d->health_dev) CUDA_TRY(cudaMemsetAsync(d->health_dev, 0, 2 * sizeof(unsigned long long), st));
+    // Temporal tiling against wave quantisation (SeArgs::quanta): reset mode only (a carried-lag thread walks several
+    // windows in sequence).  Q slices cost ceil(blocks Q / slots) / Q rounds of the longest horizon, plus ~1 % per
+    // extra slice for the hand-over through memory.
+    a.quanta = 1; a.nwblocks = se_blocks<T>(a.nwin); a.ticket = nullptr; a.progress = nullptr;
+    a.st_x = nullptr; a.st_lag = nullptr; a.st_mc = nullptr; a.st_bad = nullptr;
+    if (a.wpt == 1 && a.carry_steps == 0 && a.nwin > 0) {
+        const int hmax = d->horizons[d->n_horizons - 1];
+        const double slots = 2.0 * e->num_sms * (e->dtype == BROV_F32 ? 2.0 : 1.0);
+        if (d->time_slices == 0) {
+            double best = std::ceil(a.nwblocks / slots);
+            for (int q = 2; q <= SE_MAX_QUANTA && hmax >= 8 * q; ++q) {
+                const double cost = std::ceil((double)a.nwblocks * q / slots) / q * (1.0 + 0.01 * (q - 1));
+                if (cost < best * 0.97) { best = cost; a.quanta = q; }
+            }
+        } else {
+            a.quanta = d->time_slices < hmax ? d->time_slices : hmax;
+        }
+        if (a.quanta > 1) {
+            unsigned char* w = (unsigned char*)d->workspace_dev + se_partial_bytes(d->n_windows);
+            a.ticket = (int*)w; a.progress = a.ticket + 1;
+            CUDA_TRY(cudaMemsetAsync(w, 0, (size_t)(1 + a.nwblocks) * sizeof(int), st));
+            w += se_flag_bytes(d->n_windows);
+            a.st_x = (T*)w; w += se_align((size_t)d->n_windows * 13 * sizeof(double));
+            a.st_lag = (T*)w; w += se_align((size_t)d->n_windows * 18 * sizeof(double));
+            a.st_mc = (float*)w; w += se_align((size_t)d->n_windows * 4);
+            a.st_bad = (int*)w;
+        }
+    }
     CUDA_TRY(launch_se<T>(e->model, d->integrator, a, d->se_out_dev, st));
     return BROV_OK;
 }
@@ -979,6 +1016,7 @@ extern "C" int brov_multistep_se(brov_engine_t* e, const brov_se_desc* d, void* 
         return BROV_OK;
     }
     if (!d->X_dev || !d->U_dev) return fail(BROV_EINVAL, "X and U must not be NULL");
+    if (d->time_slices < 0 || d->time_slices > SE_MAX_QUANTA) return fail(BROV_EINVAL, "time_slices must be 0 (automatic) .. %d", SE_MAX_QUANTA);
     if (!d->workspace_dev || d->workspace_bytes < brov_se_workspace_bytes(d->n_windows)) return fail(BROV_EINVAL, "workspace too small: need %zu bytes", brov_se_workspace_bytes(d->n_windows));
     return e->dtype == BROV_F32 ? se_impl<float>(e, d, (cudaStream_t)stream) : se_impl<double>(e, d, (cudaStream_t)stream);
 }

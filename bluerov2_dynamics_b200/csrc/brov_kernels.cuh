@@ -112,6 +112,19 @@ template <typename T> struct SeArgs {
     long long win0;       // global index of local window 0
     long long row0;       // global index of local row 0 of X / U
     Health health;        // windows with a non-finite endpoint error / that came within eps of the singularity
+    // Temporal tiling (reset mode, wpt = 1), as in rollout_kernel: the longest horizon is cut into `quanta` slices,
+    // blocks take (slice, window-block) items from `ticket` in slice-major order and wait on `progress[window-block]`
+    // for their predecessor; state, lag, min |cos theta| and the non-finite flag pass through the st_* scratch rows.
+    // 125,000 windows per GPU (the 8-GPU shard of the 1M-window series) are 977 blocks on 296 slots: 4 rounds of 100
+    // steps for 3.3 rounds of work; with 3 slices 10 rounds of 34.
+    int quanta;           // <= 1: plain launch
+    int nwblocks;         // window blocks (= gridDim.x / quanta)
+    int* ticket;          // [1], zero before the launch
+    int* progress;        // [nwblocks], zero before the launch
+    T* st_x;              // [nwin][NX]
+    T* st_lag;            // [nwin][18]
+    float* st_mc;         // [nwin]
+    int* st_bad;          // [nwin]
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -745,12 +758,34 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
     constexpr int NL = LR::N;
     __shared__ double red[BLOCK / 32][MAX_H];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hmax = a.H[a.nH - 1];
+    // work item: window block wb, steps [j_begin, j_end) of its windows (temporal tiling, see SeArgs::quanta)
+    int wb = blockIdx.x, slice = 0, j_begin = 0, j_end = hmax;
+    if (a.quanta > 1) {
+        __shared__ int s_item;
+        if (tid == 0) s_item = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int item = __reduce_max_sync(0xffffffffu, s_item);
+        slice = item / a.nwblocks;
+        wb = item - slice * a.nwblocks;
+        const int per = (hmax + a.quanta - 1) / a.quanta;
+        j_begin = slice * per;
+        j_end = j_begin + per < hmax ? j_begin + per : hmax;
+        if (slice > 0) {
+            if (tid == 0) {
+                const volatile int* flag = a.progress + wb;
+                while (*flag < slice) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+    }
+    const bool last_slice = slice >= a.quanta - 1;
     // a thread scores a.wpt consecutive windows (1 except in carried-lag mode, see SeArgs::wpt)
-    const long long gk = ((long long)blockIdx.x * BLOCK + tid) * a.wpt;
+    const long long gk = ((long long)wb * BLOCK + tid) * a.wpt;
     ParamsConst<T> p;
     p.kp = a.c.kp;
     const bool uvec = ((reinterpret_cast<uintptr_t>(a.U) & 15) == 0) && (sizeof(T) * NU % 16 == 0);
-    const int hmax = a.H[a.nH - 1];
     double se[MAX_H];
 #pragma unroll
     for (int h = 0; h < MAX_H; ++h) se[h] = 0.0;
@@ -761,9 +796,16 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
         if (k >= a.nwin) break;
         const long long kr = k + (a.win0 - a.row0);  // local row of the window's start (rows before it: carry history)
         T x[NX];
+        if (slice > 0) {   // continue from what the predecessor slice left (L2-only loads: written during this launch)
 #pragma unroll
-        for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + kr * NX + j);
-        if (c == 0) {
+            for (int j = 0; j < NX; ++j) x[j] = __ldcg(a.st_x + k * NX + j);
+#pragma unroll
+            for (int j = 0; j < NL; ++j) lag[j] = __ldcg(a.st_lag + k * 18 + j);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) x[j] = __ldg(a.X + kr * NX + j);
+        }
+        if (c == 0 && slice == 0) {
             load_lag<T, MODEL, false>(a.c, a.lag0, false, k, lag);
             if constexpr (MODEL == MODEL_THRUSTER8) {
                 if (a.carry_steps > 0) {
@@ -790,11 +832,16 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
         const int nsteps = (int)(room < hmax ? (room < 0 ? 0 : room) : hmax);
         float mc = 1.0f;
         bool bad = false;
+        if (slice > 0) {
+            mc = __ldcg(a.st_mc + k);
+            bad = __ldcg(a.st_bad + k) != 0;
+        }
+        const int j_stop = nsteps < j_end ? nsteps : j_end;
         T u[NU], un[NU];
-        if (nsteps > 0) load_u<T, NU, false>(a.U + kr * NU, uvec, u);
-        for (int j = 0; j < nsteps; ++j) {
+        if (j_begin < j_stop) load_u<T, NU, false>(a.U + (kr + j_begin) * NU, uvec, u);
+        for (int j = j_begin; j < j_stop; ++j) {
             // the next step's input row is requested between stages 2 and 3 of this one (LateSide, as in the rollout)
-            const T* nxt = a.U + (kr + (j + 1 < nsteps ? j + 1 : j)) * NU;
+            const T* nxt = a.U + (kr + (j + 1 < j_stop ? j + 1 : j)) * NU;
             auto pf = [&]() { load_u<T, NU, false>(nxt, uvec, un); };
             LateSide<decltype(pf)> late{pf, 1};
             T acth;
@@ -817,8 +864,22 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
                 }
             }
         }
-        n_bad += bad ? 1 : 0;
-        n_sing += ((double)mc < a.health.eps) ? 1 : 0;
+        if (last_slice) {
+            n_bad += bad ? 1 : 0;
+            n_sing += ((double)mc < a.health.eps) ? 1 : 0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) a.st_x[k * NX + j] = x[j];
+#pragma unroll
+            for (int j = 0; j < NL; ++j) a.st_lag[k * 18 + j] = lag[j];
+            a.st_mc[k] = mc;
+            a.st_bad[k] = bad ? 1 : 0;
+        }
+    }
+    if (!last_slice) {   // hand the window block to its next slice
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicExch(a.progress + wb, slice + 1);
     }
     if (a.health.counters) {
         const int tb = __reduce_add_sync(0xffffffffu, n_bad), ts = __reduce_add_sync(0xffffffffu, n_sing);
@@ -839,7 +900,7 @@ se_kernel(const __grid_constant__ SeArgs<T> a) {
         double v = 0.0;
 #pragma unroll
         for (int w = 0; w < BLOCK / 32; ++w) v += red[w][tid];
-        a.partial[(long long)blockIdx.x * MAX_H + tid] = v;
+        a.partial[((long long)slice * (a.quanta > 1 ? a.nwblocks : 0) + wb) * MAX_H + tid] = v;
     }
 }
 

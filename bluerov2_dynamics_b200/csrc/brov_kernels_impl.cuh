@@ -148,7 +148,7 @@ template <typename T> int se_blocks(long long nwin) {
 
 template <typename T, int MODEL>
 static cudaError_t se_go(int integ, const SeArgs<T>& a, cudaStream_t st) {
-    const int nblocks = se_blocks<T>((a.nwin + a.wpt - 1) / a.wpt);
+    const int nblocks = se_blocks<T>((a.nwin + a.wpt - 1) / a.wpt) * (a.quanta > 1 ? a.quanta : 1);
     if (integ == INTEG_RK4) se_kernel<T, MODEL, INTEG_RK4><<<nblocks, ROLLOUT_BLOCK, 0, st>>>(a);
     else se_kernel<T, MODEL, INTEG_EULER><<<nblocks, ROLLOUT_BLOCK, 0, st>>>(a);
     return cudaGetLastError();
@@ -166,7 +166,8 @@ cudaError_t launch_se(int model, int integ, const SeArgs<T>& a, double* se_out, 
         case MODEL_DIQ13_U6: e = se_go<T, MODEL_DIQ13_U6>(integ, a, st); break;
     }
     if (e != cudaSuccess) return e;
-    se_finish_kernel<<<1, 256, 0, st>>>(a.partial, se_blocks<T>((a.nwin + a.wpt - 1) / a.wpt), se_out);
+    se_finish_kernel<<<1, 256, 0, st>>>(a.partial, se_blocks<T>((a.nwin + a.wpt - 1) / a.wpt) * (a.quanta > 1 ? a.quanta : 1),
+                                        se_out);
     return cudaGetLastError();
 }
 

@@ -433,7 +433,7 @@ class Engine:
     def multistep_se(self, X, U, horizons: Sequence[int], dt: float = 0.02, integrator: str = "rk4",
                      lag0=None, n_windows: Optional[int] = None, lag_mode: str = "reset", window0: int = 0,
                      row0: int = 0, se_out: Optional[torch.Tensor] = None, health_out: Optional[torch.Tensor] = None,
-                     singular_eps: float = 0.0, workspace: Optional[torch.Tensor] = None):
+                     singular_eps: float = 0.0, workspace: Optional[torch.Tensor] = None, time_slices: int = 0):
         """Sum of squared endpoint errors per horizon over sliding windows of one recorded series.
         Returns (se [MAX_H] float64 device tensor, counts list).  See brov_multistep_se in include/brov.h.
         lag_mode="carry" (thruster model, one horizon): the reference's literal semantics — the lag state left by
@@ -492,6 +492,7 @@ class Engine:
         d.workspace_dev = ws.data_ptr()
         d.workspace_bytes = nbytes
         d.lag_carry = int(carry)
+        d.time_slices = int(time_slices)      # 0: automatic (against the partial last wave), 1: off, 2..4: forced
         d.window0, d.row0 = (int(window0), int(row0)) if carry else (0, 0)
         if health_out is not None:
             if health_out.dtype != torch.int64 or health_out.device != self.device or health_out.numel() < 2:

@@ -273,7 +273,10 @@ typedef struct brov_se_desc {
      * when the series is a shard (rows before the shard's first window must then be present back to the replay depth,
      * brov_se_carry_rows). */
     int32_t lag_carry;
-    int32_t reserved;
+    /* time slices of the longest horizon (reset mode): 0 = automatic (against the partial last wave of window blocks,
+     * as brov_rollout_desc.time_slices), 1 = off, 2..4 forced.  The per-window results do not depend on it; the
+     * squared-error sums are added in another order (agreement to rounding, bit-reproducible for a given value). */
+    int32_t time_slices;
     long long window0;
     long long row0;
     /* optional health accounting as in brov_rollout_desc: windows whose endpoint error is not finite / that came within

@@ -44,3 +44,20 @@ evc = D.ShardedEvaluator(eng, X, U, HS, 0.02, "rk4", 0, 1, lag_mode="carry")
 ms_c = time_ev([evc])
 print(f"carry, three passes concurrent:       {ms_c:7.3f} ms  ({ms_c / ms_r:.3f} x reset)  rmse {evc.rmse()[0]}")
 print("back-to-back rmse", [e1.rmse()[0][0] for e1 in evs])
+
+# the 8-GPU shard of the same series on ONE GPU: 125,000 windows = 977 blocks on 296 resident slots = 3.3 rounds
+n8 = 125_000
+Xs, Us = X[:n8 + 100].contiguous(), U[:n8 + 100].contiguous()
+for q, label in ((1, "plain launch      "), (0, "automatic slicing "), (2, "2 slices          "), (3, "3 slices          "),
+                 (4, "4 slices          ")):
+    fn = lambda: eng.multistep_se(Xs, Us, HS, dt=0.02, integrator="rk4", n_windows=n8, time_slices=q)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(20):
+        se, _ = fn()
+    b.record()
+    torch.cuda.synchronize()
+    print(f"125,000 windows (1/8 shard), {label}: {a.elapsed_time(b) / 20:6.3f} ms  se {se.cpu().numpy()[:3]}")

@@ -501,3 +501,29 @@ def test_sharded_evaluator_matches_reference_golden(B, golden, use_graph):
         cnt = D.global_counts(len(X), HS)
         rs = [float(np.sqrt(tot[i] / (cnt[i] * 12))) for i in range(len(HS))]
         assert np.allclose(rs, golden[key], rtol=1e-10), (mode, rs)
+
+
+@pytest.mark.parametrize("model,nu", [("thruster8", 8), ("wrench12", 6)])
+def test_evaluator_time_slices_do_not_change_the_result(B, model, nu):
+    """Temporal tiling of the evaluator (brov_se_desc.time_slices): the windows' states pass through memory between
+    slices exactly, so forcing 2 / 3 / 4 slices, the automatic choice and the plain launch agree to summation order;
+    health counters included.  3000 windows = 24 blocks, ragged tail (the last windows run out of rows)."""
+    rng = np.random.default_rng(11)
+    T, hs = 3100, [1, 10, 100]
+    e = B.Engine(model, "f64")
+    U = rng.uniform(-0.3, 0.3, (T, nu)) * (1.0 if nu == 8 else np.array([20, 20, 20, 2, 2, 2.0]))
+    X = np.cumsum(rng.normal(0, 0.002, (T, 12)), axis=0)
+    X[:, 4] = np.clip(X[:, 4], -1.0, 1.0)
+    X[5, 4] = np.pi / 2 - 1e-4                  # one window starts next to the singularity: health counter
+    ref = None
+    for q in (1, 0, 2, 3, 4):
+        hc = torch.zeros(2, dtype=torch.int64, device="cuda")
+        se, cnt = e.multistep_se(X, U, hs, dt=DT, integrator="rk4", time_slices=q, health_out=hc, singular_eps=1e-3)
+        got = (se.cpu().numpy()[:3], cnt, hc.cpu().numpy().tolist())
+        if ref is None:
+            ref = got
+            assert ref[2][1] >= 1 and np.all(np.isfinite(ref[0]))
+        assert got[1] == ref[1] and got[2] == ref[2], (q, got, ref)
+        assert np.allclose(got[0], ref[0], rtol=1e-13, atol=0), (q, got[0], ref[0])
+    with pytest.raises(Exception):
+        e.multistep_se(X, U, hs, dt=DT, time_slices=9)

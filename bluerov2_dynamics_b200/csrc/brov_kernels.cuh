@@ -33,6 +33,7 @@ constexpr int ROLLOUT_BLOCK = 128;
 // the prefetch path, but 12 instead of 8 warps per SM bought 2 % (wrench12) / 6 % (quat13) and cost the Monte-Carlo
 // kernel 30 % in spills (profiles/r02i_tune_variants.txt): they are bound by dependent-issue latency inside a stage,
 // not by the number of warps.
+// (fp32 Monte-Carlo kernel with 160 / 192 registers: 2.9995 / 2.9292 ms against 2.9848 ms at 128, r02t)
 template <typename T> struct MaxReg { static constexpr int N = sizeof(T) == 8 ? 255 : 128; };
 // Which streamed-input path a kernel is built with (measured on B200, profiles/r02f / r02g_tune_variants.txt; ms per 100 RK4
 // steps, 65,536 fp64 / 1,048,576 fp32 vehicles, TMA ring vs register prefetch): wrench12 fp64 0.386 / 0.432, quat13 fp64

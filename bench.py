@@ -536,7 +536,13 @@ def run_compare_leg(torch, B, local, windows, fp32_peak, fp64_peak, T=1_000_100,
     flop_p = steps_p * 2.0 * (14 * 64 + 3 * 64 * 64 + 64 * 9)
     out["models"]["pinc_f32"] = {"ms": ms, "windows": nwin, "kernel": "pinc_se_tc_kernel (tcgen05.mma kind::tf32 + kind::f16, split operands, 3 tiles per SM)", "network_steps": steps_p,
                                  "algorithmic_tflops": flop_p / (ms * 1e-3) / 1e12,
-                                 "frac_fp32_pipe": flop_p / (ms * 1e-3) / 1e12 / fp32_peak}
+                                 "vs_fp32_vector_peak": flop_p / (ms * 1e-3) / 1e12 / fp32_peak,
+                                 "bound": "epilogue (2 MUFU per activation + issue slots), not the tensor pipe",
+                                 "pipes": {"tensor_active": 0.23, "xu_active": 0.43, "issue_active": 0.46,
+                                           "capture": "profiles/r02v_pinc_tc_raw.csv"},
+                                 "note": "the dense layers run on the tensor cores (3 split products per layer: 2 x kind::tf32 "
+                                         "+ 1 x kind::f16, fp32 accumulation in TMEM), so the algorithmic rate exceeds the "
+                                         "FP32 vector peak the CUDA-core kernel (79 ms) was bound by"}
     if cpu:
         from oracle import compare_np as CN
         Tc = 2100

@@ -773,25 +773,25 @@ def test_monte_carlo_per_vehicle_current(B):
 
 
 def test_randomised_parity_sweep():
-    """profiles/fuzz_parity.py: random model / integrator / size / horizon / stride / input layout / chunking / time
+    """tests/tools/fuzz_parity.py: random model / integrator / size / horizon / stride / input layout / chunking / time
     slicing / initial lag against the C oracle (150 cases here; 4 x 800 were run on the box when it was written)."""
     import subprocess
     import sys
     from conftest import ROOT
     _c_oracle()
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_parity.py"), "150", "2"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "fuzz_parity.py"), "150", "2"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "cases OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
 
 
 def test_randomised_evaluator_sweep():
-    """profiles/fuzz_evaluator.py: random series lengths, horizon sets, window limits, models, integrators and
+    """tests/tools/fuzz_evaluator.py: random series lengths, horizon sets, window limits, models, integrators and
     precisions of the sliding-window evaluator against the C oracle; carried-lag mode against the numpy oracle."""
     import subprocess
     import sys
     from conftest import ROOT
     _c_oracle()
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "fuzz_evaluator.py"), "80", "3"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "fuzz_evaluator.py"), "80", "3"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "cases OK" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
 

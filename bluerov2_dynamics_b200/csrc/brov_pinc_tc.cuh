@@ -112,9 +112,11 @@ __device__ __forceinline__ void tc_bar_init(uint32_t bar) {
 __device__ __forceinline__ void tc_bar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        // with a suspend-time hint the warp sleeps in hardware instead of polling (the polling loop was 7 % of the
+        // issued instructions, r02v)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
                      : "=r"(ok)
-                     : "r"(bar), "r"(parity)
+                     : "r"(bar), "r"(parity), "r"(4000u)
                      : "memory");
     } while (!ok);
 }
@@ -198,31 +200,32 @@ __device__ __forceinline__ void tc_put_inputs(const TcCtx& c, const float* x9, f
 }
 
 // One layer's products, issued by ONE thread after the tile's threads have synchronised on the freshly written A.
-__device__ __forceinline__ void tc_issue_layer(const TcCtx& c, int whi_off, int wlo_off, int w16_off, int K, int N) {
-    const uint32_t lbo = (uint32_t)(N / 8) * 128;      // K-chunk stride in bytes, both operand widths
-    const uint32_t whi = tc_smem(c.sw + whi_off), wlo = tc_smem(c.sw + wlo_off), w16 = tc_smem(c.sw + w16_off);
-    const uint32_t id32 = tc_idesc(TC_M, N, true), id16 = tc_idesc(TC_M, N, false);
-    bool acc = false;
-#pragma unroll 1
-    for (int prod = 0; prod < 2; ++prod) {
-        const uint32_t b0 = prod ? wlo : whi;
-        for (int k8 = 0; k8 < K / 8; ++k8) {
-            tc_mma_tf32(c.tm0, c.tm0 + 64 + 8 * k8, tc_desc(b0 + k8 * 2 * lbo, lbo, 128), id32, acc);
-            acc = true;
-        }
-    }
-    for (int k16 = 0; k16 < K / 16; ++k16)
-        tc_mma_f16(c.tm0, c.tm0 + 128 + 8 * k16, tc_desc(w16 + k16 * 2 * lbo, lbo, 128), id16);
+// K, N are compile-time: the loop unrolls into 20 (hidden layers) tcgen05.mma with descriptors that differ by an
+// add on the address field.
+template <int K, int N>
+__device__ __forceinline__ void tc_issue_layer(const TcCtx& c, int whi_off, int wlo_off, int w16_off) {
+    constexpr uint32_t lbo = (uint32_t)(N / 8) * 128;      // K-chunk stride in bytes, both operand widths
+    constexpr uint32_t id32 = tc_idesc(TC_M, N, true), id16 = tc_idesc(TC_M, N, false);
+    constexpr uint64_t step = (uint64_t)((2 * lbo) >> 4);  // two K chunks per instruction, in descriptor address units
+    const uint64_t dhi = tc_desc(tc_smem(c.sw + whi_off), lbo, 128), dlo = tc_desc(tc_smem(c.sw + wlo_off), lbo, 128),
+                   d16 = tc_desc(tc_smem(c.sw + w16_off), lbo, 128);
+#pragma unroll
+    for (int k8 = 0; k8 < K / 8; ++k8) tc_mma_tf32(c.tm0, c.tm0 + 64 + 8 * k8, dhi + k8 * step, id32, k8 > 0);
+#pragma unroll
+    for (int k8 = 0; k8 < K / 8; ++k8) tc_mma_tf32(c.tm0, c.tm0 + 64 + 8 * k8, dlo + k8 * step, id32, true);
+#pragma unroll
+    for (int k16 = 0; k16 < K / 16; ++k16) tc_mma_f16(c.tm0, c.tm0 + 128 + 8 * k16, d16 + k16 * step, id16);
     tc_commit(c.bar);
 }
 // Starts one layer for the tile: every thread has stored its row of A; the tile's first thread issues the MMAs.
-__device__ __forceinline__ void tc_layer_start(const TcCtx& c, int whi_off, int wlo_off, int w16_off, int K, int N) {
+template <int K, int N>
+__device__ __forceinline__ void tc_layer_start(const TcCtx& c, int whi_off, int wlo_off, int w16_off) {
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     asm volatile("bar.sync %0, %1;" ::"r"(1 + c.tile), "r"(TC_M) : "memory");     // the tile's 128 threads
     if (c.row == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tc_issue_layer(c, whi_off, wlo_off, w16_off, K, N);
+        tc_issue_layer<K, N>(c, whi_off, wlo_off, w16_off);
     }
 }
 // Returns with the layer's accumulators readable (and its A overwritable).
@@ -279,16 +282,16 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcCtx& c, int layer, co
 // every thread has stored its row of layer 0's A (tc_put_inputs); on return the OUTPUT layer's MMAs are in flight:
 // call tc_layer_wait, then tc_residual.  Every thread of the tile must call it (tile-wide barriers inside).
 __device__ __forceinline__ void pinc_net_tc(TcCtx& c, const TcAct& act) {
-    tc_layer_start(c, TC_L0_HI, TC_L0_LO, TC_H16_L0, 16, HID);
+    tc_layer_start<16, HID>(c, TC_L0_HI, TC_L0_LO, TC_H16_L0);
     tc_layer_wait(c);
     tc_hidden_epilogue(c, 0, act);
 #pragma unroll 1
     for (int l = 1; l <= 3; ++l) {
-        tc_layer_start(c, TC_L1 + (l - 1) * 8192, TC_L1 + (l - 1) * 8192 + 4096, TC_H16_L1 + (l - 1) * 2048, HID, HID);
+        tc_layer_start<HID, HID>(c, TC_L1 + (l - 1) * 8192, TC_L1 + (l - 1) * 8192 + 4096, TC_H16_L1 + (l - 1) * 2048);
         tc_layer_wait(c);
         tc_hidden_epilogue(c, l, act);
     }
-    tc_layer_start(c, TC_L4_HI, TC_L4_LO, TC_H16_L4, HID, 16);
+    tc_layer_start<HID, 16>(c, TC_L4_HI, TC_L4_LO, TC_H16_L4);
 }
 // residual update from the output layer's accumulators: body-frame (dx, dy) rotated by the CURRENT yaw; (cos, sin)
 // re-normalised (:639-673).  z = the 9 network states the step started from.

@@ -631,8 +631,6 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
     a.n = (int)d->n; a.steps = (int)d->steps; a.stride = (int)(d->traj_dev ? d->stride : 1);
     const size_t ualign = (sizeof(T) == 4 && NU == 6) ? 8 : 16;
     a.u_vec = !gen && aligned(d->u_dev, ualign) && (d->u_stride_t * sizeof(T)) % ualign == 0 && (d->u_stride_n * sizeof(T)) % ualign == 0;
-    // per-vehicle time-major series with 16-byte aligned rows of 32 vehicles: the TMA bulk ring
-    a.u_tma = !gen && d->u_stride_n == NU && d->u_stride_t > 0 && aligned(d->u_dev, 16) && (d->u_stride_t * sizeof(T)) % 16 == 0;
     a.traj_vec = d->traj_dev && aligned(d->traj_dev, 16) && ((size_t)d->n * NX * sizeof(T)) % 16 == 0;
 
     // lag state.  The thruster model integrates the allocation-projected filters; per-thruster states for the caller

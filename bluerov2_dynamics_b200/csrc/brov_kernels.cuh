@@ -35,14 +35,13 @@ constexpr int ROLLOUT_BLOCK = 128;
 // not by the number of warps.
 // (fp32 Monte-Carlo kernel with 160 / 192 registers: 2.9995 / 2.9292 ms against 2.9848 ms at 128, r02t)
 template <typename T> struct MaxReg { static constexpr int N = sizeof(T) == 8 ? 255 : 128; };
-// Which streamed-input path a kernel is built with (measured on B200, profiles/r02f / r02g_tune_variants.txt; ms per 100 RK4
-// steps, 65,536 fp64 / 1,048,576 fp32 vehicles, TMA ring vs register prefetch): wrench12 fp64 0.386 / 0.432, quat13 fp64
-// 0.369 / 0.424, Monte-Carlo fp32 2.94 / 3.07 (wrench12) and 3.15 / 3.51 (quat13) — the ring wins where the step
-// leaves registers for the compiler to schedule with; thruster8 fp64 0.551 / 0.485 and fp32 3.36 / 3.03, wrench12
-// fp32 2.48 / 2.40 — the barrier at the top of the loop costs more than the prefetch registers.
-template <typename T, int MODEL, bool PV> struct UseTma {
-    static constexpr bool V = sizeof(T) == 8 ? MODEL != MODEL_THRUSTER8 : PV;
-};
+// Streamed inputs: every kernel prefetches the next step's command row into registers, requested between stages 2 and 3
+// of the current step (LateSide, brov_device.cuh).  A per-warp TMA bulk-copy ring (cp.async.bulk + mbarrier, 4 steps
+// ahead) was the input path of the lag-free fp64 and the fp32 Monte-Carlo kernels for most of round 2 — it beat a
+// prefetch issued at the TOP of the step by 12-15 % there (r02g) — and was removed when the mid-step prefetch beat it
+// in turn on every kernel (r02t batch 4, per launch: quat13 fp64 3.235 -> 3.034 ms, wrench12 fp64 3.281 -> 3.225 ms,
+// Monte-Carlo fp64 0.442 -> 0.430 ms, Monte-Carlo fp32 2.987 -> 2.621 ms): the barrier wait at the top of the loop
+// costs more than 16 registers held for half a step.
 // where the per-vehicle coefficient table lives during a launch: fp32 registers, fp64 shared memory [36][BLOCK]
 template <typename T, bool PV> struct PvInRegs { static constexpr bool V = PV && sizeof(T) == 4; };
 
@@ -71,7 +70,6 @@ template <typename T> struct RolloutArgs {
     long long step0;    // global index of the first step of this launch
     int n, steps, stride;
     int u_vec, traj_vec;
-    int u_tma;          // inputs are the per-vehicle time-major layout, 16-byte aligned: TMA bulk ring
     int lag_in_w;       // lag_in holds allocation-projected states [n][6][3]
     int mincos_init;    // 1: ignore the incoming mincos values (first chunk)
     int gen_snap_step;
@@ -157,64 +155,6 @@ __device__ __forceinline__ void load_u(const T* __restrict__ p, bool vec, T* __r
     } else {
 #pragma unroll
         for (int i = 0; i < NU; ++i) u[i] = STREAM ? __ldcs(p + i) : __ldg(p + i);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// per-warp input ring filled by the TMA engine: one cp.async.bulk per warp and step moves the warp's 32 input rows
-// (contiguous in the time-major per-vehicle layout [T][N][NU]) global -> shared, completion on an mbarrier.
-// No register staging, no load scoreboard in the step: the r02a capture showed the register prefetch (LDG into
-// registers one step ahead) costing the wrench fp64 kernel 20 % of its cycles in long-scoreboard stalls because the
-// loads shared a scoreboard with the first shared-memory constant load of the step.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int U_STAGES = 4;   // steps in flight per warp (2 measured the same: the ring is never the bottleneck)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-// arm the barrier with the byte count, then start the bulk copy that completes on it (bytes % 16 == 0, 16 B aligned)
-// No "memory" clobbers on the ring's instructions: the ring is only ever touched through volatile asm (these and
-// load_u_smem), which the compiler keeps in program order among themselves; a clobber would also pin every ordinary
-// shared-memory load of the step — the fp64 constant block — behind the wait at the top of the loop, and the r02e
-// capture showed exactly that as short-scoreboard stalls all over the step (5.11 against 4.51 ms per 1000 steps).
-__device__ __forceinline__ void tma_load_1d(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-                 "l"(src_gmem), "r"(bytes), "r"(bar));
-}
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(ok)
-                     : "r"(addr), "r"(parity));
-    } while (!ok);
-}
-// warp barrier WITHOUT compiler memory-fence semantics (__syncwarp() has them and would keep the step's constant
-// loads from moving across the top of the loop): all the ring needs is that every lane has executed its reads of a
-// slot — volatile asm, in program order before this — when lane 0 hands the slot back to the TMA engine
-__device__ __forceinline__ void warp_sync_nofence() { asm volatile("bar.warp.sync 0xffffffff;"); }
-// this lane's input row out of a ring slot; `row` is a 32-bit shared-window address (one register, no generic
-// pointer arithmetic in the step loop)
-template <typename T, int NU>
-__device__ __forceinline__ void load_u_smem(uint32_t row, T* __restrict__ u) {
-    if constexpr (sizeof(T) == 8) {
-#pragma unroll
-        for (int j = 0; j < NU / 2; ++j)
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(u[2 * j]), "=d"(u[2 * j + 1]) : "r"(row + 16 * j));
-    } else if constexpr (NU % 4 == 0) {
-#pragma unroll
-        for (int j = 0; j < NU / 4; ++j)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(u[4 * j]), "=f"(u[4 * j + 1]), "=f"(u[4 * j + 2]), "=f"(u[4 * j + 3]) : "r"(row + 16 * j));
-    } else {   // fp32, 6 inputs: 24-byte rows
-#pragma unroll
-        for (int j = 0; j < NU / 2; ++j)
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[2 * j]), "=f"(u[2 * j + 1]) : "r"(row + 8 * j));
     }
 }
 
@@ -390,26 +330,14 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     const int warp_n = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem));   // live vehicles of this warp
     const int n_valid = warp_n * NX;
 
-    // Inputs of the step, one of three sources:
+    // Inputs of the step, one of two sources:
     //  GEN       generated in the kernel: gs is the AR(1) state of the command signal, the deviates of the next step
     //            are drawn between the stages of the current one (GenSide);
-    //  TMA ring  per-vehicle time-major series, 16-byte aligned: the warp's rows of step k are one contiguous block,
-    //            fetched U_STAGES - 1 steps ahead by the TMA engine into the warp's shared-memory ring (kernels
-    //            chosen by UseTma; unaligned / shared / constant layouts fall back to plain loads, L1 hits);
-    //  prefetch  every layout, next step's row loaded into registers one step ahead (the other kernels).
+    //  prefetch  any layout: the next step's row is requested into registers between stages 2 and 3 of the current
+    //            step (LateSide).
     T u[NU];
-    constexpr bool TMA = !GEN && UseTma<T, MODEL, PV>::V;
-    constexpr bool PREFETCH = !GEN && !TMA;
-    constexpr uint32_t ROW_BYTES = NU * sizeof(T);
-    constexpr uint32_t SLOT_BYTES = 32 * ROW_BYTES;
-    __shared__ __align__(8) uint64_t u_bar[TMA ? BLOCK / 32 : 1][U_STAGES];
-    const uint32_t ring = smem_u32(tiles + (a.traj ? BLOCK * NX : 0) + warp * (U_STAGES * 32 * NU));   // shared-window address
-    const uint32_t bars = smem_u32(&u_bar[TMA ? warp : 0][0]);
-    const uint32_t warp_bytes = (uint32_t)warp_n * ROW_BYTES;
-    const bool tma = TMA && a.u_tma && warp_n > 0 && (warp_bytes % 16u) == 0;   // uniform per warp
+    constexpr bool PREFETCH = !GEN;
     const T* up = a.U + i * a.u_stride_n + (long long)k_begin * a.u_stride_t;
-    const T* wsrc = a.U + warp_v0 * NU + (long long)k_begin * a.u_stride_t;     // row of the warp's first vehicle
-    const uint32_t myrow = ring + (uint32_t)(lane < warp_n ? lane : (warp_n > 0 ? warp_n - 1 : 0)) * ROW_BYTES;
     const bool uvec = a.u_vec != 0;
     const bool stream = a.u_stride_n != 0;  // per-vehicle inputs are read exactly once: evict-first
     float gs[GEN ? NU : 1];
@@ -417,18 +345,6 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
         const T* ssrc = slice > 0 ? a.gen.state_out : a.gen.state_in;
 #pragma unroll
         for (int j = 0; j < NU; ++j) gs[j] = ssrc ? (float)__ldcg(ssrc + i * NU + j) : 0.0f;
-    } else if constexpr (TMA) {
-        if (tma) {
-            if (lane == 0) {
-#pragma unroll
-                for (int s = 0; s < U_STAGES; ++s) mbar_init(bars + 8 * s, 1);
-                mbar_init_fence();
-#pragma unroll
-                for (int s = 0; s < U_STAGES - 1; ++s)
-                    if (s < nsteps) tma_load_1d(ring + s * SLOT_BYTES, wsrc + (long long)s * a.u_stride_t, warp_bytes, bars + 8 * s);
-            }
-            __syncwarp();
-        }
     } else if (nsteps > 0) {
         if (stream) load_u<T, NU, true>(up, uvec, u); else load_u<T, NU, false>(up, uvec, u);
     }
@@ -456,19 +372,6 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
 #pragma unroll
             for (int j = 0; j < NU; ++j) u[j] = T(gs[j]);
             side.start(veh, gstep0 + k + 1, k + 1 < nsteps);
-        } else if constexpr (TMA) {
-            if (tma) {
-                // refill the slot read one step ago (every lane has executed those reads: they precede the last step)
-                const int kn = k + U_STAGES - 1;
-                warp_sync_nofence();
-                if (lane == 0 && kn < nsteps)
-                    tma_load_1d(ring + (kn % U_STAGES) * SLOT_BYTES, wsrc + (long long)kn * a.u_stride_t, warp_bytes,
-                                bars + 8 * (kn % U_STAGES));
-                mbar_wait(bars + 8 * (k % U_STAGES), (uint32_t)(k / U_STAGES) & 1u);
-                load_u_smem<T, NU>(myrow + (k % U_STAGES) * SLOT_BYTES, u);
-            } else {
-                load_u<T, NU, false>(up + (long long)k * a.u_stride_t, uvec, u);
-            }
         }
 
         T acth;

@@ -5,20 +5,18 @@
 
 namespace brov {
 
-// dynamic shared memory of a rollout launch: [fp64 per-vehicle coefficient table][snapshot tiles][TMA input ring]
-template <typename T, int MODEL, bool PV> static size_t rollout_smem(bool traj, bool ring) {
+// dynamic shared memory of a rollout launch: [fp64 per-vehicle coefficient table][snapshot tiles]
+template <typename T, int MODEL, bool PV> static size_t rollout_smem(bool traj) {
     constexpr int NX = ModelDim<MODEL>::NX;
-    constexpr int NU = ModelDim<MODEL>::NU;
     size_t smem = traj ? (size_t)ROLLOUT_BLOCK * NX * sizeof(T) : 0;
     if (PV && !PvInRegs<T, PV>::V) smem += (size_t)KP_COUNT * ROLLOUT_BLOCK * sizeof(T);
-    if (ring && UseTma<T, MODEL, PV>::V) smem += (size_t)ROLLOUT_BLOCK * U_STAGES * NU * sizeof(T);
     return smem;
 }
 
 template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
 static cudaError_t rollout_launch(const RolloutArgs<T>& a, cudaStream_t st) {
     const int grid = ((a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK) * (a.quanta > 1 ? a.quanta : 1);
-    const size_t smem = rollout_smem<T, MODEL, PV>(a.traj != nullptr, !GEN && a.u_tma);
+    const size_t smem = rollout_smem<T, MODEL, PV>(a.traj != nullptr);
     auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN>;
     if (smem > 16 * 1024) {
         // static + dynamic shared memory beyond 48 KB needs the opt-in (the fp64 coefficient table alone is 36 KB)
@@ -37,9 +35,9 @@ static cudaError_t rollout_launch(const RolloutArgs<T>& a, cudaStream_t st) {
 // resident blocks per SM of the kernel that launch_rollout would pick (for the temporal-tiling heuristic)
 template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
 static int rollout_occ(bool traj) {
-    int nb = 0;   // streamed inputs are assumed to take the TMA ring (the layout worth tuning the launch shape for)
+    int nb = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN>,
-                                                                  ROLLOUT_BLOCK, rollout_smem<T, MODEL, PV>(traj, !GEN));
+                                                                  ROLLOUT_BLOCK, rollout_smem<T, MODEL, PV>(traj));
     return e == cudaSuccess ? nb : 0;
 }
 

@@ -125,13 +125,13 @@ def _rollout_mixed(B, e, x0, U, z0):
     return lag
 
 
-# ------------------------------------------------------------------------------------------------ TMA input ring
+# ------------------------------------------------------------------------------------------------ input load paths
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 @pytest.mark.parametrize("kind,nu", [("thruster8", 8), ("wrench12", 6)])
-def test_tma_input_ring_equals_plain_loads(B, dtype, kind, nu):
-    """Per-vehicle time-major inputs go through the per-warp cp.async.bulk ring; a view shifted by one scalar is not
-    16-byte aligned and takes the plain-load path.  Same bits, for ragged ensembles (partial warps, odd counts of
-    24-byte rows), horizons around the ring depth, and time-sliced launches."""
+def test_vector_input_loads_equal_scalar_loads(B, dtype, kind, nu):
+    """Aligned per-vehicle time-major inputs are prefetched with 128-bit loads; a view shifted by one scalar is not
+    16-byte aligned and takes the scalar-load path.  Same bits, for ragged ensembles (partial warps, odd counts of
+    24-byte rows), short horizons, and time-sliced launches."""
     e = B.Engine(kind, dtype)
     rng = np.random.default_rng(8)
     for n, T in ((1, 1), (31, 2), (33, 3), (97, 4), (129, 5), (1000, 9), (4097, 37)):

@@ -541,14 +541,16 @@ __device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restr
 //   Fu      THRUSTER8 -> static thrust F[8] of this step (alloc*F[6] when LAGW); wrench models -> commanded wrench;
 //           double-integrator models -> accelerations
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int MODEL, bool LAG1, bool LAGW, class P>
+// CU = false: built for "no ocean current" — the relative-velocity block and its (uniform) branch are not in the code at
+// all.  The branch alone, four times per step, costs the rollout kernels 1-4 % (r02t batch 6).
+template <typename T, int MODEL, bool LAG1, bool LAGW, class P, bool CU = true>
 __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int substep, const T* __restrict__ x,
                                           const Trig<T>& tr, const T* __restrict__ lag, const T* __restrict__ Fu,
                                           T* __restrict__ xd, T* __restrict__ lagd) {
     if constexpr (MODEL == MODEL_THRUSTER8) {
         T tau[6];
         thruster_tau<T, LAGW>(c, substep, lag, Fu, tau);
-        rhs_euler12<T>(x, tr, tau, p, c.has_current != 0, xd);
+        rhs_euler12<T>(x, tr, tau, p, CU && c.has_current != 0, xd);
     } else if constexpr (MODEL == MODEL_DIQ13_U6) {
         rhs_diq13<T>(x, Fu, xd);
     } else if constexpr (ModelDim<MODEL>::DI) {
@@ -562,8 +564,8 @@ __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int su
             for (int i = 0; i < 6; ++i) { tl[i] = lag[i]; lagd[i] = (Fu[i] - tl[i]) * il; }
             tau = tl;
         }
-        if constexpr (MODEL == MODEL_WRENCH12) rhs_euler12<T>(x, tr, tau, p, c.has_current != 0, xd);
-        else rhs_quat13<T>(x, tau, p, c.has_current != 0, xd);
+        if constexpr (MODEL == MODEL_WRENCH12) rhs_euler12<T>(x, tr, tau, p, CU && c.has_current != 0, xd);
+        else rhs_quat13<T>(x, tau, p, CU && c.has_current != 0, xd);
     }
 }
 
@@ -720,7 +722,7 @@ struct NoSide {
 //           vehicle is to the singularity of the Euler-rate kinematics (fossen/BlueROV2.py:43-62)
 // ---------------------------------------------------------------------------------------------------------------
 //   side    work to interleave with the step (GenSide: the next step's input deviates; NoSide: nothing)
-template <typename T, int MODEL, int INTEG, bool LAG1, class P, class SIDE>
+template <typename T, int MODEL, int INTEG, bool LAG1, class P, class SIDE, bool CU = true>
 __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T* __restrict__ x, T* __restrict__ lag,
                                                const T* __restrict__ u, T& abs_cth, SIDE& side) {
     constexpr int NX = ModelDim<MODEL>::NX;
@@ -747,7 +749,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
     if constexpr (EULER_ANGLES) trig_full<T>(c, x + 3, tr0);
     abs_cth = (EULER_ANGLES && !ModelDim<MODEL>::DI) ? abs_(tr0.cth) : T(1);
     if constexpr (INTEG == INTEG_EULER) {
-        model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, 0, x, tr0, lag, Fu, k, kl);
+        model_rhs<T, MODEL, LAG1, LAGW, P, CU>(c, p, 0, x, tr0, lag, Fu, k, kl);
         side.all();
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] += dt * k[i];
@@ -761,7 +763,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
         const T hdt = T(0.5) * dt;
         Trig<T> trs;
         T dang[3];
-        model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, 0, x, tr0, lag, Fu, k, kl);
+        model_rhs<T, MODEL, LAG1, LAGW, P, CU>(c, p, 0, x, tr0, lag, Fu, k, kl);
 #pragma unroll
         for (int s = 1; s <= 3; ++s) {
             side.work(s - 1);
@@ -784,7 +786,7 @@ __device__ __forceinline__ void integrate_step(const Consts<T>& c, const P& p, T
                 for (int i = 0; i < 3; ++i) dang[i] = h * k[3 + i];
                 trig_stage(c, tr0, dang, xs + 3, trs);
             }
-            model_rhs<T, MODEL, LAG1, LAGW, P>(c, p, s, xs, trs, LAG1 ? ls : lag, Fu, k, kl);
+            model_rhs<T, MODEL, LAG1, LAGW, P, CU>(c, p, s, xs, trs, LAG1 ? ls : lag, Fu, k, kl);
         }
         side.work(3);
         const T dt6 = dt * T(1.0 / 6.0);

@@ -233,7 +233,7 @@ __device__ __forceinline__ void count_health(const Health& h, bool bad, bool nea
 }
 
 // GEN: the inputs are generated in the kernel (gen_advance) instead of being read from a.U
-template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN, bool CU>
 __global__ void __launch_bounds__(ROLLOUT_BLOCK) __maxnreg__(MaxReg<T>::N)
 rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
     constexpr int BLOCK = ROLLOUT_BLOCK;
@@ -379,9 +379,9 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
             const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
             auto pf = [&]() { if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un); };
             LateSide<decltype(pf)> late{pf, 1};
-            integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth, late);
+            integrate_step<T, MODEL, INTEG, LAG1, decltype(p), decltype(late), CU>(cc, p, x, lag, u, acth, late);
         } else {
-            integrate_step<T, MODEL, INTEG, LAG1, decltype(p)>(cc, p, x, lag, u, acth, side);
+            integrate_step<T, MODEL, INTEG, LAG1, decltype(p), decltype(side), CU>(cc, p, x, lag, u, acth, side);
         }
         mc = fminf(mc, (float)acth);
 
@@ -918,7 +918,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T>
 cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st);
-template <typename T> int rollout_blocks_per_sm(int model, int integ, bool lag1, bool pv, bool gen, bool traj);
+template <typename T> int rollout_blocks_per_sm(int model, int integ, bool lag1, bool pv, bool gen, bool traj, bool cur);
 template <typename T> cudaError_t launch_lag_tail(const LagTailArgs<T>& a, cudaStream_t st);
 template <typename T> cudaError_t launch_gen_inputs(int nu, const GenInputsArgs<T>& a, cudaStream_t st);
 template <typename T>

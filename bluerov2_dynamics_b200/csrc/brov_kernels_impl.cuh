@@ -13,11 +13,11 @@ template <typename T, int MODEL, bool PV> static size_t rollout_smem(bool traj) 
     return smem;
 }
 
-template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN, bool CU>
 static cudaError_t rollout_launch(const RolloutArgs<T>& a, cudaStream_t st) {
     const int grid = ((a.n + ROLLOUT_BLOCK - 1) / ROLLOUT_BLOCK) * (a.quanta > 1 ? a.quanta : 1);
     const size_t smem = rollout_smem<T, MODEL, PV>(a.traj != nullptr);
-    auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN>;
+    auto kern = rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN, CU>;
     if (smem > 16 * 1024) {
         // static + dynamic shared memory beyond 48 KB needs the opt-in (the fp64 coefficient table alone is 36 KB)
         cudaFuncAttributes fa;
@@ -33,21 +33,30 @@ static cudaError_t rollout_launch(const RolloutArgs<T>& a, cudaStream_t st) {
 }
 
 // resident blocks per SM of the kernel that launch_rollout would pick (for the temporal-tiling heuristic)
-template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN>
+template <typename T, int MODEL, int INTEG, bool LAG1, bool PV, bool GEN, bool CU>
 static int rollout_occ(bool traj) {
     int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN>,
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rollout_kernel<T, MODEL, INTEG, LAG1, PV, GEN, CU>,
                                                                   ROLLOUT_BLOCK, rollout_smem<T, MODEL, PV>(traj));
     return e == cudaSuccess ? nb : 0;
 }
 
 // runtime -> template dispatch; F is a generic lambda called with std::integral_constant tags
 template <typename T, class F>
-static auto rollout_dispatch(int model, int integ, bool lag1, bool pv, bool gen, F&& f) {
+static auto rollout_dispatch(int model, int integ, bool lag1, bool pv, bool gen, bool cur, F&& f) {
+    // CU tag: false = the "no ocean current" build of a streamed-input Fossen kernel (RolloutExists), true = the flag is
+    // read at run time
     auto with_flags = [&](auto M, auto L1) {
         auto with_integ = [&](auto I) {
-            if (pv) return gen ? f(M, I, L1, std::true_type{}, std::true_type{}) : f(M, I, L1, std::true_type{}, std::false_type{});
-            return gen ? f(M, I, L1, std::false_type{}, std::true_type{}) : f(M, I, L1, std::false_type{}, std::false_type{});
+            auto with_cur = [&](auto PV, auto G) {
+                constexpr bool has_nocur = !decltype(G)::value && !ModelDim<decltype(M)::value>::DI;
+                if constexpr (has_nocur) {
+                    if (!cur) return f(M, I, L1, PV, G, std::false_type{});
+                }
+                return f(M, I, L1, PV, G, std::true_type{});
+            };
+            if (pv) return gen ? with_cur(std::true_type{}, std::true_type{}) : with_cur(std::true_type{}, std::false_type{});
+            return gen ? with_cur(std::false_type{}, std::true_type{}) : with_cur(std::false_type{}, std::false_type{});
         };
         return integ == INTEG_RK4 ? with_integ(std::integral_constant<int, INTEG_RK4>{})
                                   : with_integ(std::integral_constant<int, INTEG_EULER>{});
@@ -72,11 +81,12 @@ static auto rollout_dispatch(int model, int integ, bool lag1, bool pv, bool gen,
 template <int MODEL, bool PV> struct RolloutExists { static constexpr bool V = !(PV && ModelDim<MODEL>::DI); };
 
 template <typename T>
-int rollout_blocks_per_sm(int model, int integ, bool lag1, bool pv, bool gen, bool traj) {
+int rollout_blocks_per_sm(int model, int integ, bool lag1, bool pv, bool gen, bool traj, bool cur) {
     if (model < MODEL_THRUSTER8 || model > MODEL_DIQ13_U6) return 0;
-    return rollout_dispatch<T>(model, integ, lag1, pv, gen, [&](auto M, auto I, auto L1, auto PV, auto G) -> int {
+    return rollout_dispatch<T>(model, integ, lag1, pv, gen, cur, [&](auto M, auto I, auto L1, auto PV, auto G, auto CU) -> int {
         if constexpr (RolloutExists<decltype(M)::value, decltype(PV)::value>::V)
-            return rollout_occ<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value>(traj);
+            return rollout_occ<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value,
+                               decltype(CU)::value>(traj);
         else
             return 0;
     });
@@ -86,10 +96,11 @@ template <typename T>
 cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st) {
     if (a.n <= 0 || a.steps <= 0) return cudaSuccess;
     if (model < MODEL_THRUSTER8 || model > MODEL_DIQ13_U6) return cudaErrorInvalidValue;
-    return rollout_dispatch<T>(model, integ, lag1, a.pv != nullptr, a.gen.on != 0,
-                               [&](auto M, auto I, auto L1, auto PV, auto G) -> cudaError_t {
+    return rollout_dispatch<T>(model, integ, lag1, a.pv != nullptr, a.gen.on != 0, a.c.has_current != 0,
+                               [&](auto M, auto I, auto L1, auto PV, auto G, auto CU) -> cudaError_t {
         if constexpr (RolloutExists<decltype(M)::value, decltype(PV)::value>::V)
-            return rollout_launch<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value>(a, st);
+            return rollout_launch<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value,
+                                  decltype(CU)::value>(a, st);
         else
             return cudaErrorInvalidValue;
     });
@@ -200,7 +211,7 @@ cudaError_t launch_thruster_series(const ThrusterSeriesArgs<T>& a, cudaStream_t 
 
 #define BROV_INSTANTIATE(T)                                                                                         \
     template cudaError_t launch_rollout<T>(int, int, bool, const RolloutArgs<T>&, cudaStream_t);                   \
-    template int rollout_blocks_per_sm<T>(int, int, bool, bool, bool, bool);                                      \
+    template int rollout_blocks_per_sm<T>(int, int, bool, bool, bool, bool, bool);                                      \
     template cudaError_t launch_lag_tail<T>(const LagTailArgs<T>&, cudaStream_t);                                  \
     template cudaError_t launch_gen_inputs<T>(int, const GenInputsArgs<T>&, cudaStream_t);                         \
     template cudaError_t launch_rhs<T>(int, bool, const RhsArgs<T>&, cudaStream_t);                                \

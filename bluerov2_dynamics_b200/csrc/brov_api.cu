@@ -663,7 +663,7 @@ static int rollout_impl(brov_engine* e, const brov_rollout_desc* d, cudaStream_t
     int Q = d->time_slices;
     if (Q == 0 && can_slice) {
         const int per_sm = rollout_blocks_per_sm<T>(e->model, d->integrator, e->use_lag1 != 0, e->pv != nullptr, gen, d->traj_dev != nullptr,
-                                                     a.c.has_current != 0);
+                                                     a.c.has_current != 0 || !(a.u_vec && d->u_stride_n != 0));
         const long long slots = (long long)per_sm * e->num_sms;
         Q = 1;
         if (slots > 0 && a.nvblocks > slots) {

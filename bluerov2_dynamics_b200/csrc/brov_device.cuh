@@ -542,7 +542,8 @@ __device__ __forceinline__ void project_lag(const Consts<T>& c, const T* __restr
 //           double-integrator models -> accelerations
 // ---------------------------------------------------------------------------------------------------------------
 // CU = false: built for "no ocean current" — the relative-velocity block and its (uniform) branch are not in the code at
-// all.  The branch alone, four times per step, costs the rollout kernels 1-4 % (r02t batch 6).
+// all.  The branch alone, four times per step, costs the rollout kernels 1-4 % (r02t batch 6).  (The rollout kernel's
+// CU = false build also fixes the input layout at compile time, brov_kernels.cuh.)
 template <typename T, int MODEL, bool LAG1, bool LAGW, class P, bool CU = true>
 __device__ __forceinline__ void model_rhs(const Consts<T>& c, const P& p, int substep, const T* __restrict__ x,
                                           const Trig<T>& tr, const T* __restrict__ lag, const T* __restrict__ Fu,

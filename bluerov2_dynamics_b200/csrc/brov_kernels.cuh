@@ -377,7 +377,15 @@ rollout_kernel(const __grid_constant__ RolloutArgs<T> a) {
         T acth;
         if constexpr (PREFETCH) {   // the next step's row is requested between stages 2 and 3 (LateSide)
             const T* nxt = up + (long long)((k + 1 < nsteps) ? (k + 1) : k) * a.u_stride_t;
-            auto pf = [&]() { if (stream) load_u<T, NU, true>(nxt, uvec, un); else load_u<T, NU, false>(nxt, uvec, un); };
+            // CU = false is the build for the common case — no ocean current AND aligned per-vehicle input rows — with
+            // the layout decided at compile time as well: no branch at the prefetch point in the middle of the step
+            // (+1 %, r02t batch 7; not for the fp64 Monte-Carlo kernels, which lose 4 % with it)
+            constexpr bool FASTU = !CU && !(PV && sizeof(T) == 8);
+            auto pf = [&]() {
+                if constexpr (FASTU) load_u<T, NU, true>(nxt, true, un);
+                else if (stream) load_u<T, NU, true>(nxt, uvec, un);
+                else load_u<T, NU, false>(nxt, uvec, un);
+            };
             LateSide<decltype(pf)> late{pf, 1};
             integrate_step<T, MODEL, INTEG, LAG1, decltype(p), decltype(late), CU>(cc, p, x, lag, u, acth, late);
         } else {

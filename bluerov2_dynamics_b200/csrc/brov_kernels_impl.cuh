@@ -44,8 +44,8 @@ static int rollout_occ(bool traj) {
 // runtime -> template dispatch; F is a generic lambda called with std::integral_constant tags
 template <typename T, class F>
 static auto rollout_dispatch(int model, int integ, bool lag1, bool pv, bool gen, bool cur, F&& f) {
-    // CU tag: false = the "no ocean current" build of a streamed-input Fossen kernel (RolloutExists), true = the flag is
-    // read at run time
+    // CU tag: false = the common-case build of a streamed-input Fossen kernel (no ocean current, aligned per-vehicle
+    // input rows: both decided at compile time), true = the general build (flags read at run time); `cur` = general
     auto with_flags = [&](auto M, auto L1) {
         auto with_integ = [&](auto I) {
             auto with_cur = [&](auto PV, auto G) {
@@ -96,7 +96,8 @@ template <typename T>
 cudaError_t launch_rollout(int model, int integ, bool lag1, const RolloutArgs<T>& a, cudaStream_t st) {
     if (a.n <= 0 || a.steps <= 0) return cudaSuccess;
     if (model < MODEL_THRUSTER8 || model > MODEL_DIQ13_U6) return cudaErrorInvalidValue;
-    return rollout_dispatch<T>(model, integ, lag1, a.pv != nullptr, a.gen.on != 0, a.c.has_current != 0,
+    const bool general = a.c.has_current != 0 || !(a.u_vec && a.u_stride_n != 0);
+    return rollout_dispatch<T>(model, integ, lag1, a.pv != nullptr, a.gen.on != 0, general,
                                [&](auto M, auto I, auto L1, auto PV, auto G, auto CU) -> cudaError_t {
         if constexpr (RolloutExists<decltype(M)::value, decltype(PV)::value>::V)
             return rollout_launch<T, decltype(M)::value, decltype(I)::value, decltype(L1)::value, decltype(PV)::value, decltype(G)::value,

@@ -57,7 +57,7 @@ SEED = 1
 FLOP_PER_STEP = {"thruster8": 1756.0, "wrench12": 676.0, "quat13": 805.0}   # SURVEY 8(d), algorithmic
 NOMINAL_TFLOPS = {"f64": 37.2, "f32": 74.4}       # 148 SMs x 64 (128) FMA lanes x 2 x 1.965 GHz
 # executed-instruction evidence from the committed ncu captures (profiles/README.md): share of cycles the FP pipe is busy
-PIPE_ACTIVE = {"rollout_f64": {"value": 0.700, "capture": "profiles/r02w_rollout_raw.csv (sm__pipe_fp64_cycles_active, % of peak sustained active; 0.678 of elapsed)"},
+PIPE_ACTIVE = {"rollout_f64": {"value": 0.715, "capture": "profiles/r02af_rollout_raw.csv (sm__pipe_fp64_cycles_active, % of peak sustained active; 0.694 of elapsed)"},
                "rollout_f32": {"value": 0.72, "capture": "profiles/r01j_rollout_f32_raw.csv"}}
 CFG2 = dict(name="cfg2", model="thruster8", dtype="f64", n_per_gpu=65536, stride=0, chunk=1000, ring=10)
 CFG3 = dict(name="cfg3", model="thruster8", dtype="f32", n_per_gpu=1 << 20, stride=10, chunk=100, ring=8)

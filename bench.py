@@ -16,8 +16,8 @@ recursion), so three ways of feeding them exist and all are timed on the SAME nu
                     41.9 GB, each chunk far larger than L2 and read once per launch), streamed by the kernel;
   roofline.generated  inputs generated inside the kernel (no input array at all);
   e2e               host buffers through brov_rollout_host: every call copies its chunk of inputs host->device from
-                    pinned memory and the final state back (PCIe-bound); e2e.generated: the same call with generated
-                    inputs, where only x0 / lag / generator state cross PCIe.
+                    pinned memory and the final state back (PCIe-bound); e2e.generated: ONE call runs the whole
+                    10,000-step job of configs[1] with generated inputs, only x0 / lag / generator state cross PCIe.
 `roofline` nests the other BASELINE configs so that the driver's record keeps them: fp32 (configs[2], 1,048,576
 vehicles, stride-10 writeback), monte_carlo (configs[3]), rmse (configs[4], NCCL all-reduce for N > 1, both lag
 semantics), default_api (per-thruster lag states returned, the drop-in default).  N > 1: the ensemble is sharded by

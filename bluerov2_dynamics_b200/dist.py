@@ -2,7 +2,7 @@
 
 The path shards without any data-path exchange: vehicles of a rollout and windows of the RMSE evaluator are
 independent, so each rank takes a contiguous index range.  The only collective is the sum of the per-rank squared
-error vectors (<= 4 doubles) of the evaluator."""
+error vectors and health counters (6 doubles) of the evaluator."""
 from __future__ import annotations
 
 import os

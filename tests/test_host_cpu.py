@@ -248,3 +248,44 @@ def test_sim_generator_random_stream_matches_reference(golden):
     scale = np.repeat([0.0005, 0.001, 0.0005, 0.001], 3)
     noisy = golden["simgen_states_true_s10"] + (nz * scale)[::10]
     assert np.allclose(noisy, golden["simgen_states_noisy_s10"], rtol=0, atol=1e-15)
+
+
+def test_window_shards_cover_every_window_once_and_hold_their_rows():
+    """dist.window_shard / window_shard_carry (pure arithmetic): for random series lengths, horizons, world sizes and
+    replay depths the ranks' windows partition 0..T-H-1, every rank holds the rows its windows read (H-row halo) and,
+    in carry mode, the rows its first window's replay reaches back to — the condition brov_multistep_se enforces
+    (`row0 <= max(0, (window0 * H - carry_steps) / H)`)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("brov_dist", os.path.join(ROOT, "bluerov2_dynamics_b200", "dist.py"))
+    D = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(D)
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        T = int(rng.integers(1, 5000))
+        world = int(rng.integers(1, 9))
+        hs = sorted(set(int(h) for h in rng.integers(1, 120, size=int(rng.integers(1, 4)))))
+        depth = int(rng.integers(1, 250))
+        # reset mode: one shard for all horizons (windows counted for the shortest one)
+        nwin = max(T - hs[0], 0)
+        seen = 0
+        for r in range(world):
+            lo, hi, n = D.window_shard(T, hs, r, world)
+            assert n >= 0 and lo == seen if n else True
+            if n:
+                assert hi == min(T, lo + n + hs[-1]) and hi <= T
+                seen = lo + n
+        assert seen == nwin or nwin == 0
+        # carry mode: one shard per horizon
+        for H in hs:
+            nw = max(T - H, 0)
+            nxt = 0
+            for r in range(world):
+                row_lo, row_hi, n, w0 = D.window_shard_carry(T, H, r, world, depth)
+                if not n:
+                    continue
+                assert w0 == nxt
+                nxt = w0 + n
+                assert row_hi == min(T, w0 + n + H) and row_lo <= w0
+                assert row_lo <= max(0, (w0 * H - depth) // H)          # the C ABI's replay-history condition
+                assert row_lo >= 0
+            assert nxt == nw
